@@ -1,0 +1,141 @@
+/*
+ * sn2.h -- C ABI of libsn2_b200.so: the B200 (sm_100a) implementation of the StrataNet2
+ * PointNet++ forward/backward + 2D coverage-projection hot path.
+ *
+ * The reference is pure Python (no FFI of its own).  The interfaces these entry points replace are
+ * the third-party operator calls on the reference hot path and the reference's own projection
+ * functions; each entry cites the call site (file:line under the reference tree) it stands in for.
+ * INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; every buffer is owned by the caller (device memory unless the
+ *     parameter name ends in _host); the library never allocates device memory and never
+ *     synchronises; work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - dense batches: B plots of exactly N points (reference contract, model/point_net2.py:112-116).
+ *   - return value: 0 on success, negative SN2_E* otherwise (sn2_error_string() explains).  Asynchronous
+ *     kernel faults surface at the caller's next synchronisation, as with any CUDA library.
+ *   - stateless and re-entrant per stream; one process per GPU.
+ *   - positions are "pos4": float4 per point (x, y, z, unused) in metres.
+ *   - indices are int32 inside the library (the Python operator wrappers widen to int64).
+ *   - fp32 everywhere; distances are d2 = ((dx*dx + dy*dy) + dz*dz) with each operation rounded
+ *     separately (no FMA contraction) so that index outputs are bit-exact against the CPU oracle.
+ */
+#ifndef SN2_H_
+#define SN2_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SN2_ABI_VERSION 1
+
+enum {
+    SN2_OK = 0,
+    SN2_EINVAL = -1,      /* bad shape / null pointer / unsupported argument */
+    SN2_EUNSUPPORTED = -2, /* valid request outside what this build implements (e.g. N too large) */
+    SN2_ECUDA = -3,       /* a CUDA runtime call or launch failed (cudaGetLastError) */
+};
+
+/* fixed network widths of the reference architecture (model/point_net2.py:78-95) */
+#define SN2_F0 8   /* point features after dropping x,y                    (:77, :118) */
+#define SN2_C1 16  /* SA1 MLP [11,16,16]                                    (:79)       */
+#define SN2_C2 32  /* SA2 MLP [19,32]                                       (:80)       */
+#define SN2_C3 64  /* SA3 MLP [35,64], FP3 MLP [96,64]                      (:81, :88)  */
+#define SN2_CF 34  /* FP2 MLP [80,34], FP1 MLP [42,34]                      (:89-90)    */
+#define SN2_CF_LD 36 /* row stride (floats) of 34-wide feature buffers: 16-byte aligned rows */
+#define SN2_GRID_MAX 64                       /* max cells per axis of the per-plot xy grid */
+#define SN2_GRID_CELLS (SN2_GRID_MAX * SN2_GRID_MAX)
+#define SN2_GRID_HDR 8                        /* floats per plot in the grid header */
+
+int sn2_abi_version(void);
+const char *sn2_error_string(int code);
+/* last CUDA error text recorded by this thread's most recent failing call (never NULL) */
+const char *sn2_last_cuda_error(void);
+
+/* ---- a0-a2: input layout.  Replaces get_long_form + column drop (model/point_net2.py:107-118,
+ * 155-158).  xyz (B,3,N), cloud (B,F,N) fp32 -> pos4 [B*N] float4, feat [B*N, F-2] row-major.
+ * F must be 10 (n_input_feats, config.py:101). */
+int sn2_ingest(const float *xyz, const float *cloud, int B, int N, int F, float *pos4, float *feat,
+               void *stream);
+
+/* ---- a3/a4: farthest point sampling.  Replaces torch_cluster fps (model/point_net2.py:22).
+ * start: [B] local start index per plot, or NULL for 0 (canonical random_start=False).
+ * idx_out [B*M] GLOBAL row indices (b*N + local), pos4_out [B*M] float4 (may be NULL).
+ * Arg-max ties -> lowest index.  M <= N, N <= sn2_fps_max_points(). */
+int sn2_fps_max_points(void);
+int sn2_fps(const float *pos4, int B, int N, int M, const int *start, int *idx_out,
+            float *pos4_out, void *stream);
+
+/* ---- a3/a4: radius ball query.  Replaces torch_cluster radius (model/point_net2.py:23-25).
+ * Step 1: bin the N points of every plot into an xy grid whose cell edge is >= r.
+ *   grid_hdr [B*SN2_GRID_HDR] float, cell_start [B*(SN2_GRID_CELLS+1)] int32,
+ *   sorted4 [B*N] float4 (x, y, z, local index as int bits). */
+int sn2_grid_build(const float *pos4, int B, int N, float r, float *grid_hdr, int *cell_start,
+                   float *sorted4, void *stream);
+/* Step 2: neighbours per query = min(K, #{i in plot : d2(i, q) < r2}); cnt [B*M]. */
+int sn2_ball_count(const float *grid_hdr, const int *cell_start, const float *sorted4,
+                   const float *qpos4, int B, int N, int M, float r2, int K, int *cnt, void *stream);
+/* Step 3: exclusive scan cnt -> rowptr [B*M+1] (int32); scratch [B] int32. */
+int sn2_rowptr_scan(const int *cnt, int B, int M, int *rowptr, int *scratch, void *stream);
+/* Step 4: col[rowptr[q] .. rowptr[q+1]) = the first K in-radius points in ASCENDING GLOBAL INDEX. */
+int sn2_ball_fill(const float *grid_hdr, const int *cell_start, const float *sorted4,
+                  const float *qpos4, int B, int N, int M, float r2, int K, const int *rowptr,
+                  int *col, void *stream);
+
+/* ---- a3/a4/a9: PointConv (eval-mode BN).  Replaces torch_geometric PointConv + scatter max
+ * (model/point_net2.py:19,27).  level 1: feat [*,8] -> MLP[11,16,16] -> out [Q,16];
+ * level 2: feat [*,16] -> MLP[19,32] -> out [Q,32].  w_host: packed weights (see sn2/weights.py),
+ * nw floats, HOST memory (passed to the kernel by value). */
+int sn2_pointconv_fwd(int level, const float *pos4, const float *feat, const float *qpos4,
+                      const int *rowptr, const int *col, int Q, const float *w_host, int nw,
+                      float *out, void *stream);
+
+/* ---- a5: global set abstraction.  Replaces MLP[35,64] + global_max_pool (model/point_net2.py:37-42).
+ * x2 [B*M,32], pos4 [B*M] -> g [B,64]. */
+int sn2_global_sa_fwd(const float *x2, const float *pos4, int B, int M, const float *w_host, int nw,
+                      float *g, void *stream);
+
+/* ---- a6: FP3 (k=1 interpolation from the plot vector + skip + MLP[96,64]); model/point_net2.py:62-67,91.
+ * g [B,64], x2 [B*M,32], pos4 [B*M] -> out [B*M,64]. */
+int sn2_fp3_fwd(const float *g, const float *x2, const float *pos4, int B, int M, const float *w_host,
+                int nw, float *out, void *stream);
+
+/* ---- a7/a8 search part: 3 nearest sources of the same plot per query (torch_cluster knn inside
+ * knn_interpolate, model/point_net2.py:63).  Ties -> lower source index.  Ms >= 3.
+ * nbr [B*Nq,3] int32 GLOBAL source indices (ascending distance), w [B*Nq,3] = 1/max(d2,1e-16). */
+int sn2_knn3(const float *spos4, const float *qpos4, int B, int Ms, int Nq, int *nbr, float *w,
+             void *stream);
+
+/* ---- a7: FP2 = interpolate(f3 [B*Ms,64]) ++ x1 [B*Nq,16] -> MLP[80,34] -> out [B*Nq, SN2_CF_LD]. */
+int sn2_fp2_fwd(const float *f3, const int *nbr, const float *w, const float *x1, int Q,
+                const float *w_host, int nw, float *out, void *stream);
+
+/* ---- a8+a10: FP1 = interpolate(f2 [*,SN2_CF_LD]) ++ feat [Q,8] -> MLP[42,34] -> lin1+ReLU -> lin2 ->
+ * softmax(4) / sigmoid(1) -> cov = proba*density (model/point_net2.py:141-151).
+ * cov, proba: [Q,4] row-major. */
+int sn2_fp1_head_fwd(const float *f2, const int *nbr, const float *w, const float *feat, int Q,
+                     const float *w_host, int nw, float *cov, float *proba, void *stream);
+
+/* ---- a12: plot-wise coverages.  Replaces project_to_plotwise_coverages (model/project_to_2d.py:7-55).
+ * cloud (B,F,N) device (rows 0,1 = normalised x,y), pred [B*N,4].
+ * out [B,4] = [low, 1-low, med, high] mean over occupied pixels.
+ * Optional (NULL to skip): pix [B*N] int32 = px*(D+1) + py (px, py in [0, D]); pmax [B,3,D*D] fp32 (0 where empty);
+ * parg [B,3,D*D] int32 GLOBAL point index of the per-pixel max (first index on ties; -1 empty). */
+int sn2_project_plotwise(const float *cloud, const float *pred, int B, int N, int F, int D, float *out,
+                         int *pix, float *pmax, int *parg, void *stream);
+
+/* ---- a13: rasters.  Replaces project_to_2d_rasters (model/project_to_2d.py:58-113), batched.
+ * cloud (B,F,N); cov element (plot b, point n, channel c) at cov[b*cov_sb + n*cov_sn + c*cov_sc];
+ * rasters [B,3,D,D] float64, NaN where empty, rows flipped (np.flip axis 0); scale = 10*D/diam_meters,
+ * shift = diam_meters // 2.  Optional pix [B*N] int32 = y*D + x (unflipped). */
+int sn2_project_rasters(const float *cloud, const float *cov, long long cov_sb, long long cov_sn,
+                        long long cov_sc, int B, int N, int F, int D, float scale, float shift,
+                        double *rasters, int *pix, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SN2_H_ */

@@ -1,0 +1,253 @@
+"""Host-side wrappers over the C ABI (include/sn2.h).
+
+Two levels:
+  * dense primitives (``ingest``, ``fps_dense``, ``ball_query_dense`` ...) used by the fused forward
+    of ``model.point_net2.PointNet2``: B plots of exactly N points, int32 indices, pos4 positions;
+  * operator-level functions with the upstream names and argument meaning that the reference calls
+    (``fps``, ``radius``, ``knn``, ``global_max_pool``, ``scatter_max`` ... --
+    /root/reference/model/point_net2.py:9, /root/reference/model/project_to_2d.py:4), returning
+    int64 indices in the upstream layout, so parity tests read like calls into the original wheels.
+
+torch is used for device memory and streams only; every computation is a kernel of libsn2_b200.so.
+No CPU path exists: CPU tensors raise RuntimeError.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, dptr, hptr, stream_ptr
+
+GRID_CELLS = 64 * 64
+GRID_HDR = 8
+CF_LD = 36
+
+
+def m_of(n: int, ratio: float) -> int:
+    """Sample count of torch_cluster.fps: ceil(float32(n) * float32(ratio))."""
+    return int(math.ceil(float(np.float32(n) * np.float32(ratio))))
+
+
+def r2_of(r: float) -> float:
+    """Threshold of torch_cluster.radius: r*r in double, rounded to fp32."""
+    return float(np.float32(float(r) * float(r)))
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("sn2: CUDA tensors required (this build has no CPU fallback)")
+    return t.detach().to(torch.float32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# dense primitives
+# ------------------------------------------------------------------------------------------------
+def ingest(xyz: torch.Tensor, cloud: torch.Tensor):
+    """(B,3,N) + (B,10,N) device fp32 -> pos4 (B*N,4), feat (B*N,8)."""
+    lib = _lib.load()
+    B, F, N = cloud.shape
+    pos4 = torch.empty((B * N, 4), dtype=torch.float32, device=cloud.device)
+    feat = torch.empty((B * N, F - 2), dtype=torch.float32, device=cloud.device)
+    check(lib.sn2_ingest(dptr(xyz, torch.float32), dptr(cloud, torch.float32), B, N, F, dptr(pos4), dptr(feat),
+                         stream_ptr()), "sn2_ingest")
+    return pos4, feat
+
+
+def fps_dense(pos4: torch.Tensor, B: int, N: int, M: int, start: torch.Tensor | None = None):
+    """-> idx int32 [B*M] (global rows), pos4_out [B*M,4]."""
+    lib = _lib.load()
+    idx = torch.empty(B * M, dtype=torch.int32, device=pos4.device)
+    out = torch.empty((B * M, 4), dtype=torch.float32, device=pos4.device)
+    check(lib.sn2_fps(dptr(pos4, torch.float32), B, N, M, dptr(start, torch.int32) if start is not None else None,
+                      dptr(idx), dptr(out), stream_ptr()), "sn2_fps")
+    return idx, out
+
+
+def ball_query_dense(pos4: torch.Tensor, qpos4: torch.Tensor, B: int, N: int, M: int, r: float, K: int):
+    """-> rowptr int32 [B*M+1], col int32 [E] (global point rows, ascending inside each query)."""
+    lib = _lib.load()
+    dev = pos4.device
+    hdr = torch.empty(B * GRID_HDR, dtype=torch.float32, device=dev)
+    cell_start = torch.empty(B * (GRID_CELLS + 1), dtype=torch.int32, device=dev)
+    sorted4 = torch.empty((B * N, 4), dtype=torch.float32, device=dev)
+    st = stream_ptr()
+    check(lib.sn2_grid_build(dptr(pos4, torch.float32), B, N, float(r), dptr(hdr), dptr(cell_start), dptr(sorted4), st),
+          "sn2_grid_build")
+    r2 = r2_of(r)
+    cnt = torch.empty(B * M, dtype=torch.int32, device=dev)
+    check(lib.sn2_ball_count(dptr(hdr), dptr(cell_start), dptr(sorted4), dptr(qpos4, torch.float32), B, N, M, r2, int(K),
+                             dptr(cnt), st), "sn2_ball_count")
+    rowptr = torch.empty(B * M + 1, dtype=torch.int32, device=dev)
+    scratch = torch.empty(B, dtype=torch.int32, device=dev)
+    check(lib.sn2_rowptr_scan(dptr(cnt), B, M, dptr(rowptr), dptr(scratch), st), "sn2_rowptr_scan")
+    E = int(rowptr[-1].item())  # the one host sync of the level: sizes the edge list
+    col = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    check(lib.sn2_ball_fill(dptr(hdr), dptr(cell_start), dptr(sorted4), dptr(qpos4), B, N, M, r2, int(K), dptr(rowptr),
+                            dptr(col), st), "sn2_ball_fill")
+    return rowptr, col[:E]
+
+
+def pointconv_fwd(level: int, pos4, feat, qpos4, rowptr, col, w_host: torch.Tensor):
+    lib = _lib.load()
+    Q = qpos4.shape[0]
+    cout = 16 if level == 1 else 32
+    out = torch.empty((Q, cout), dtype=torch.float32, device=pos4.device)
+    check(lib.sn2_pointconv_fwd(level, dptr(pos4, torch.float32), dptr(feat, torch.float32), dptr(qpos4, torch.float32),
+                                dptr(rowptr, torch.int32), dptr(col, torch.int32), Q, hptr(w_host), w_host.numel(),
+                                dptr(out), stream_ptr()), "sn2_pointconv_fwd")
+    return out
+
+
+def global_sa_fwd(x2, pos4, B: int, M: int, w_host):
+    lib = _lib.load()
+    g = torch.empty((B, 64), dtype=torch.float32, device=x2.device)
+    check(lib.sn2_global_sa_fwd(dptr(x2, torch.float32), dptr(pos4, torch.float32), B, M, hptr(w_host), w_host.numel(),
+                                dptr(g), stream_ptr()), "sn2_global_sa_fwd")
+    return g
+
+
+def fp3_fwd(g, x2, pos4, B: int, M: int, w_host):
+    lib = _lib.load()
+    out = torch.empty((B * M, 64), dtype=torch.float32, device=x2.device)
+    check(lib.sn2_fp3_fwd(dptr(g, torch.float32), dptr(x2, torch.float32), dptr(pos4, torch.float32), B, M, hptr(w_host),
+                          w_host.numel(), dptr(out), stream_ptr()), "sn2_fp3_fwd")
+    return out
+
+
+def knn3_dense(spos4, qpos4, B: int, Ms: int, Nq: int):
+    """-> nbr int32 [B*Nq,3] (global source rows, ascending distance), w fp32 [B*Nq,3]."""
+    lib = _lib.load()
+    nbr = torch.empty((B * Nq, 3), dtype=torch.int32, device=spos4.device)
+    w = torch.empty((B * Nq, 3), dtype=torch.float32, device=spos4.device)
+    check(lib.sn2_knn3(dptr(spos4, torch.float32), dptr(qpos4, torch.float32), B, Ms, Nq, dptr(nbr), dptr(w), stream_ptr()),
+          "sn2_knn3")
+    return nbr, w
+
+
+def fp2_fwd(f3, nbr, w, x1, w_host):
+    lib = _lib.load()
+    Q = x1.shape[0]
+    out = torch.empty((Q, CF_LD), dtype=torch.float32, device=x1.device)
+    check(lib.sn2_fp2_fwd(dptr(f3, torch.float32), dptr(nbr, torch.int32), dptr(w, torch.float32), dptr(x1, torch.float32), Q,
+                          hptr(w_host), w_host.numel(), dptr(out), stream_ptr()), "sn2_fp2_fwd")
+    return out
+
+
+def fp1_head_fwd(f2, nbr, w, feat, w_host):
+    lib = _lib.load()
+    Q = feat.shape[0]
+    cov = torch.empty((Q, 4), dtype=torch.float32, device=feat.device)
+    proba = torch.empty((Q, 4), dtype=torch.float32, device=feat.device)
+    check(lib.sn2_fp1_head_fwd(dptr(f2, torch.float32), dptr(nbr, torch.int32), dptr(w, torch.float32),
+                               dptr(feat, torch.float32), Q, hptr(w_host), w_host.numel(), dptr(cov), dptr(proba),
+                               stream_ptr()), "sn2_fp1_head_fwd")
+    return cov, proba
+
+
+def project_plotwise(cloud_dev, pred, D: int, want_aux: bool = False):
+    """cloud (B,F,N) device, pred (B*N,4) -> out (B,4) [+ pix (B*N), pmax (B,3,D,D), parg (B,3,D,D)]."""
+    lib = _lib.load()
+    B, F, N = cloud_dev.shape
+    dev = cloud_dev.device
+    out = torch.empty((B, 4), dtype=torch.float32, device=dev)
+    pix = pmax = parg = None
+    if want_aux:
+        pix = torch.empty(B * N, dtype=torch.int32, device=dev)
+        pmax = torch.empty((B, 3, D, D), dtype=torch.float32, device=dev)
+        parg = torch.empty((B, 3, D, D), dtype=torch.int32, device=dev)
+    check(lib.sn2_project_plotwise(dptr(cloud_dev, torch.float32), dptr(pred, torch.float32), B, N, F, D, dptr(out), dptr(pix),
+                                   dptr(pmax), dptr(parg), stream_ptr()), "sn2_project_plotwise")
+    return (out, pix, pmax, parg) if want_aux else out
+
+
+def project_rasters(cloud_dev, cov, layout: str, D: int, diam_meters: int, want_pix: bool = False):
+    """cloud (B,F,N) device; cov either "point_major" (B*N,4) or "channel_major" (B,4,N).
+    -> rasters float64 (B,3,D,D) [+ pix int32 (B*N) = y*D + x before the flip]."""
+    lib = _lib.load()
+    B, F, N = cloud_dev.shape
+    if layout == "point_major":
+        sb, sn, sc = N * 4, 4, 1
+    elif layout == "channel_major":
+        sb, sn, sc = 4 * N, 1, N
+    else:
+        raise ValueError(layout)
+    dev = cloud_dev.device
+    rasters = torch.empty((B, 3, D, D), dtype=torch.float64, device=dev)
+    pix = torch.empty(B * N, dtype=torch.int32, device=dev) if want_pix else None
+    scale = 10 * (D / diam_meters)          # /root/reference/model/project_to_2d.py:68
+    shift = float(diam_meters // 2)         # :74
+    check(lib.sn2_project_rasters(dptr(cloud_dev, torch.float32), dptr(cov, torch.float32), sb, sn, sc, B, N, F, D,
+                                  float(scale), shift, dptr(rasters), dptr(pix), stream_ptr()), "sn2_project_rasters")
+    return (rasters, pix) if want_pix else rasters
+
+
+# ------------------------------------------------------------------------------------------------
+# operator-level API (upstream names / argument meaning; dense batches only)
+# ------------------------------------------------------------------------------------------------
+def _dense_shape(batch: torch.Tensor | None, n: int) -> tuple[int, int]:
+    """Validate that ``batch`` is B equal, sorted, contiguous segments and return (B, n_per_plot).
+    The hot path is dense by contract (/root/reference/model/point_net2.py:112-116)."""
+    if batch is None:
+        return 1, n
+    if batch.numel() != n:
+        raise RuntimeError("sn2: batch vector length does not match the number of points")
+    B = int(batch[-1].item()) + 1 if n else 0
+    if B == 0 or n % B:
+        raise RuntimeError("sn2: ragged batches are not supported (plots must have equal point counts)")
+    per = n // B
+    expect = torch.arange(B, device=batch.device, dtype=batch.dtype).repeat_interleave(per)
+    if not torch.equal(batch, expect):
+        raise RuntimeError("sn2: batch vector must be sorted with equal-sized plots")
+    return B, per
+
+
+def to_pos4(pos: torch.Tensor) -> torch.Tensor:
+    pos = _f32(pos)
+    if pos.dim() != 2 or pos.shape[1] != 3:
+        raise RuntimeError("sn2: positions must have shape [n, 3]")
+    return torch.nn.functional.pad(pos, (0, 1)).contiguous()
+
+
+def fps(x, batch=None, ratio=0.5, random_start=False, start=None):
+    """Drop-in for torch_cluster/torch_geometric ``fps`` (/root/reference/model/point_net2.py:22).
+    Canonical start = first point of each plot; ``start`` (local index per plot) overrides it;
+    ``random_start=True`` draws it with torch's generator."""
+    B, n = _dense_shape(batch, x.shape[0])
+    M = m_of(n, ratio)
+    st = None
+    if start is not None:
+        st = torch.as_tensor(start, dtype=torch.int32, device=x.device).contiguous()
+    elif random_start:
+        st = torch.randint(0, n, (B,), device=x.device, dtype=torch.int32)
+    idx, _ = fps_dense(to_pos4(x), B, n, M, st)
+    return idx.to(torch.int64)
+
+
+def radius(x, y, r, batch_x=None, batch_y=None, max_num_neighbors=32, num_workers=1):
+    """Drop-in for ``radius`` (/root/reference/model/point_net2.py:23-25): int64 [2,E], row 0 = index into
+    y, row 1 = index into x, grouped by query, ascending x index, strict d2 < fp32(r*r), first K."""
+    B, n = _dense_shape(batch_x, x.shape[0])
+    By, m = _dense_shape(batch_y, y.shape[0])
+    if B != By:
+        raise RuntimeError("sn2: batch_x and batch_y describe different numbers of plots")
+    rowptr, col = ball_query_dense(to_pos4(x), to_pos4(y), B, n, m, float(r), int(max_num_neighbors))
+    cnt = (rowptr[1:] - rowptr[:-1]).to(torch.int64)
+    row = torch.repeat_interleave(torch.arange(B * m, device=x.device, dtype=torch.int64), cnt)
+    return torch.stack([row, col.to(torch.int64)], dim=0)
+
+
+def knn(x, y, k, batch_x=None, batch_y=None, cosine=False, num_workers=1):
+    """Drop-in for ``knn`` with k == 3 (the only k the path searches; k=1 against a single source is a
+    broadcast, see fp3): int64 [2, 3*len(y)], row 0 = y index, row 1 = x index, ascending distance."""
+    if k != 3 or cosine:
+        raise RuntimeError("sn2: knn supports k=3, euclidean")
+    B, ms = _dense_shape(batch_x, x.shape[0])
+    By, nq = _dense_shape(batch_y, y.shape[0])
+    if B != By:
+        raise RuntimeError("sn2: batch_x and batch_y describe different numbers of plots")
+    nbr, _ = knn3_dense(to_pos4(x), to_pos4(y), B, ms, nq)
+    row = torch.arange(B * nq, device=x.device, dtype=torch.int64).repeat_interleave(3)
+    return torch.stack([row, nbr.reshape(-1).to(torch.int64)], dim=0)

@@ -1,0 +1,69 @@
+"""Fused forward of the PointNet++ hot path on one B200 (eval mode).
+
+Replaces the call chain of /root/reference/model/point_net2.py:106-153 (sa1 -> sa2 -> sa3 -> fp3 ->
+fp2 -> fp1 -> head) with 16 kernel launches of libsn2_b200.so on dense [B, N] data.  The only host
+synchronisations are the two edge-count read-backs that size the neighbour lists.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import torch
+
+from . import ops, weights
+
+
+@dataclass
+class ForwardTrace:
+    """Intermediates kept for parity tests (and, later, for the backward pass)."""
+    tensors: dict = field(default_factory=dict)
+
+
+def _packed(model) -> dict:
+    ver = weights.params_version(model)
+    cache = getattr(model, "_sn2_wcache", None)
+    if cache is None or cache[0] != ver:
+        cache = (ver, weights.pack_eval(model))
+        object.__setattr__(model, "_sn2_wcache", cache)
+    return cache[1]
+
+
+def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_neighbors: int = 2000,
+                 trace: ForwardTrace | None = None):
+    """xyz (B,3,N), cloud (B,10,N) fp32 (host or device) -> coverages (B*N,4), proba (B*N,4) on device."""
+    if cloud.dim() != 3 or xyz.dim() != 3 or xyz.shape[1] != 3 or cloud.shape[0] != xyz.shape[0] \
+            or cloud.shape[2] != xyz.shape[2]:
+        raise RuntimeError("PointNet2.forward: expected xyz (B,3,N) and cloud (B,F,N)")
+    B, F, N = cloud.shape
+    if N != model.subsample_size:
+        raise RuntimeError(f"PointNet2.forward: every plot must have subsample_size={model.subsample_size} points, got {N}")
+    W = _packed(model)
+    xyz_d = xyz.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+    cloud_d = cloud.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+    sa1, sa2 = model.sa1_module, model.sa2_module
+
+    pos0, feat0 = ops.ingest(xyz_d, cloud_d)
+    M1 = ops.m_of(N, sa1.ratio)
+    idx1, pos1 = ops.fps_dense(pos0, B, N, M1)
+    rowptr1, col1 = ops.ball_query_dense(pos0, pos1, B, N, M1, sa1.r, max_num_neighbors)
+    x1 = ops.pointconv_fwd(1, pos0, feat0, pos1, rowptr1, col1, W["sa1"])
+
+    M2 = ops.m_of(M1, sa2.ratio)
+    idx2, pos2 = ops.fps_dense(pos1, B, M1, M2)
+    rowptr2, col2 = ops.ball_query_dense(pos1, pos2, B, M1, M2, sa2.r, max_num_neighbors)
+    x2 = ops.pointconv_fwd(2, pos1, x1, pos2, rowptr2, col2, W["sa2"])
+
+    g = ops.global_sa_fwd(x2, pos2, B, M2, W["sa3"])
+    f3 = ops.fp3_fwd(g, x2, pos2, B, M2, W["fp3"])
+    nbr2, w2 = ops.knn3_dense(pos2, pos1, B, M2, M1)
+    f2 = ops.fp2_fwd(f3, nbr2, w2, x1, W["fp2"])
+    nbr1, w1 = ops.knn3_dense(pos1, pos0, B, M1, N)
+    cov, proba = ops.fp1_head_fwd(f2, nbr1, w1, feat0, W["fp1"])
+
+    if trace is not None:
+        trace.tensors.update(
+            cloud_dev=cloud_d, pos0=pos0, feat0=feat0, idx1=idx1, pos1=pos1, rowptr1=rowptr1, col1=col1, x1=x1,
+            idx2=idx2, pos2=pos2, rowptr2=rowptr2, col2=col2, x2=x2, G=g, fp3=f3, nbr2=nbr2, w2=w2, fp2=f2,
+            nbr1=nbr1, w1=w1, M1=M1, M2=M2,
+        )
+    return cov, proba, g, cloud_d

@@ -1,0 +1,196 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via sn2.ops / the drop-in model package)
+against the CPU oracle on the same seeded inputs.  Bit-exact for indices, rtol 1e-3 for fp32 values
+(BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-3, 1e-5  # fp32 tolerance stated by BASELINE.json north_star (rtol) + tiny abs floor
+
+
+def _plots(config, B, N, variant="plain"):
+    from sn2.synth import synth_batch
+
+    return synth_batch(config, B, N, variant)
+
+
+def _long(xyz):  # (B,3,N) -> (B*N,3)
+    return xyz.permute(0, 2, 1).reshape(-1, 3).contiguous()
+
+
+def _batch(B, N):
+    return torch.arange(B, dtype=torch.int64).repeat_interleave(N)
+
+
+@pytest.mark.parametrize("variant", ["plain", "cm", "dup"])
+@pytest.mark.parametrize("N", [300, 1000, 2500, 4096, 10000, 16384])
+def test_fps_bit_exact(cuda_device, N, variant):
+    from oracle import thirdparty_ops as tp
+    from sn2 import ops
+
+    B = 3
+    data = _plots(11, B, N, variant)
+    pos, batch = _long(data["xyz"]), _batch(B, N)
+    want = tp.fps(pos, batch, ratio=0.25)
+    got = ops.fps(pos.to(cuda_device), batch.to(cuda_device), ratio=0.25)
+    assert got.dtype == torch.int64
+    assert torch.equal(got.cpu(), want)
+
+
+def test_fps_known_answers(cuda_device):
+    from oracle import thirdparty_ops as tp
+    from sn2 import ops
+
+    # 4 points on a square: from corner 0 the far corner wins, then an exact tie -> lowest index
+    pos = torch.tensor([[0., 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]])
+    got = ops.fps(pos.to(cuda_device), None, ratio=0.75).cpu()
+    assert got.tolist() == [0, 3, 1]
+    assert torch.equal(got, tp.fps(pos, None, ratio=0.75))
+    # all points identical -> always index 0
+    pos = torch.zeros(64, 3)
+    assert ops.fps(pos.to(cuda_device), None, ratio=0.25).cpu().tolist() == [0] * 16
+    # explicit start
+    pos = _long(_plots(12, 2, 500)["xyz"])
+    b = _batch(2, 500)
+    want = tp.fps(pos, b, ratio=0.1, start=[17, 499])
+    got = ops.fps(pos.to(cuda_device), b.to(cuda_device), ratio=0.1, start=[17, 499]).cpu()
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("N,K,variant", [(2500, 2000, "plain"), (10000, 2000, "cm"), (10000, 64, "plain"),
+                                         (6000, 16, "dup"), (16384, 2000, "plain")])
+def test_radius_bit_exact(cuda_device, N, K, variant):
+    from oracle import thirdparty_ops as tp
+    from sn2 import ops
+
+    B = 2
+    data = _plots(13, B, N, variant)
+    pos, batch = _long(data["xyz"]), _batch(B, N)
+    idx = tp.fps(pos, batch, ratio=0.25)
+    r = float(np.sqrt(2.0))
+    want = tp.radius(pos, pos[idx], r, batch, batch[idx], max_num_neighbors=K)
+    got = ops.radius(pos.to(cuda_device), pos[idx].to(cuda_device), r, batch.to(cuda_device),
+                     batch[idx].to(cuda_device), max_num_neighbors=K).cpu()
+    assert got.shape == want.shape
+    assert torch.equal(got, want)  # same edges in the same (query, ascending index) order
+
+
+def test_radius_boundary_is_strict(cuda_device):
+    from oracle import thirdparty_ops as tp
+    from sn2 import ops
+
+    # d2 == r2 exactly must be excluded (strict '<'); r = 2 -> r2 = 4
+    x = torch.tensor([[0., 0, 0], [2, 0, 0], [1.9999999, 0, 0], [0, 0, 2], [5, 5, 5]])
+    y = torch.tensor([[0., 0, 0]])
+    got = ops.radius(x.to(cuda_device), y.to(cuda_device), 2.0, None, None, max_num_neighbors=10).cpu()
+    assert got[1].tolist() == [0, 2]
+    assert torch.equal(got, tp.radius(x, y, 2.0, None, None, max_num_neighbors=10))
+
+
+@pytest.mark.parametrize("Ms,Nq,variant", [(625, 2500, "plain"), (2500, 10000, "cm"), (1500, 6000, "dup"), (4096, 16384, "plain")])
+def test_knn3_bit_exact(cuda_device, Ms, Nq, variant):
+    from oracle import thirdparty_ops as tp
+    from sn2 import ops
+
+    B = 2
+    data = _plots(14, B, Nq, variant)
+    q = _long(data["xyz"])
+    bq = _batch(B, Nq)
+    src_idx = tp.fps(q, bq, ratio=Ms / Nq)
+    assert src_idx.numel() == B * Ms
+    s, bs = q[src_idx], bq[src_idx]
+    want_idx, want_d2 = tp.knn_raw(s, q, 3, bs, bq)
+    nbr, w = ops.knn3_dense(ops.to_pos4(s.to(cuda_device)), ops.to_pos4(q.to(cuda_device)), B, Ms, Nq)
+    assert torch.equal(nbr.cpu().to(torch.int64), want_idx)
+    want_w = 1.0 / torch.clamp(want_d2, min=1e-16)
+    assert torch.equal(w.cpu(), want_w)
+
+
+def _make_models(N, device):
+    from model.point_net2 import PointNet2
+    from oracle.pointnet2_port import PointNet2Port
+    from sn2.config import default_args
+    from sn2.synth import randomize_bn_
+
+    args = default_args(subsample_size=N, cuda=device.index)
+    torch.manual_seed(0)
+    net = PointNet2(args)
+    randomize_bn_(net)
+    net.eval()
+    port = PointNet2Port(default_args(subsample_size=N))
+    port.load_state_dict({k: v.cpu() for k, v in net.state_dict().items()})
+    port.eval()
+    return args, net, port
+
+
+@pytest.mark.parametrize("B,N,variant", [(1, 10000, "plain"), (3, 4096, "cm"), (2, 16384, "plain"), (2, 10000, "dup")])
+def test_forward_parity(cuda_device, B, N, variant):
+    from sn2.pipeline import ForwardTrace
+
+    args, net, port = _make_models(N, cuda_device)
+    data = _plots(1, B, N, variant)
+    with torch.no_grad():
+        cov_o, proba_o = port(data, trace=True)
+        tr = ForwardTrace()
+        cov, proba = net(data, trace=tr)
+    t, o = tr.tensors, port.trace
+    # bit-exact index outputs
+    assert torch.equal(t["idx1"].cpu().long(), o["sa1_idx"])
+    assert torch.equal(t["col1"].cpu().long(), o["sa1_col"])
+    idx2_global = t["idx2"].cpu().long()
+    assert torch.equal(idx2_global, o["sa2_idx"])
+    assert torch.equal(t["col2"].cpu().long(), o["sa2_col"])
+    # fp32 values
+    for name, got, want in (("x1", t["x1"], o["sa1_x"]), ("x2", t["x2"], o["sa2_x"]), ("G", t["G"], o["G"]),
+                            ("fp3", t["fp3"], o["fp3"]), ("fp2", t["fp2"][:, :34], o["fp2"]),
+                            ("cov", cov, cov_o), ("proba", proba, proba_o)):
+        torch.testing.assert_close(got.cpu(), want, rtol=RTOL, atol=ATOL, msg=lambda m, n=name: f"{n}: {m}")
+    assert cov.shape == (B * N, 4) and cov.is_cuda
+
+
+@pytest.mark.parametrize("B,N", [(1, 10000), (4, 4096)])
+def test_projections_parity(cuda_device, B, N):
+    from model.project_to_2d import project_to_2d_rasters, project_to_plotwise_coverages, project_to_2d_rasters_batched
+    from oracle.pointnet2_port import (plotwise_pixel_ids, project_to_2d_rasters_port,
+                                       project_to_plotwise_coverages_port, raster_pixel_ids)
+    from sn2 import ops
+    from sn2.config import default_args
+
+    args = default_args(subsample_size=N, cuda=cuda_device.index)
+    data = _plots(2, B, N, "cm")
+    g = torch.Generator().manual_seed(5)
+    pred = torch.rand(B * N, 4, generator=g)
+    pred[::7] = pred[1::7][: pred[::7].shape[0]]  # exact duplicates -> arg-max ties
+    want, aux = project_to_plotwise_coverages_port(pred, data["cloud"], args, return_aux=True)
+    got = project_to_plotwise_coverages(pred.to(cuda_device), data["cloud"], args)
+    torch.testing.assert_close(got.cpu(), want, rtol=RTOL, atol=ATOL)
+    # raster cell indices bit-exact + per-pixel max exact + first-index arg-max
+    out, pix, pmax, parg = ops.project_plotwise(data["cloud"].to(cuda_device), pred.to(cuda_device), args.diam_pix, want_aux=True)
+    D = args.diam_pix
+    wpix = plotwise_pixel_ids(data["cloud"], D)
+    assert torch.equal(pix.cpu().view(B, N), (wpix[:, 0] * (D + 1) + wpix[:, 1]).int())
+    for b in range(B):
+        for band, ch in enumerate((0, 2, 3)):
+            vals = pred[b * N:(b + 1) * N, ch]
+            lin = (wpix[b, 0] * D + wpix[b, 1]).long()
+            ref = torch.zeros(D * D).scatter_reduce(0, lin, vals, reduce="amax", include_self=False)
+            assert torch.equal(pmax[b, band].cpu().reshape(-1), ref)
+            arg = parg[b, band].cpu().reshape(-1).long()
+            occ = arg >= 0
+            first = torch.full((D * D,), N, dtype=torch.int64).scatter_reduce(
+                0, lin[vals == ref[lin]], torch.arange(N)[vals == ref[lin]], reduce="amin", include_self=True)
+            assert torch.equal(arg[occ] - b * N, first[occ])
+    # rasters: single-plot drop-in signature and batched form
+    cov_cf = pred.view(B, N, 4).transpose(1, 2).contiguous()  # (B,4,N) as get_batch_format gives
+    rb = project_to_2d_rasters_batched(data["cloud"], pred.to(cuda_device), args).cpu().numpy()
+    for b in range(B):
+        want_r = project_to_2d_rasters_port(data["cloud"][b], cov_cf[b], args)
+        got_r = project_to_2d_rasters(data["cloud"][b], cov_cf[b].to(cuda_device), args)
+        assert got_r.dtype == np.float64 and got_r.shape == (3, D, D)
+        assert np.array_equal(got_r, want_r, equal_nan=True)
+        assert np.array_equal(rb[b], want_r, equal_nan=True)
+    _, rpix = ops.project_rasters(data["cloud"].to(cuda_device), pred.to(cuda_device), "point_major", D, args.diam_meters, want_pix=True)
+    wr = raster_pixel_ids(data["cloud"], D, args.diam_meters)
+    assert torch.equal(rpix.cpu().view(B, N), (wr[:, 1] * D + wr[:, 0]).int())

@@ -1,0 +1,142 @@
+"""CPU tests of the host side: drop-in module layout, checkpoint round trip, weight packing, C-ABI
+exports.  No kernel is launched here (no GPU in this container)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from sn2 import _lib, ops, weights
+from sn2.config import default_args
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_state_dict_is_reference_layout(tmp_path):
+    from model.point_net2 import PointNet2
+    from oracle.pointnet2_port import PointNet2Port
+
+    args = default_args(stats_path=str(tmp_path))
+    net = PointNet2(args)
+    sd = net.state_dict()
+    ref_keys = list(PointNet2Port(args).state_dict().keys())
+    assert list(sd.keys()) == ref_keys and len(sd) == 53
+    assert sum(p.numel() for p in net.parameters()) == 14997
+    # checkpoint round trip through the reference's file naming / dict layout (a14)
+    net.best_metric_epoch, net.best_metric_value = 12, 0.25
+    net.save_state(args)
+    path = os.path.join(str(tmp_path), "PCC_model_full.pt")
+    ck = torch.load(path)
+    assert set(ck) == {"best_metric_epoch", "state_dict", "best_metric_value"}
+    other = PointNet2(args).load_state(path)
+    assert other.best_metric_epoch == 12 and other.best_metric_value == 0.25
+    for k in sd:
+        assert torch.equal(sd[k], other.state_dict()[k])
+    args.current_fold_id = 3
+    net.save_state(args)
+    assert os.path.exists(os.path.join(str(tmp_path), "PCC_model_fold_n=3.pt"))
+    assert torch.equal(net.load_best_state(args).state_dict()["lin2.bias"], sd["lin2.bias"])
+
+
+def test_reference_checkpoint_loads_when_reference_reachable(tmp_path):
+    from oracle.ref_loader import load_reference, reference_root
+
+    if reference_root() is None:
+        pytest.skip("reference files not reachable")
+    from model.point_net2 import PointNet2
+
+    pn2, _ = load_reference()
+    args = default_args(stats_path=str(tmp_path))
+    ref = pn2.PointNet2(args)
+    ref.save_state(args)
+    ours = PointNet2(args).load_best_state(args)
+    for (k1, v1), (k2, v2) in zip(ref.state_dict().items(), ours.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+    ours.save_state(args)
+    ref.load_best_state(args)  # and back
+
+
+def test_early_stopping_bookkeeping(tmp_path):
+    from model.point_net2 import PointNet2
+
+    args = default_args(stats_path=str(tmp_path), patience_in_epochs=2, epoch_to_start_early_stop=3)
+    net = PointNet2(args)
+    assert net.stop_early(1.0, 1, args) is False and net.best_metric_epoch == 1
+    assert net.stop_early(2.0, 2, args) is False          # before epoch_to_start_early_stop
+    assert net.stop_early(2.0, 3, args) is True and net.stopped_early
+    assert net.stop_early(0.5, 4, args) is False and net.best_metric_value == 0.5
+
+
+def test_layout_helpers_roundtrip():
+    from model.point_net2 import PointNet2
+
+    net = PointNet2(default_args(subsample_size=7))
+    data = torch.arange(2 * 3 * 7, dtype=torch.float32).view(2, 3, 7)
+    long = PointNet2.get_long_form(data)
+    assert long.shape == (14, 3) and torch.equal(long[8], data[1, :, 1])
+    assert torch.equal(net.get_batch_format(long), data)
+
+
+def test_forward_fails_loudly_without_cuda():
+    from model.point_net2 import PointNet2
+    from model.project_to_2d import project_to_plotwise_coverages
+
+    net = PointNet2(default_args(subsample_size=16)).eval()
+    data = {"xyz": torch.zeros(1, 3, 16), "cloud": torch.zeros(1, 10, 16)}
+    with pytest.raises(RuntimeError):
+        net(data)
+    with pytest.raises(RuntimeError):
+        project_to_plotwise_coverages(torch.zeros(16, 4), data["cloud"], default_args())
+    with pytest.raises(RuntimeError):
+        ops.fps(torch.zeros(8, 3), None, 0.5)
+
+
+def test_weight_packing_sizes_and_bn_fold():
+    from model.point_net2 import PointNet2
+    from sn2.synth import randomize_bn_
+
+    net = PointNet2(default_args())
+    randomize_bn_(net)
+    packed = weights.pack_eval(net)
+    assert {k: v.numel() for k, v in packed.items()} == weights.EXPECTED_SIZES
+    blk = net.sa2_module.conv.local_nn[0]
+    w = packed["sa2"]
+    assert torch.equal(w[:19 * 32].view(19, 32), blk[0].weight.detach().t())
+    s = w[19 * 32 + 32:19 * 32 + 64]
+    t = w[19 * 32 + 64:]
+    x = torch.rand(5, 32)
+    want = torch.nn.functional.batch_norm(x, blk[2].running_mean, blk[2].running_var, blk[2].weight, blk[2].bias, False)
+    torch.testing.assert_close(x * s + t, want, rtol=1e-5, atol=1e-6)
+    v0 = weights.params_version(net)
+    with torch.no_grad():
+        net.lin1.bias.add_(1.0)
+    assert weights.params_version(net) != v0
+
+
+def test_dense_batch_validation():
+    b = torch.tensor([0, 0, 1, 1])
+    assert ops._dense_shape(b, 4) == (2, 2)
+    with pytest.raises(RuntimeError):
+        ops._dense_shape(torch.tensor([0, 0, 0, 1]), 4)
+    with pytest.raises(RuntimeError):
+        ops._dense_shape(torch.tensor([0, 1, 0, 1]), 4)
+    assert ops.m_of(10000, 0.25) == 2500 and ops.r2_of(np.sqrt(8.0)) == 8.0
+
+
+def test_library_exports_every_declared_symbol():
+    """The .so loads and exports exactly what include/sn2.h declares (no compute call)."""
+    hdr = open(os.path.join(ROOT, "include", "sn2.h")).read()
+    declared = set(re.findall(r"\b(sn2_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    if not os.path.exists(_lib.LIB_PATH):
+        subprocess.check_call(["python", os.path.join(ROOT, "stratanet2-vegetation-coverage-maps_b200", "build.py")])
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    loaded = _lib.load(require_cuda=False)
+    assert loaded.sn2_abi_version() == 1
+    assert b"invalid" in loaded.sn2_error_string(-1)
+    assert loaded.sn2_fps_max_points() >= 16384
