@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the PointNet2 + 2D-projection hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2]
+
+One "step" = one pass of the hot path over one batch of synthetic plots: PointNet2
+eval forward + project_to_plotwise_coverages + project_to_2d_rasters.  Default workload is
+BASELINE.json configs[1]: 64 plots x 16 384 points, fp32, one B200.  With N > 1 (torchrun, one process
+per GPU) every rank runs its own 64 plots (weak scaling, no data-path collective: plots are
+independent); value = plots of all ranks / max-over-ranks time.
+
+Prints ONE JSON line (rank 0).  ``value``: inputs resident in HBM.  ``e2e``: the same step through the
+public drop-in API (``model.point_net2.PointNet2.forward`` + ``model.project_to_2d``) from pinned HOST
+buffers with the result read back to the host inside the timed region.  ``roofline``: the dominant
+kernel, timed live with CUDA events in the same timed region.  ``cpu_baseline``: the CPU oracle (the
+reference's own model files on restated third-party ops when staged, else the port) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "stratanet2-vegetation-coverage-maps_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CONFIGS = {
+    1: dict(B=1, N=10000, name="config1: 1 plot x 10k pts, eval fwd + both projections"),
+    2: dict(B=64, N=16384, name="config2: batched inference 64 plots x 16384 pts, fp32, eval fwd + both projections"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_model(N, device_index):
+    from model.point_net2 import PointNet2
+    from sn2.config import default_args
+    from sn2.synth import randomize_bn_
+
+    args = default_args(subsample_size=N, cuda=device_index)
+    torch.manual_seed(0)
+    net = PointNet2(args)
+    randomize_bn_(net)
+    net.eval()
+    return args, net
+
+
+def cpu_model(N, state_dict=None):
+    """-> (kind, forward_fn(data) -> (cov, proba), plotwise_fn, raster_fn, args)."""
+    from oracle import thirdparty_ops as tp  # noqa: F401  (the oracle is the CPU arm being timed)
+    from oracle.pointnet2_port import PointNet2Port, project_to_2d_rasters_port, project_to_plotwise_coverages_port
+    from oracle.ref_loader import load_reference, reference_root
+    from sn2.config import default_args
+    from sn2.synth import randomize_bn_
+
+    args = default_args(subsample_size=N)
+    torch.manual_seed(0)
+    if reference_root() is not None:
+        pn2, p2d = load_reference()
+        net = pn2.PointNet2(args)
+        kind = "reference"
+        plotwise, raster = p2d.project_to_plotwise_coverages, p2d.project_to_2d_rasters
+    else:
+        net = PointNet2Port(args)
+        kind = "port"
+        plotwise, raster = project_to_plotwise_coverages_port, project_to_2d_rasters_port
+    randomize_bn_(net)
+    if state_dict is not None:
+        net.load_state_dict(state_dict)
+    net.eval()
+    return kind, net, plotwise, raster, args
+
+
+def cpu_step(net, plotwise, raster, args, data):
+    with torch.no_grad():
+        cov, proba = net(data)
+        pw = plotwise(cov, data["cloud"], args)
+        B, _, N = data["cloud"].shape
+        cov_b = cov.view(B, N, 4).transpose(1, 2)
+        rasters = [raster(data["cloud"][b], cov_b[b], args) for b in range(B)]
+    return pw, rasters
+
+
+def time_cpu(N, config_id, plots, repeats):
+    from sn2.synth import synth_batch
+
+    torch.set_num_threads(os.cpu_count())
+    kind, net, plotwise, raster, args = cpu_model(N)
+    data = synth_batch(config_id, plots, N)
+    cpu_step(net, plotwise, raster, args, data)  # warm-up
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        cpu_step(net, plotwise, raster, args, data)
+        best = min(best, time.perf_counter() - t0)
+    return kind, plots / best, best
+
+
+def run_reference(opts, cfg):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from sn2.synth import synth_batch
+
+    N = cfg["N"]
+    plots = 2  # bounded sample: each step = 2 plots of the same workload
+    torch.set_num_threads(os.cpu_count())
+    kind, net, plotwise, raster, args = cpu_model(N)
+    data = synth_batch(opts.config, plots, N)
+    for _ in range(max(1, min(opts.warmup, 1))):
+        cpu_step(net, plotwise, raster, args, data)
+    t0 = time.perf_counter()
+    for _ in range(opts.steps):
+        cpu_step(net, plotwise, raster, args, data)
+    dt = time.perf_counter() - t0
+    value = plots * opts.steps / dt
+    sample = f"{plots} plots x {N} pts per step (bounded sample of {cfg['name']})"
+    print(json.dumps({
+        "impl": "reference", "metric": "plots/sec (PointNet2 eval forward + project_to_2d)", "value": value, "unit": "plots/s",
+        "n_gpus": opts.gpus, "steps": opts.steps, "warmup": opts.warmup, "ms_per_step": 1e3 * dt / opts.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["name"], "plots_per_step": plots, "points_per_plot": N},
+        "points_per_s": value * N,
+        "cpu_baseline": {"value": value, "unit": "plots/s", "cores": os.cpu_count(), "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "plots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    opts = ap.parse_args()
+    cfg = CONFIGS[opts.config]
+    if opts.impl == "reference":
+        return run_reference(opts, cfg)
+
+    import torch.distributed as dist
+    from model.project_to_2d import project_to_2d_rasters_batched, project_to_plotwise_coverages
+    from sn2 import ops
+    from sn2.pipeline import StageTimer, forward_eval
+    from sn2.synth import synth_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, N = cfg["B"], cfg["N"]
+    W = max(opts.warmup, 3)
+    args, net = make_model(N, local)
+    data = synth_batch(opts.config, B, N, first_plot=rank * B)  # every rank its own plots
+    host = {k: v.pin_memory() for k, v in data.items()}
+    dev_in = {k: v.to(dev) for k, v in data.items()}
+    D = args.diam_pix
+    pw_host = torch.empty((B, 4), dtype=torch.float32).pin_memory()
+    rs_host = torch.empty((B, 3, D, D), dtype=torch.float64).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_resident(timer=None):
+        cov, proba, g, cloud_d = forward_eval(net, dev_in["xyz"], dev_in["cloud"], dev, 2000, None, timer)
+        T = timer.stage if timer is not None else None
+        if T:
+            with T("project_plotwise"):
+                pw = ops.project_plotwise(cloud_d, cov, D)
+            with T("project_rasters"):
+                rs = ops.project_rasters(cloud_d, cov, "point_major", D, args.diam_meters)
+        else:
+            pw = ops.project_plotwise(cloud_d, cov, D)
+            rs = ops.project_rasters(cloud_d, cov, "point_major", D, args.diam_meters)
+        return pw, rs
+
+    def step_e2e():
+        with torch.no_grad():
+            cov, proba = net(host)                                             # H2D of xyz + cloud inside
+            pw = project_to_plotwise_coverages(cov, net.last_cloud_device, args)
+            rs = project_to_2d_rasters_batched(net.last_cloud_device, cov, args)
+        pw_host.copy_(pw, non_blocking=True)                                   # D2H of the step's results
+        rs_host.copy_(rs, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, with_timer):
+        timer = StageTimer() if with_timer else None
+        evs = []
+        barrier()
+        for _ in range(steps):
+            flush.fill_(1)  # L2 flush between timed iterations (outside the event pair)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(timer) if with_timer else fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        return total_ms, timer
+
+    with torch.no_grad():
+        for _ in range(W):
+            step_resident()
+            step_e2e()
+        sampler = ClockSampler(local)
+        sampler.start()
+        l0 = ops.LAUNCHES
+        ms_res, timer = timed(step_resident, opts.steps, True)
+        launches = ops.LAUNCHES - l0
+        ms_e2e, _ = timed(step_e2e, opts.steps, False)
+        clocks = sampler.stop()
+
+    t = torch.tensor([ms_res, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_res, ms_e2e = float(t[0]), float(t[1])
+    plots_total = B * world * opts.steps
+    value = plots_total / (ms_res / 1e3)
+    e2e_value = plots_total / (ms_e2e / 1e3)
+
+    # roofline of the dominant kernel (largest share of the resident step), live CUDA-event time
+    stages = timer.totals_ms()
+    per_step = {k: v / opts.steps for k, v in stages.items()}
+    dom = max(per_step, key=per_step.get)
+    M1, M2 = ops.m_of(N, args.ratio1), ops.m_of(ops.m_of(N, args.ratio1), args.ratio2)
+    alg_bytes = {  # SURVEY.md §8d algorithmic bytes per plot, x B plots per launch
+        "fps1": 12 * N + 4 * M1, "fps2": 12 * M1 + 4 * M2,
+        "knn1": 12 * (N + M1) + 24 * N, "knn2": 12 * (M1 + M2) + 24 * M1,
+        "fp1_head": 4 * 34 * M1 + 4 * 8 * N + 24 * N + 2 * 16 * N,
+        "ingest": 4 * 13 * N + 4 * 12 * N,
+    }
+    hbm_peak, peak_src = peaks()
+    roof = None
+    if dom in alg_bytes:
+        ach = alg_bytes[dom] * B / (per_step[dom] / 1e3) / 1e9
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "ms_per_launch": per_step[dom],
+                "algorithmic_bytes_per_launch": alg_bytes[dom] * B}
+        if dom.startswith("fps"):
+            n, m = (N, M1) if dom == "fps1" else (M1, M2)
+            evals = float(n) * m * B
+            roof["note"] = ("FPS is a serial chain of M dependent arg-max iterations per plot: latency/SIMT bound, not HBM bound; "
+                            "on-chip model below")
+            roof["fps_distance_evals_per_s"] = evals / (per_step[dom] / 1e3)
+            roof["fps_ns_per_iteration"] = per_step[dom] * 1e6 / m
+
+    out = {
+        "metric": "plots/sec (PointNet2 eval forward + project_to_2d)", "value": value, "unit": "plots/s",
+        "n_gpus": world, "steps": opts.steps, "warmup": W, "ms_per_step": ms_res / opts.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["name"], "plots_per_gpu_per_step": B, "points_per_plot": N, "max_num_neighbors": 2000,
+                   "l2": "flushed between timed steps (256 MiB write outside the event pairs)", "parallelism": f"plot-sharded x{world}"},
+        "points_per_s": value * N,
+        "e2e": {"value": e2e_value, "unit": "plots/s", "ms_per_step": ms_e2e / opts.steps,
+                "h2d_bytes_per_step": int(sum(v.numel() * 4 for v in host.values())),
+                "d2h_bytes_per_step": int(pw_host.numel() * 4 + rs_host.numel() * 8),
+                "api": "model.point_net2.PointNet2.forward + model.project_to_2d (pinned host in, host out)"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "stage_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
+        "roofline": roof,
+    }
+    if rank == 0 and world == 1 and not opts.no_cpu_baseline:
+        sample_plots = 2
+        kind, v, best = time_cpu(N, opts.config, sample_plots, repeats=2)
+        out["cpu_baseline"] = {"value": v, "unit": "plots/s", "cores": os.cpu_count(), "kind": kind,
+                               "sample": f"{sample_plots} plots x {N} pts, best of 2 after 1 warm-up ({best:.2f} s); "
+                                         "reference model files verbatim on restated third-party ops" if kind == "reference"
+                               else f"{sample_plots} plots x {N} pts, best of 2 after 1 warm-up ({best:.2f} s); oracle port"}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

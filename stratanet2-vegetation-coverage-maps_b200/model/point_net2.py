@@ -103,7 +103,7 @@ class PointNet2(nn.Module):
             self.cuda(self.cuda_device)
 
     # ---------------------------------------------------------------------------------------
-    def forward(self, cloud_data, trace=None):
+    def forward(self, cloud_data, trace=None, timer=None):
         """cloud_data: {"xyz": (B,3,N), "cloud": (B,10,N)} fp32 -> (coverages_pointwise, proba_pointwise),
         both (B*N,4) on the device, plot-major (reference :106-153)."""
         if self.cuda_device is None:
@@ -115,7 +115,7 @@ class PointNet2(nn.Module):
         device = torch.device("cuda", self.cuda_device)
         with torch.cuda.device(device):
             cov, proba, g, cloud_dev = _pipeline.forward_eval(
-                self, cloud_data["xyz"], cloud_data["cloud"], device, SAModule.max_num_neighbors, trace)
+                self, cloud_data["xyz"], cloud_data["cloud"], device, SAModule.max_num_neighbors, trace, timer)
         if self.log_embeddings:
             self.last_G_tensor = g
         # device copy of the normalised cloud, reused by model.project_to_2d to skip a second H2D

@@ -21,6 +21,14 @@ import torch
 from . import _lib
 from ._lib import check, dptr, hptr, stream_ptr
 
+LAUNCHES = 0  # kernels of libsn2_b200.so enqueued by this process (bench.py reports the delta)
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
 GRID_CELLS = 64 * 64
 GRID_HDR = 8
 CF_LD = 36
@@ -53,6 +61,7 @@ def ingest(xyz: torch.Tensor, cloud: torch.Tensor):
     feat = torch.empty((B * N, F - 2), dtype=torch.float32, device=cloud.device)
     check(lib.sn2_ingest(dptr(xyz, torch.float32), dptr(cloud, torch.float32), B, N, F, dptr(pos4), dptr(feat),
                          stream_ptr()), "sn2_ingest")
+    _count(1)
     return pos4, feat
 
 
@@ -63,6 +72,7 @@ def fps_dense(pos4: torch.Tensor, B: int, N: int, M: int, start: torch.Tensor | 
     out = torch.empty((B * M, 4), dtype=torch.float32, device=pos4.device)
     check(lib.sn2_fps(dptr(pos4, torch.float32), B, N, M, dptr(start, torch.int32) if start is not None else None,
                       dptr(idx), dptr(out), stream_ptr()), "sn2_fps")
+    _count(1)
     return idx, out
 
 
@@ -76,17 +86,21 @@ def ball_query_dense(pos4: torch.Tensor, qpos4: torch.Tensor, B: int, N: int, M:
     st = stream_ptr()
     check(lib.sn2_grid_build(dptr(pos4, torch.float32), B, N, float(r), dptr(hdr), dptr(cell_start), dptr(sorted4), st),
           "sn2_grid_build")
+    _count(1)
     r2 = r2_of(r)
     cnt = torch.empty(B * M, dtype=torch.int32, device=dev)
     check(lib.sn2_ball_count(dptr(hdr), dptr(cell_start), dptr(sorted4), dptr(qpos4, torch.float32), B, N, M, r2, int(K),
                              dptr(cnt), st), "sn2_ball_count")
+    _count(1)
     rowptr = torch.empty(B * M + 1, dtype=torch.int32, device=dev)
     scratch = torch.empty(B, dtype=torch.int32, device=dev)
     check(lib.sn2_rowptr_scan(dptr(cnt), B, M, dptr(rowptr), dptr(scratch), st), "sn2_rowptr_scan")
+    _count(2)
     E = int(rowptr[-1].item())  # the one host sync of the level: sizes the edge list
     col = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
     check(lib.sn2_ball_fill(dptr(hdr), dptr(cell_start), dptr(sorted4), dptr(qpos4), B, N, M, r2, int(K), dptr(rowptr),
                             dptr(col), st), "sn2_ball_fill")
+    _count(1)
     return rowptr, col[:E]
 
 
@@ -98,6 +112,7 @@ def pointconv_fwd(level: int, pos4, feat, qpos4, rowptr, col, w_host: torch.Tens
     check(lib.sn2_pointconv_fwd(level, dptr(pos4, torch.float32), dptr(feat, torch.float32), dptr(qpos4, torch.float32),
                                 dptr(rowptr, torch.int32), dptr(col, torch.int32), Q, hptr(w_host), w_host.numel(),
                                 dptr(out), stream_ptr()), "sn2_pointconv_fwd")
+    _count(1)
     return out
 
 
@@ -106,6 +121,7 @@ def global_sa_fwd(x2, pos4, B: int, M: int, w_host):
     g = torch.empty((B, 64), dtype=torch.float32, device=x2.device)
     check(lib.sn2_global_sa_fwd(dptr(x2, torch.float32), dptr(pos4, torch.float32), B, M, hptr(w_host), w_host.numel(),
                                 dptr(g), stream_ptr()), "sn2_global_sa_fwd")
+    _count(1)
     return g
 
 
@@ -114,6 +130,7 @@ def fp3_fwd(g, x2, pos4, B: int, M: int, w_host):
     out = torch.empty((B * M, 64), dtype=torch.float32, device=x2.device)
     check(lib.sn2_fp3_fwd(dptr(g, torch.float32), dptr(x2, torch.float32), dptr(pos4, torch.float32), B, M, hptr(w_host),
                           w_host.numel(), dptr(out), stream_ptr()), "sn2_fp3_fwd")
+    _count(1)
     return out
 
 
@@ -124,6 +141,7 @@ def knn3_dense(spos4, qpos4, B: int, Ms: int, Nq: int):
     w = torch.empty((B * Nq, 3), dtype=torch.float32, device=spos4.device)
     check(lib.sn2_knn3(dptr(spos4, torch.float32), dptr(qpos4, torch.float32), B, Ms, Nq, dptr(nbr), dptr(w), stream_ptr()),
           "sn2_knn3")
+    _count(1)
     return nbr, w
 
 
@@ -133,6 +151,7 @@ def fp2_fwd(f3, nbr, w, x1, w_host):
     out = torch.empty((Q, CF_LD), dtype=torch.float32, device=x1.device)
     check(lib.sn2_fp2_fwd(dptr(f3, torch.float32), dptr(nbr, torch.int32), dptr(w, torch.float32), dptr(x1, torch.float32), Q,
                           hptr(w_host), w_host.numel(), dptr(out), stream_ptr()), "sn2_fp2_fwd")
+    _count(1)
     return out
 
 
@@ -144,6 +163,7 @@ def fp1_head_fwd(f2, nbr, w, feat, w_host):
     check(lib.sn2_fp1_head_fwd(dptr(f2, torch.float32), dptr(nbr, torch.int32), dptr(w, torch.float32),
                                dptr(feat, torch.float32), Q, hptr(w_host), w_host.numel(), dptr(cov), dptr(proba),
                                stream_ptr()), "sn2_fp1_head_fwd")
+    _count(1)
     return cov, proba
 
 
@@ -160,6 +180,7 @@ def project_plotwise(cloud_dev, pred, D: int, want_aux: bool = False):
         parg = torch.empty((B, 3, D, D), dtype=torch.int32, device=dev)
     check(lib.sn2_project_plotwise(dptr(cloud_dev, torch.float32), dptr(pred, torch.float32), B, N, F, D, dptr(out), dptr(pix),
                                    dptr(pmax), dptr(parg), stream_ptr()), "sn2_project_plotwise")
+    _count(1)
     return (out, pix, pmax, parg) if want_aux else out
 
 
@@ -181,6 +202,7 @@ def project_rasters(cloud_dev, cov, layout: str, D: int, diam_meters: int, want_
     shift = float(diam_meters // 2)         # :74
     check(lib.sn2_project_rasters(dptr(cloud_dev, torch.float32), dptr(cov, torch.float32), sb, sn, sc, B, N, F, D,
                                   float(scale), shift, dptr(rasters), dptr(pix), stream_ptr()), "sn2_project_rasters")
+    _count(1)
     return (rasters, pix) if want_pix else rasters
 
 

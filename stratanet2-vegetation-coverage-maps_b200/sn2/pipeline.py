@@ -13,6 +13,51 @@ import torch
 from . import ops, weights
 
 
+class StageTimer:
+    """Optional per-stage CUDA-event timing on the current stream (bench.py's live roofline numbers).
+    Recording an event pair costs a few microseconds and adds no synchronisation."""
+
+    def __init__(self):
+        self.events = []  # (stage, start, end)
+
+    def stage(self, name):
+        return _Stage(self, name)
+
+    def totals_ms(self):
+        out = {}
+        for name, a, b in self.events:
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+
+class _Stage:
+    def __init__(self, timer, name):
+        self.timer, self.name = timer, name
+
+    def __enter__(self):
+        self.a = torch.cuda.Event(enable_timing=True)
+        self.b = torch.cuda.Event(enable_timing=True)
+        self.a.record()
+
+    def __exit__(self, *exc):
+        self.b.record()
+        self.timer.events.append((self.name, self.a, self.b))
+
+
+class _NoTimer:
+    def stage(self, name):
+        return self
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NOTIMER = _NoTimer()
+
+
 @dataclass
 class ForwardTrace:
     """Intermediates kept for parity tests (and, later, for the backward pass)."""
@@ -29,7 +74,7 @@ def _packed(model) -> dict:
 
 
 def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_neighbors: int = 2000,
-                 trace: ForwardTrace | None = None):
+                 trace: ForwardTrace | None = None, timer=None):
     """xyz (B,3,N), cloud (B,10,N) fp32 (host or device) -> coverages (B*N,4), proba (B*N,4) on device."""
     if cloud.dim() != 3 or xyz.dim() != 3 or xyz.shape[1] != 3 or cloud.shape[0] != xyz.shape[0] \
             or cloud.shape[2] != xyz.shape[2]:
@@ -42,23 +87,37 @@ def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_
     cloud_d = cloud.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
     sa1, sa2 = model.sa1_module, model.sa2_module
 
-    pos0, feat0 = ops.ingest(xyz_d, cloud_d)
+    T = timer if timer is not None else _NOTIMER
+    with T.stage("ingest"):
+        pos0, feat0 = ops.ingest(xyz_d, cloud_d)
     M1 = ops.m_of(N, sa1.ratio)
-    idx1, pos1 = ops.fps_dense(pos0, B, N, M1)
-    rowptr1, col1 = ops.ball_query_dense(pos0, pos1, B, N, M1, sa1.r, max_num_neighbors)
-    x1 = ops.pointconv_fwd(1, pos0, feat0, pos1, rowptr1, col1, W["sa1"])
+    with T.stage("fps1"):
+        idx1, pos1 = ops.fps_dense(pos0, B, N, M1)
+    with T.stage("ball1"):
+        rowptr1, col1 = ops.ball_query_dense(pos0, pos1, B, N, M1, sa1.r, max_num_neighbors)
+    with T.stage("pointconv1"):
+        x1 = ops.pointconv_fwd(1, pos0, feat0, pos1, rowptr1, col1, W["sa1"])
 
     M2 = ops.m_of(M1, sa2.ratio)
-    idx2, pos2 = ops.fps_dense(pos1, B, M1, M2)
-    rowptr2, col2 = ops.ball_query_dense(pos1, pos2, B, M1, M2, sa2.r, max_num_neighbors)
-    x2 = ops.pointconv_fwd(2, pos1, x1, pos2, rowptr2, col2, W["sa2"])
+    with T.stage("fps2"):
+        idx2, pos2 = ops.fps_dense(pos1, B, M1, M2)
+    with T.stage("ball2"):
+        rowptr2, col2 = ops.ball_query_dense(pos1, pos2, B, M1, M2, sa2.r, max_num_neighbors)
+    with T.stage("pointconv2"):
+        x2 = ops.pointconv_fwd(2, pos1, x1, pos2, rowptr2, col2, W["sa2"])
 
-    g = ops.global_sa_fwd(x2, pos2, B, M2, W["sa3"])
-    f3 = ops.fp3_fwd(g, x2, pos2, B, M2, W["fp3"])
-    nbr2, w2 = ops.knn3_dense(pos2, pos1, B, M2, M1)
-    f2 = ops.fp2_fwd(f3, nbr2, w2, x1, W["fp2"])
-    nbr1, w1 = ops.knn3_dense(pos1, pos0, B, M1, N)
-    cov, proba = ops.fp1_head_fwd(f2, nbr1, w1, feat0, W["fp1"])
+    with T.stage("global_sa"):
+        g = ops.global_sa_fwd(x2, pos2, B, M2, W["sa3"])
+    with T.stage("fp3"):
+        f3 = ops.fp3_fwd(g, x2, pos2, B, M2, W["fp3"])
+    with T.stage("knn2"):
+        nbr2, w2 = ops.knn3_dense(pos2, pos1, B, M2, M1)
+    with T.stage("fp2"):
+        f2 = ops.fp2_fwd(f3, nbr2, w2, x1, W["fp2"])
+    with T.stage("knn1"):
+        nbr1, w1 = ops.knn3_dense(pos1, pos0, B, M1, N)
+    with T.stage("fp1_head"):
+        cov, proba = ops.fp1_head_fwd(f2, nbr1, w1, feat0, W["fp1"])
 
     if trace is not None:
         trace.tensors.update(

@@ -21,9 +21,12 @@ def test_fps_c_matches_numpy_and_batches():
     pos = torch.round(pos * 20) / 20  # quantised -> many exact ties
     batch = torch.arange(3).repeat_interleave(400)
     got = tp.fps(pos, batch, ratio=0.3)
+    m = m_of(400, 0.3)
+    assert m == 121  # float32(400) * float32(0.3) = 120.000005 -> ceil: the fp32 count rule of A1
+    assert got.numel() == 3 * m
     for b in range(3):
-        want = tp.fps_slow(pos[b * 400:(b + 1) * 400].numpy(), 120) + b * 400
-        assert np.array_equal(got[b * 120:(b + 1) * 120].numpy(), want)
+        want = tp.fps_slow(pos[b * 400:(b + 1) * 400].numpy(), m) + b * 400
+        assert np.array_equal(got[b * m:(b + 1) * m].numpy(), want)
     got = tp.fps(pos[:400], None, ratio=0.1, start=[7])
     assert np.array_equal(got.numpy(), tp.fps_slow(pos[:400].numpy(), 40, start=7))
 
