@@ -68,6 +68,12 @@ int sn2_ingest(const float *xyz, const float *cloud, int B, int N, int F, float 
 int sn2_fps_max_points(void);
 int sn2_fps(const float *pos4, int B, int N, int M, const int *start, int *idx_out,
             float *pos4_out, void *stream);
+/* Same contract with an explicit algorithm: both produce identical indices.
+ * BRUTE: every point updated every iteration; BUCKETED: Morton-sorted 64-point buckets with exact
+ * bounding-box pruning (csrc/fps.cu); AUTO picks BUCKETED for N >= 1024. */
+enum { SN2_FPS_AUTO = 0, SN2_FPS_BRUTE = 1, SN2_FPS_BUCKETED = 2 /* 8 warps */, SN2_FPS_BUCKETED16 = 3 /* 16 warps */ };
+int sn2_fps_algo(const float *pos4, int B, int N, int M, const int *start, int *idx_out,
+                 float *pos4_out, int algo, void *stream);
 
 /* ---- a3/a4: radius ball query.  Replaces torch_cluster radius (model/point_net2.py:23-25).
  * Step 1: bin the N points of every plot into an xy grid whose cell edge is >= r.
@@ -75,6 +81,7 @@ int sn2_fps(const float *pos4, int B, int N, int M, const int *start, int *idx_o
  *   sorted4 [B*N] float4 (x, y, z, local index as int bits). */
 int sn2_grid_build(const float *pos4, int B, int N, float r, float *grid_hdr, int *cell_start,
                    float *sorted4, void *stream);
+/* r < 0 selects an automatic cell edge for about -r points per cell (used by sn2_knn3_grid). */
 /* Step 2: neighbours per query = min(K, #{i in plot : d2(i, q) < r2}); cnt [B*M]. */
 int sn2_ball_count(const float *grid_hdr, const int *cell_start, const float *sorted4,
                    const float *qpos4, int B, int N, int M, float r2, int K, int *cnt, void *stream);
@@ -108,6 +115,11 @@ int sn2_fp3_fwd(const float *g, const float *x2, const float *pos4, int B, int M
  * nbr [B*Nq,3] int32 GLOBAL source indices (ascending distance), w [B*Nq,3] = 1/max(d2,1e-16). */
 int sn2_knn3(const float *spos4, const float *qpos4, int B, int Ms, int Nq, int *nbr, float *w,
              void *stream);
+
+/* Same result from the xy grid of the SOURCES (sn2_grid_build(spos4, B, Ms, r = -3.0f, ...)): ring search
+ * with an exact termination bound, ~100x fewer distance evaluations than the scan above. */
+int sn2_knn3_grid(const float *grid_hdr, const int *cell_start, const float *sorted4, const float *qpos4,
+                  int B, int Ms, int Nq, int *nbr, float *w, void *stream);
 
 /* ---- a7: FP2 = interpolate(f3 [B*Ms,64]) ++ x1 [B*Nq,16] -> MLP[80,34] -> out [B*Nq, SN2_CF_LD]. */
 int sn2_fp2_fwd(const float *f3, const int *nbr, const float *w, const float *x1, int Q,

@@ -62,7 +62,10 @@ grid_build_kernel(const float4 *__restrict__ pos, int N, float r, float *__restr
         mxy = warp_max(red[3][lane]);
         if (lane == 0) {
             float ext = fmaxf(mxx - mnx, mxy - mny);
-            float cs = fmaxf(r * 1.0001f, ext / (float)(SN2_GRID_MAX - 1));
+            // r > 0: cell edge just above r (3x3 search is exhaustive for radius r);
+            // r < 0: auto edge for ~(-r) points per cell (k-NN ring search, csrc/knn.cu)
+            float want = r > 0.f ? r * 1.0001f : sqrtf(fmaxf((mxx - mnx) * (mxy - mny) * (-r) / (float)N, 0.f));
+            float cs = fmaxf(want, ext / (float)(SN2_GRID_MAX - 1));
             cs = fmaxf(cs, 1e-20f);
             float inv = 1.0f / cs;
             int gx = min(SN2_GRID_MAX, (int)floorf((mxx - mnx) * inv) + 1);
@@ -291,7 +294,7 @@ ball_fill_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cel
 extern "C" int sn2_grid_build(const float *pos4, int B, int N, float r, float *grid_hdr, int *cell_start,
                               float *sorted4, void *stream)
 {
-    if (!pos4 || !grid_hdr || !cell_start || !sorted4 || B <= 0 || N <= 0 || !(r > 0.f)) return SN2_EINVAL;
+    if (!pos4 || !grid_hdr || !cell_start || !sorted4 || B <= 0 || N <= 0 || !(r != 0.f)) return SN2_EINVAL;
     sn2::grid_build_kernel<<<B, sn2::GB_THREADS, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4 *>(pos4), N, r, grid_hdr, cell_start, reinterpret_cast<float4 *>(sorted4));
     SN2_LAUNCH_CHECK("grid_build_kernel");

@@ -117,6 +117,297 @@ fps_kernel(const float4 *__restrict__ pos, int N, int M, const int *__restrict__
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Bucketed exact FPS.  Same result as the brute-force kernel above (same fp32 distances, same
+// lowest-index tie rule), far fewer distance evaluations and a short dependent chain per sample:
+//   * prologue: points are sorted by a 30-bit Morton code (bitonic sort in shared memory) and cut into
+//     buckets of 64 consecutive points with tight bounding boxes.
+//   * iteration: a bucket whose box is at fp32 distance lb >= its current max cannot change (every
+//     point i has dist[i] <= max <= lb <= d2(i, sample); lb is evaluated with the same rounded op
+//     sequence as d2 and fp32 rounding is monotone, so the bound also holds for the computed values);
+//     only the other buckets update their 64 points and refresh their (max, lowest original index at
+//     the max).  On 16k-point plots ~9 of 256 buckets are active per iteration.
+//   * NW warps; bucket j belongs to warp j % NW, slot j / NW (Morton neighbours land in different
+//     warps).  Lane l owns points l and l+32 of each of its warp's KB buckets.  Their running dist and
+//     their (original index << 16 | position) keys live in TENSOR MEMORY: the active slot is a run-time
+//     value, registers cannot be indexed dynamically (a jump table per slot measured ~350 cycles per
+//     active bucket and made ptxas speculate all 32 cases), shared memory is full with the
+//     coordinates (196 KB at N = 16384), and tcgen05.ld/st take the column as a register operand at
+//     shared-memory-like latency (measured 54 cycles, tools/tmem_probe.cu).  Warp w uses TMEM lanes
+//     32*(w%4).. and columns (w/4)*4*KB..; slot k = 4 columns (dist0, dist1, key0, key1).
+//   * Lane k keeps bucket slot k's box, current max and winner key in registers, so the per-sample
+//     bucket test is pure ALU.  Few warps on purpose: the loop is a latency chain and every extra warp
+//     repeats the control work (32 warps measured issue-bound).
+//   * arg-max: REDUX max over the bucket maxima, REDUX min over the keys of the tied lanes (lowest
+//     original index wins, the position rides along in the low 16 bits), one __syncthreads over
+//     double-buffered per-warp slots, every warp re-reduces the NW slots itself.
+constexpr unsigned FB_PAD = 0xffffffffu;
+
+__device__ __forceinline__ void tmem_ld4(unsigned addr, unsigned &a, unsigned &b, unsigned &c, unsigned &d)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
+}
+__device__ __forceinline__ void tmem_st4(unsigned addr, unsigned a, unsigned b, unsigned c, unsigned d)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+__device__ __forceinline__ void tmem_st2(unsigned addr, unsigned a, unsigned b)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};\n" ::"r"(addr), "r"(a), "r"(b));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+template <int NW, int KB, bool PROF = false>
+__global__ void __launch_bounds__(NW * 32, 1)
+fps_bucket_kernel(const float4 *__restrict__ pos, int N, int M, int P2, const int *__restrict__ start,
+                  int *__restrict__ idx_out, float4 *__restrict__ pos_out, long long *__restrict__ prof)
+{
+    static_assert(KB >= 1 && KB <= 32, "one bucket slot per lane at most");
+    static_assert(NW % 4 == 0 && NW <= 32, "whole warpgroups");
+    constexpr int THREADS = NW * 32;
+    constexpr int CAP = NW * KB * 64;                                // point capacity
+    constexpr int TCOLS = (NW / 4) * 4 * KB < 32 ? 32 : (NW / 4) * 4 * KB;  // TMEM columns (power of two >= 32)
+    static_assert((TCOLS & (TCOLS - 1)) == 0 && TCOLS <= 512, "TMEM allocation must be a power of two");
+    extern __shared__ __align__(16) unsigned char fb_smem[];
+    // sort keys [P2] u64, later reused as sx/sy/sz [CAP]
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(fb_smem);
+    float *sx = reinterpret_cast<float *>(fb_smem);
+    float *sy = sx + CAP;
+    float *sz = sy + CAP;
+    __shared__ uint2 slot[2][32];
+    __shared__ float red[6][32];
+    __shared__ int s_last;
+    __shared__ unsigned s_tmem;
+
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float4 *p = pos + (size_t)b * N;
+
+    // ---- 0. tensor-memory scratch ---------------------------------------------------------------
+    if (warp == 0) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_tmem);
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst), "r"(TCOLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+
+    // ---- 1. plot bounding box -> Morton keys -------------------------------------------------
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = tid; i < N; i += THREADS) {
+        const float4 v = __ldg(p + i);
+        lo[0] = fminf(lo[0], v.x); hi[0] = fmaxf(hi[0], v.x);
+        lo[1] = fminf(lo[1], v.y); hi[1] = fmaxf(hi[1], v.y);
+        lo[2] = fminf(lo[2], v.z); hi[2] = fmaxf(hi[2], v.z);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = -warp_max(-lo[a]);
+        hi[a] = warp_max(hi[a]);
+        if (lane == 0) { red[a][warp] = lo[a]; red[3 + a][warp] = hi[a]; }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n");
+    const unsigned tmem_base = s_tmem;
+    // this warp's TMEM window: lanes 32*(warp%4).., columns (warp/4)*4*KB..
+    const unsigned wbase = tmem_base + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * 4 * KB);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = -warp_max(lane < NW ? -red[a][lane] : -INFINITY);
+        hi[a] = warp_max(lane < NW ? red[3 + a][lane] : -INFINITY);
+    }
+    const float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+    const float scale = ext > 0.f ? 1023.0f / ext : 0.f;
+    auto spread = [](unsigned v) {  // 10 bits -> every third bit
+        v = (v | (v << 16)) & 0x030000ffu;
+        v = (v | (v << 8)) & 0x0300f00fu;
+        v = (v | (v << 4)) & 0x030c30c3u;
+        v = (v | (v << 2)) & 0x09249249u;
+        return v;
+    };
+    for (int i = tid; i < P2; i += THREADS) {
+        unsigned long long k = ~0ull;
+        if (i < N) {
+            const float4 v = __ldg(p + i);
+            const unsigned qx = min(1023u, (unsigned)((v.x - lo[0]) * scale));
+            const unsigned qy = min(1023u, (unsigned)((v.y - lo[1]) * scale));
+            const unsigned qz = min(1023u, (unsigned)((v.z - lo[2]) * scale));
+            const unsigned code = spread(qx) | (spread(qy) << 1) | (spread(qz) << 2);
+            k = ((unsigned long long)code << 32) | (unsigned)i;
+        }
+        keys[i] = k;
+    }
+    __syncthreads();
+
+    // ---- 2. bitonic sort of P2 keys ----------------------------------------------------------
+    for (int k = 2; k <= P2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (P2 >> 1); t += THREADS) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int ixj = i | j;
+                const unsigned long long a = keys[i], c = keys[ixj];
+                const bool up = (i & k) == 0;
+                if ((a > c) == up) { keys[i] = c; keys[ixj] = a; }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- 3. ownership: thread owns positions (k*NW+warp)*64 + h*32 + lane ----------------------
+    const unsigned st = start ? (unsigned)start[b] : 0u;
+    float bv = 0.f;                                             // lane k: current max of bucket slot k
+    unsigned bkey = FB_PAD;                                     // lane k: key of the point holding that max
+    float blo[3] = {0.f, 0.f, 0.f}, bhi[3] = {0.f, 0.f, 0.f};  // lane k: box of bucket slot k
+    {
+        unsigned orig[KB][2];
+#pragma unroll
+        for (int k = 0; k < KB; ++k)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int pp = ((k * NW + warp) * 64) + h * 32 + lane;
+                orig[k][h] = pp < P2 ? (unsigned)(keys[pp] & 0xffffffffull) : FB_PAD;
+            }
+        __syncthreads();  // keys are dead from here: the region becomes sx/sy/sz
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+            unsigned kk[2];
+            float dd[2];
+            bool any = false;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int pp = ((k * NW + warp) * 64) + h * 32 + lane;
+                const unsigned o = orig[k][h];
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                kk[h] = FB_PAD;
+                if (o != FB_PAD) {
+                    v = __ldg(p + o);
+                    mn[0] = fminf(mn[0], v.x); mx[0] = fmaxf(mx[0], v.x);
+                    mn[1] = fminf(mn[1], v.y); mx[1] = fmaxf(mx[1], v.y);
+                    mn[2] = fminf(mn[2], v.z); mx[2] = fmaxf(mx[2], v.z);
+                    any = true;
+                    if (o == st) s_last = pp;
+                    kk[h] = (o << 16) | (unsigned)pp;
+                }
+                dd[h] = o != FB_PAD ? INFINITY : 0.f;  // padding: dist 0 forever, key PAD -> never wins
+                sx[pp] = v.x; sy[pp] = v.y; sz[pp] = v.z;
+            }
+            tmem_st4(wbase + 4 * k, __float_as_uint(dd[0]), __float_as_uint(dd[1]), kk[0], kk[1]);
+            const bool bany = __any_sync(SN2_FULL, any);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float l = -warp_max(-mn[a]), h2 = warp_max(mx[a]);
+                if (lane == k) { blo[a] = l; bhi[a] = h2; }  // empty bucket: (+inf, -inf) -> lb = inf, never active
+            }
+            if (lane == k) bv = bany ? INFINITY : 0.f;
+        }
+        tmem_wait_st();
+    }
+    __syncthreads();
+    int last = s_last;
+    if (tid == 0) {
+        idx_out[(size_t)b * M] = b * N + (int)st;
+        if (pos_out) pos_out[(size_t)b * M] = __ldg(p + st);
+    }
+
+    // ---- 4. sampling loop ---------------------------------------------------------------------
+    int buf = 0;
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = 0;
+#define FB_TICK(i) if (PROF) { long long t_ = clock64(); pt[i] += t_ - tprev; tprev = t_; }
+    if (PROF) tprev = clock64();
+    for (int it = 1; it < M; ++it) {
+        const float lx = sx[last], ly = sy[last], lz = sz[last];
+        bool act = false;
+        if (lane < KB) {
+            const float cx = fminf(fmaxf(lx, blo[0]), bhi[0]);
+            const float cy = fminf(fmaxf(ly, blo[1]), bhi[1]);
+            const float cz = fminf(fmaxf(lz, blo[2]), bhi[2]);
+            act = dist2(cx, cy, cz, lx, ly, lz) < bv;
+        }
+        unsigned mask = __ballot_sync(SN2_FULL, act);
+        if (PROF) pt[6] += __popc(mask);
+        FB_TICK(0)
+        while (mask) {  // warp-uniform
+            const int k = __ffs(mask) - 1;
+            mask &= mask - 1;
+            unsigned d0, d1, k0, k1;
+            tmem_ld4(wbase + 4 * k, d0, d1, k0, k1);
+            const int p0 = ((k * NW + warp) * 64) + lane;
+            const float e0 = dist2(sx[p0], sy[p0], sz[p0], lx, ly, lz);
+            const float e1 = dist2(sx[p0 + 32], sy[p0 + 32], sz[p0 + 32], lx, ly, lz);
+            tmem_wait_ld();
+            const float n0 = fminf(__uint_as_float(d0), e0);
+            const float n1 = fminf(__uint_as_float(d1), e1);
+            tmem_st2(wbase + 4 * k, __float_as_uint(n0), __float_as_uint(n1));
+            const unsigned m = __reduce_max_sync(SN2_FULL, __float_as_uint(fmaxf(n0, n1)));
+            const unsigned c0 = __float_as_uint(n0) == m ? k0 : FB_PAD;
+            const unsigned c1 = __float_as_uint(n1) == m ? k1 : FB_PAD;
+            const unsigned mk = __reduce_min_sync(SN2_FULL, min(c0, c1));
+            if (lane == k) { bv = __uint_as_float(m); bkey = mk; }
+        }
+        tmem_wait_st();
+        FB_TICK(1)
+        // warp arg-max over this warp's bucket slots
+        const unsigned vb = lane < KB ? __float_as_uint(bv) : 0u;
+        const unsigned wm = __reduce_max_sync(SN2_FULL, vb);
+        const unsigned wk = __reduce_min_sync(SN2_FULL, (lane < KB && vb == wm) ? bkey : FB_PAD);
+        FB_TICK(2)
+        if (lane == 0) slot[buf][warp] = make_uint2(wm, wk);
+        __syncthreads();
+        FB_TICK(3)
+        const uint2 sl = lane < NW ? slot[buf][lane] : make_uint2(0u, FB_PAD);
+        const unsigned gm = __reduce_max_sync(SN2_FULL, sl.x);
+        const unsigned gk = __reduce_min_sync(SN2_FULL, (lane < NW && sl.x == gm) ? sl.y : FB_PAD);
+        last = (int)(gk & 0xffffu);
+        if (tid == 0) {
+            idx_out[(size_t)b * M + it] = b * N + (int)(gk >> 16);
+            if (pos_out) pos_out[(size_t)b * M + it] = make_float4(sx[last], sy[last], sz[last], 0.f);
+        }
+        buf ^= 1;
+        FB_TICK(4)
+    }
+    if (PROF && prof && lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) prof[((size_t)b * NW + warp) * 8 + i] = pt[i];
+    }
+#undef FB_TICK
+    // ---- 5. release tensor memory ---------------------------------------------------------------
+    asm volatile("tcgen05.fence::before_thread_sync;\n");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TCOLS));
+}
+
+template <int NW, int KB>
+static int launch_fps_bucket(const float4 *pos, int B, int N, int M, const int *start, int *idx, float4 *pos_out,
+                             cudaStream_t st)
+{
+    int P2 = 64;
+    while (P2 < N) P2 <<= 1;
+    const size_t cap = (size_t)NW * KB * 64;
+    if ((size_t)N > cap) return SN2_EINVAL;
+    const size_t smem = 3 * cap * 4 > (size_t)P2 * 8 ? 3 * cap * 4 : (size_t)P2 * 8;
+    auto kern = fps_bucket_kernel<NW, KB, false>;
+    SN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fps_bucket attr");
+    kern<<<B, NW * 32, smem, st>>>(pos, N, M, P2, start, idx, pos_out, nullptr);
+    SN2_LAUNCH_CHECK("fps_bucket_kernel");
+    return SN2_OK;
+}
+
+template <int NW>
+static int dispatch_fps_bucket(const float4 *p, int B, int N, int M, const int *start, int *idx, float4 *po, cudaStream_t st)
+{
+    const int per_warp = (N + NW * 64 - 1) / (NW * 64);  // bucket slots per warp needed
+    if (per_warp <= 4) return launch_fps_bucket<NW, 4>(p, B, N, M, start, idx, po, st);
+    if (per_warp <= 8) return launch_fps_bucket<NW, 8>(p, B, N, M, start, idx, po, st);
+    if (per_warp <= 16) return launch_fps_bucket<NW, 16>(p, B, N, M, start, idx, po, st);
+    if constexpr (NW <= 8) {
+        if (per_warp <= 32) return launch_fps_bucket<NW, 32>(p, B, N, M, start, idx, po, st);
+    }
+    return SN2_EUNSUPPORTED;
+}
+
 template <int THREADS, int PPT, bool REGXYZ>
 static int launch_fps(const float4 *pos, int B, int N, int M, const int *start, int *idx, float4 *pos_out,
                       cudaStream_t st)
@@ -147,8 +438,8 @@ extern "C" int sn2_ingest(const float *xyz, const float *cloud, int B, int N, in
     return SN2_OK;
 }
 
-extern "C" int sn2_fps(const float *pos4, int B, int N, int M, const int *start, int *idx_out, float *pos4_out,
-                       void *stream)
+extern "C" int sn2_fps_algo(const float *pos4, int B, int N, int M, const int *start, int *idx_out,
+                            float *pos4_out, int algo, void *stream)
 {
     if (!pos4 || !idx_out || B <= 0 || N <= 0 || M <= 0 || M > N) return SN2_EINVAL;
     if (N > sn2_fps_max_points()) return SN2_EUNSUPPORTED;
@@ -156,6 +447,11 @@ extern "C" int sn2_fps(const float *pos4, int B, int N, int M, const int *start,
     float4 *po = reinterpret_cast<float4 *>(pos4_out);
     cudaStream_t st = (cudaStream_t)stream;
     using namespace sn2;
+    // measured on B200 (tools/bench_fps.py): pruning wins above ~4k points, the plain scan below
+    if (algo == SN2_FPS_AUTO) algo = (N > 4096) ? SN2_FPS_BUCKETED : SN2_FPS_BRUTE;
+    if (algo == SN2_FPS_BUCKETED) return dispatch_fps_bucket<8>(p, B, N, M, start, idx_out, po, st);
+    if (algo == SN2_FPS_BUCKETED16) return dispatch_fps_bucket<16>(p, B, N, M, start, idx_out, po, st);
+    if (algo != SN2_FPS_BRUTE) return SN2_EINVAL;
     if (N <= 256) return launch_fps<128, 2, true>(p, B, N, M, start, idx_out, po, st);
     if (N <= 1024) return launch_fps<256, 4, true>(p, B, N, M, start, idx_out, po, st);
     if (N <= 2560) return launch_fps<512, 5, true>(p, B, N, M, start, idx_out, po, st);
@@ -163,4 +459,39 @@ extern "C" int sn2_fps(const float *pos4, int B, int N, int M, const int *start,
     if (N <= 8192) return launch_fps<1024, 8, true>(p, B, N, M, start, idx_out, po, st);
     if (N <= 10240) return launch_fps<1024, 10, false>(p, B, N, M, start, idx_out, po, st);
     return launch_fps<1024, 16, false>(p, B, N, M, start, idx_out, po, st);
+}
+
+// Debug/profiling entry (not part of the product ABI): per-warp phase cycle counters of the bucketed kernel.
+// prof [B*NW*8] int64: test+ballot, bucket updates, warp arg-max, barrier wait, block arg-max, -, sum(active), -
+extern "C" int sn2_debug_fps_profile(const float *pos4, int B, int N, int M, int *idx_out, long long *prof, int nw,
+                                     void *stream)
+{
+    using namespace sn2;
+    const float4 *p = reinterpret_cast<const float4 *>(pos4);
+    int P2 = 64;
+    while (P2 < N) P2 <<= 1;
+    cudaStream_t st = (cudaStream_t)stream;
+#define SN2_PROF_LAUNCH(NW, KB)                                                                                      \
+    {                                                                                                                \
+        const size_t cap = (size_t)NW * KB * 64;                                                                     \
+        if ((size_t)N > cap) return SN2_EINVAL;                                                                      \
+        const size_t smem = 3 * cap * 4 > (size_t)P2 * 8 ? 3 * cap * 4 : (size_t)P2 * 8;                             \
+        auto kern = fps_bucket_kernel<NW, KB, true>;                                                                 \
+        SN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attr");    \
+        kern<<<B, NW * 32, smem, st>>>(p, N, M, P2, nullptr, idx_out, nullptr, prof);                                \
+        SN2_LAUNCH_CHECK("fps_bucket_kernel<prof>");                                                                 \
+        return SN2_OK;                                                                                               \
+    }
+    if (nw == 8 && N <= 4096) SN2_PROF_LAUNCH(8, 8)
+    if (nw == 8) SN2_PROF_LAUNCH(8, 32)
+    if (nw == 16 && N <= 4096) SN2_PROF_LAUNCH(16, 4)
+    if (nw == 16) SN2_PROF_LAUNCH(16, 16)
+#undef SN2_PROF_LAUNCH
+    return SN2_EINVAL;
+}
+
+extern "C" int sn2_fps(const float *pos4, int B, int N, int M, const int *start, int *idx_out, float *pos4_out,
+                       void *stream)
+{
+    return sn2_fps_algo(pos4, B, N, M, start, idx_out, pos4_out, SN2_FPS_AUTO, stream);
 }

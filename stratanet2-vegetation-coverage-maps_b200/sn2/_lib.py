@@ -25,6 +25,7 @@ SIGNATURES = {
     "sn2_ingest": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "sn2_fps_max_points": [],
     "sn2_fps": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "sn2_fps_algo": [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
     "sn2_grid_build": [_vp, _i, _i, _f, _vp, _vp, _vp, _vp],
     "sn2_ball_count": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp],
     "sn2_rowptr_scan": [_vp, _i, _i, _vp, _vp, _vp],
@@ -33,6 +34,7 @@ SIGNATURES = {
     "sn2_global_sa_fwd": [_vp, _vp, _i, _i, _vp, _i, _vp, _vp],
     "sn2_fp3_fwd": [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp],
     "sn2_knn3": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "sn2_knn3_grid": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "sn2_fp2_fwd": [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp],
     "sn2_fp1_head_fwd": [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp],
     "sn2_project_plotwise": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],

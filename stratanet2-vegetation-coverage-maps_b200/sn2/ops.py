@@ -65,13 +65,16 @@ def ingest(xyz: torch.Tensor, cloud: torch.Tensor):
     return pos4, feat
 
 
-def fps_dense(pos4: torch.Tensor, B: int, N: int, M: int, start: torch.Tensor | None = None):
+FPS_AUTO, FPS_BRUTE, FPS_BUCKETED, FPS_BUCKETED16 = 0, 1, 2, 3
+
+
+def fps_dense(pos4: torch.Tensor, B: int, N: int, M: int, start: torch.Tensor | None = None, algo: int = FPS_AUTO):
     """-> idx int32 [B*M] (global rows), pos4_out [B*M,4]."""
     lib = _lib.load()
     idx = torch.empty(B * M, dtype=torch.int32, device=pos4.device)
     out = torch.empty((B * M, 4), dtype=torch.float32, device=pos4.device)
-    check(lib.sn2_fps(dptr(pos4, torch.float32), B, N, M, dptr(start, torch.int32) if start is not None else None,
-                      dptr(idx), dptr(out), stream_ptr()), "sn2_fps")
+    check(lib.sn2_fps_algo(dptr(pos4, torch.float32), B, N, M, dptr(start, torch.int32) if start is not None else None,
+                           dptr(idx), dptr(out), int(algo), stream_ptr()), "sn2_fps")
     _count(1)
     return idx, out
 
@@ -134,13 +137,32 @@ def fp3_fwd(g, x2, pos4, B: int, M: int, w_host):
     return out
 
 
-def knn3_dense(spos4, qpos4, B: int, Ms: int, Nq: int):
-    """-> nbr int32 [B*Nq,3] (global source rows, ascending distance), w fp32 [B*Nq,3]."""
+KNN_AUTO, KNN_BRUTE, KNN_GRID = 0, 1, 2
+
+
+def knn3_dense(spos4, qpos4, B: int, Ms: int, Nq: int, algo: int = KNN_AUTO):
+    """-> nbr int32 [B*Nq,3] (global source rows, ascending distance), w fp32 [B*Nq,3].
+    KNN_GRID bins the sources (one extra kernel) and ring-searches; KNN_BRUTE scans all sources."""
     lib = _lib.load()
-    nbr = torch.empty((B * Nq, 3), dtype=torch.int32, device=spos4.device)
-    w = torch.empty((B * Nq, 3), dtype=torch.float32, device=spos4.device)
-    check(lib.sn2_knn3(dptr(spos4, torch.float32), dptr(qpos4, torch.float32), B, Ms, Nq, dptr(nbr), dptr(w), stream_ptr()),
-          "sn2_knn3")
+    dev = spos4.device
+    nbr = torch.empty((B * Nq, 3), dtype=torch.int32, device=dev)
+    w = torch.empty((B * Nq, 3), dtype=torch.float32, device=dev)
+    if algo == KNN_AUTO:
+        algo = KNN_GRID if Ms >= 256 else KNN_BRUTE
+    if algo == KNN_BRUTE:
+        check(lib.sn2_knn3(dptr(spos4, torch.float32), dptr(qpos4, torch.float32), B, Ms, Nq, dptr(nbr), dptr(w),
+                           stream_ptr()), "sn2_knn3")
+        _count(1)
+        return nbr, w
+    hdr = torch.empty(B * GRID_HDR, dtype=torch.float32, device=dev)
+    cell_start = torch.empty(B * (GRID_CELLS + 1), dtype=torch.int32, device=dev)
+    sorted4 = torch.empty((B * Ms, 4), dtype=torch.float32, device=dev)
+    st = stream_ptr()
+    check(lib.sn2_grid_build(dptr(spos4, torch.float32), B, Ms, -3.0, dptr(hdr), dptr(cell_start), dptr(sorted4), st),
+          "sn2_grid_build")
+    _count(1)
+    check(lib.sn2_knn3_grid(dptr(hdr), dptr(cell_start), dptr(sorted4), dptr(qpos4, torch.float32), B, Ms, Nq, dptr(nbr),
+                            dptr(w), st), "sn2_knn3_grid")
     _count(1)
     return nbr, w
 
@@ -233,7 +255,7 @@ def to_pos4(pos: torch.Tensor) -> torch.Tensor:
     return torch.nn.functional.pad(pos, (0, 1)).contiguous()
 
 
-def fps(x, batch=None, ratio=0.5, random_start=False, start=None):
+def fps(x, batch=None, ratio=0.5, random_start=False, start=None, algo: int = FPS_AUTO):
     """Drop-in for torch_cluster/torch_geometric ``fps`` (/root/reference/model/point_net2.py:22).
     Canonical start = first point of each plot; ``start`` (local index per plot) overrides it;
     ``random_start=True`` draws it with torch's generator."""
@@ -244,7 +266,7 @@ def fps(x, batch=None, ratio=0.5, random_start=False, start=None):
         st = torch.as_tensor(start, dtype=torch.int32, device=x.device).contiguous()
     elif random_start:
         st = torch.randint(0, n, (B,), device=x.device, dtype=torch.int32)
-    idx, _ = fps_dense(to_pos4(x), B, n, M, st)
+    idx, _ = fps_dense(to_pos4(x), B, n, M, st, algo)
     return idx.to(torch.int64)
 
 

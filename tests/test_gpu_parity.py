@@ -25,8 +25,9 @@ def _batch(B, N):
 
 
 @pytest.mark.parametrize("variant", ["plain", "cm", "dup"])
-@pytest.mark.parametrize("N", [300, 1000, 2500, 4096, 10000, 16384])
+@pytest.mark.parametrize("N", [300, 1000, 2500, 4096, 5000, 10000, 12345, 16384])
 def test_fps_bit_exact(cuda_device, N, variant):
+    """Both FPS kernels (brute force and bucketed/pruned) reproduce the oracle's indices exactly."""
     from oracle import thirdparty_ops as tp
     from sn2 import ops
 
@@ -34,9 +35,24 @@ def test_fps_bit_exact(cuda_device, N, variant):
     data = _plots(11, B, N, variant)
     pos, batch = _long(data["xyz"]), _batch(B, N)
     want = tp.fps(pos, batch, ratio=0.25)
-    got = ops.fps(pos.to(cuda_device), batch.to(cuda_device), ratio=0.25)
-    assert got.dtype == torch.int64
-    assert torch.equal(got.cpu(), want)
+    for algo in (ops.FPS_BRUTE, ops.FPS_BUCKETED, ops.FPS_BUCKETED16, ops.FPS_AUTO):
+        got = ops.fps(pos.to(cuda_device), batch.to(cuda_device), ratio=0.25, algo=algo)
+        assert got.dtype == torch.int64
+        assert torch.equal(got.cpu(), want), f"algo {algo}"
+
+
+def test_fps_bucketed_degenerate_inputs(cuda_device):
+    from oracle import thirdparty_ops as tp
+    from sn2 import ops
+
+    # all points identical, collinear points, and a plot made of 3 distinct locations only
+    cases = [torch.zeros(3000, 3), torch.stack([torch.arange(2048.) * 0.01, torch.zeros(2048), torch.zeros(2048)], 1),
+             torch.tensor([[0., 0, 0], [1, 1, 1], [5, 0, 2]]).repeat(700, 1)]
+    for pos in cases:
+        want = tp.fps(pos, None, ratio=0.25)
+        for algo in (ops.FPS_BRUTE, ops.FPS_BUCKETED, ops.FPS_BUCKETED16):
+            got = ops.fps(pos.to(cuda_device), None, ratio=0.25, algo=algo).cpu()
+            assert torch.equal(got, want), f"algo {algo}"
 
 
 def test_fps_known_answers(cuda_device):
@@ -102,10 +118,31 @@ def test_knn3_bit_exact(cuda_device, Ms, Nq, variant):
     assert src_idx.numel() == B * Ms
     s, bs = q[src_idx], bq[src_idx]
     want_idx, want_d2 = tp.knn_raw(s, q, 3, bs, bq)
-    nbr, w = ops.knn3_dense(ops.to_pos4(s.to(cuda_device)), ops.to_pos4(q.to(cuda_device)), B, Ms, Nq)
-    assert torch.equal(nbr.cpu().to(torch.int64), want_idx)
     want_w = 1.0 / torch.clamp(want_d2, min=1e-16)
-    assert torch.equal(w.cpu(), want_w)
+    for algo in (ops.KNN_BRUTE, ops.KNN_GRID):
+        nbr, w = ops.knn3_dense(ops.to_pos4(s.to(cuda_device)), ops.to_pos4(q.to(cuda_device)), B, Ms, Nq, algo)
+        assert torch.equal(nbr.cpu().to(torch.int64), want_idx), f"algo {algo}"
+        assert torch.equal(w.cpu(), want_w), f"algo {algo}"
+
+
+def test_knn3_grid_hard_cases(cuda_device):
+    """Queries far outside the sources' bounding box, heavy duplicates, collinear sources."""
+    from oracle import thirdparty_ops as tp
+    from sn2 import ops
+
+    g = torch.Generator().manual_seed(3)
+    src = torch.rand(600, 3, generator=g)
+    src[:, 2] *= 10
+    qry = torch.cat([torch.rand(500, 3, generator=g) * 6 - 3, src[:50], torch.tensor([[100., -50., 3.]])])
+    cases = [(src, qry),
+             (torch.tensor([[0., 0, 0], [1, 0, 0], [1, 0, 0], [0, 0, 5]]).repeat(100, 1), qry),
+             (torch.stack([torch.arange(400.) * 0.01, torch.zeros(400), torch.zeros(400)], 1), qry)]
+    for s, q in cases:
+        want_idx, want_d2 = tp.knn_raw(s, q, 3)
+        for algo in (ops.KNN_BRUTE, ops.KNN_GRID):
+            nbr, w = ops.knn3_dense(ops.to_pos4(s.to(cuda_device)), ops.to_pos4(q.to(cuda_device)), 1, s.shape[0], q.shape[0], algo)
+            assert torch.equal(nbr.cpu().to(torch.int64), want_idx), f"algo {algo}"
+            assert torch.equal(w.cpu(), 1.0 / torch.clamp(want_d2, min=1e-16))
 
 
 def _make_models(N, device):
