@@ -100,6 +100,18 @@ int sn2_pointconv_fwd(int level, const float *pos4, const float *feat, const flo
                       const int *rowptr, const int *col, int Q, const float *w_host, int nw,
                       float *out, void *stream);
 
+/* ---- a3/a4 fused (eval): ball query + PointConv in one kernel, no neighbour list (csrc/sa_fused.cu).
+ * (grid_hdr, cell_start, sorted4) = sn2_grid_build of the N points with r; qsorted4 [B*M] = the queries in
+ * any spatially coherent order with their local query index in .w (sn2_grid_build of the queries gives it).
+ * u_scratch [B*N, 16|32]: per-point half of the first layer (written by this call).
+ * ovf_scratch [B*M + 1] int32: overflow list of the centroids whose cap binds (redone exactly).
+ * out [B*M, 16|32] indexed by the ORIGINAL query index; cnt_out (optional) = min(K, #neighbours).
+ * Same edges as sn2_ball_* (including when the cap K binds); values equal sn2_pointconv_fwd to fp32 rounding. */
+int sn2_sa_fused_fwd(int level, const float *grid_hdr, const int *cell_start, const float *sorted4,
+                     const float *qsorted4, const float *pos4, const float *feat, float *u_scratch,
+                     int *ovf_scratch, int B, int N, int M, float r2, int K, const float *w_host, int nw,
+                     float *out, int *cnt_out, void *stream);
+
 /* ---- a5: global set abstraction.  Replaces MLP[35,64] + global_max_pool (model/point_net2.py:37-42).
  * x2 [B*M,32], pos4 [B*M] -> g [B,64]. */
 int sn2_global_sa_fwd(const float *x2, const float *pos4, int B, int M, const float *w_host, int nw,

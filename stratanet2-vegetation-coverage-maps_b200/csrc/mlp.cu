@@ -8,140 +8,45 @@
 // unrolled, so every FFMA takes its weight as a constant-bank operand (no load instruction, no
 // register, no shared-memory traffic for weights).  Activations stay in registers from the gather
 // to the max / store.
-#include "sn2_common.cuh"
-#include <string.h>
+#include "mlp_common.cuh"
 
 namespace sn2 {
 
-template <int CIN, int COUT>
-struct Layer {          // flat float layout: w (k-major), b, s, t
-    float w[CIN][COUT];  // transposed Linear weight: w[k][o] = W[o][k]
-    float b[COUT];
-    float s[COUT];       // eval BN scale
-    float t[COUT];       // eval BN shift
-};
-template <int CIN, int COUT>
-struct Lin {
-    float w[CIN][COUT];
-    float b[COUT];
-};
-
-struct W_SA1 { Layer<SN2_F0 + 3, SN2_C1> l1; Layer<SN2_C1, SN2_C1> l2; };
-struct W_SA2 { Layer<SN2_C1 + 3, SN2_C2> l1; };
-struct W_SA3 { Layer<SN2_C2 + 3, SN2_C3> l1; };
-struct W_FP3 { Layer<SN2_C3 + SN2_C2, SN2_C3> l1; };
-struct W_FP2 { Layer<SN2_C3 + SN2_C1, SN2_CF> l1; };
-struct W_FP1 { Layer<SN2_CF + SN2_F0, SN2_CF> l1; Lin<SN2_CF, 16> lin1; Lin<16, 5> lin2; };
-
-template <int COUT, typename L>
-__device__ __forceinline__ void acc_init(const L &l, float (&acc)[COUT])
-{
-#pragma unroll
-    for (int o = 0; o < COUT; ++o) acc[o] = l.b[o];
-}
-// acc += in * w[K0 + k][:]
-template <int K0, int COUT, typename L>
-__device__ __forceinline__ void acc_step(const L &l, float in, float (&acc)[COUT], int k)
-{
-#pragma unroll
-    for (int o = 0; o < COUT; ++o) acc[o] = fmaf(in, l.w[K0 + k][o], acc[o]);
-}
-template <int COUT, typename L>
-__device__ __forceinline__ void relu_bn(const L &l, float (&acc)[COUT])
-{
-#pragma unroll
-    for (int o = 0; o < COUT; ++o) acc[o] = fmaf(fmaxf(acc[o], 0.f), l.s[o], l.t[o]);
-}
-
 // ---------------------------------------------------------------------------------------------
-// PointConv: one warp per query (centroid), one lane per neighbour.
+// PointConv over a materialised neighbour list: one warp per query (centroid), one lane per edge.
 // ---------------------------------------------------------------------------------------------
+template <int LEVEL>
 __global__ void __launch_bounds__(256)
-pointconv1_kernel(const float4 *__restrict__ pos, const float *__restrict__ feat,
-                  const float4 *__restrict__ qpos, const int *__restrict__ rowptr,
-                  const int *__restrict__ col, int Q, const __grid_constant__ W_SA1 W, float *__restrict__ out)
+pointconv_kernel(const float4 *__restrict__ pos, const float *__restrict__ feat, const float4 *__restrict__ qpos,
+                 const int *__restrict__ rowptr, const int *__restrict__ col, int Q,
+                 const __grid_constant__ typename SAEdge<LEVEL>::W W, float *__restrict__ out)
 {
+    using E = SAEdge<LEVEL>;
     const int lane = threadIdx.x & 31;
     const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= Q) return;
     const int s = __ldg(rowptr + q), e = __ldg(rowptr + q + 1);
     const float4 qp = __ldg(qpos + q);
-    float mx[SN2_C1];
+    float mx[E::COUT];
 #pragma unroll
-    for (int o = 0; o < SN2_C1; ++o) mx[o] = -INFINITY;
+    for (int o = 0; o < E::COUT; ++o) mx[o] = -INFINITY;
     for (int base = s; base < e; base += 32) {
         const int j = base + lane;
         if (j < e) {
             const int p = __ldg(col + j);
             const float4 pp = __ldg(pos + p);
-            const float4 f0 = ldg4(feat + (size_t)p * SN2_F0), f1 = ldg4(feat + (size_t)p * SN2_F0 + 4);
-            const float in[SN2_F0 + 3] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w,
-                                          pp.x - qp.x, pp.y - qp.y, pp.z - qp.z};
-            float h1[SN2_C1];
-            acc_init(W.l1, h1);
+            float h[E::COUT];
+            E::run(W, feat + (size_t)p * E::CIN, pp.x - qp.x, pp.y - qp.y, pp.z - qp.z, h);
 #pragma unroll
-            for (int k = 0; k < SN2_F0 + 3; ++k) acc_step<0>(W.l1, in[k], h1, k);
-            relu_bn(W.l1, h1);
-            float h2[SN2_C1];
-            acc_init(W.l2, h2);
-#pragma unroll
-            for (int k = 0; k < SN2_C1; ++k) acc_step<0>(W.l2, h1[k], h2, k);
-            relu_bn(W.l2, h2);
-#pragma unroll
-            for (int o = 0; o < SN2_C1; ++o) mx[o] = fmaxf(mx[o], h2[o]);
+            for (int o = 0; o < E::COUT; ++o) mx[o] = fmaxf(mx[o], h[o]);
         }
     }
 #pragma unroll
-    for (int o = 0; o < SN2_C1; ++o) mx[o] = (e > s) ? warp_max(mx[o]) : 0.f;
+    for (int o = 0; o < E::COUT; ++o) mx[o] = (e > s) ? warp_max(mx[o]) : 0.f;  // torch_scatter: empty row -> 0
     if (lane == 0) {
-        float4 *o4 = reinterpret_cast<float4 *>(out + (size_t)q * SN2_C1);
+        float4 *o4 = reinterpret_cast<float4 *>(out + (size_t)q * E::COUT);
 #pragma unroll
-        for (int v = 0; v < SN2_C1 / 4; ++v) o4[v] = make_float4(mx[4 * v], mx[4 * v + 1], mx[4 * v + 2], mx[4 * v + 3]);
-    }
-}
-
-__global__ void __launch_bounds__(256)
-pointconv2_kernel(const float4 *__restrict__ pos, const float *__restrict__ feat,
-                  const float4 *__restrict__ qpos, const int *__restrict__ rowptr,
-                  const int *__restrict__ col, int Q, const __grid_constant__ W_SA2 W, float *__restrict__ out)
-{
-    const int lane = threadIdx.x & 31;
-    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (q >= Q) return;
-    const int s = __ldg(rowptr + q), e = __ldg(rowptr + q + 1);
-    const float4 qp = __ldg(qpos + q);
-    float mx[SN2_C2];
-#pragma unroll
-    for (int o = 0; o < SN2_C2; ++o) mx[o] = -INFINITY;
-    for (int base = s; base < e; base += 32) {
-        const int j = base + lane;
-        if (j < e) {
-            const int p = __ldg(col + j);
-            const float4 pp = __ldg(pos + p);
-            float h[SN2_C2];
-            acc_init(W.l1, h);
-#pragma unroll
-            for (int v = 0; v < SN2_C1 / 4; ++v) {
-                const float4 f = ldg4(feat + (size_t)p * SN2_C1 + 4 * v);
-                acc_step<0>(W.l1, f.x, h, 4 * v);
-                acc_step<0>(W.l1, f.y, h, 4 * v + 1);
-                acc_step<0>(W.l1, f.z, h, 4 * v + 2);
-                acc_step<0>(W.l1, f.w, h, 4 * v + 3);
-            }
-            acc_step<SN2_C1>(W.l1, pp.x - qp.x, h, 0);
-            acc_step<SN2_C1>(W.l1, pp.y - qp.y, h, 1);
-            acc_step<SN2_C1>(W.l1, pp.z - qp.z, h, 2);
-            relu_bn(W.l1, h);
-#pragma unroll
-            for (int o = 0; o < SN2_C2; ++o) mx[o] = fmaxf(mx[o], h[o]);
-        }
-    }
-#pragma unroll
-    for (int o = 0; o < SN2_C2; ++o) mx[o] = (e > s) ? warp_max(mx[o]) : 0.f;
-    if (lane == 0) {
-        float4 *o4 = reinterpret_cast<float4 *>(out + (size_t)q * SN2_C2);
-#pragma unroll
-        for (int v = 0; v < SN2_C2 / 4; ++v) o4[v] = make_float4(mx[4 * v], mx[4 * v + 1], mx[4 * v + 2], mx[4 * v + 3]);
+        for (int v = 0; v < E::COUT / 4; ++v) o4[v] = make_float4(mx[4 * v], mx[4 * v + 1], mx[4 * v + 2], mx[4 * v + 3]);
     }
 }
 
@@ -385,14 +290,6 @@ knn3_kernel(const float4 *__restrict__ spos, const float4 *__restrict__ qpos, in
     }
 }
 
-template <typename WS>
-static int load_weights(WS &w, const float *w_host, int nw)
-{
-    if (!w_host || (size_t)nw * sizeof(float) != sizeof(WS)) return SN2_EINVAL;
-    memcpy(&w, w_host, sizeof(WS));
-    return SN2_OK;
-}
-
 }  // namespace sn2
 
 using namespace sn2;
@@ -407,13 +304,13 @@ extern "C" int sn2_pointconv_fwd(int level, const float *pos4, const float *feat
     if (level == 1) {
         W_SA1 w;
         if (int rc = load_weights(w, w_host, nw)) return rc;
-        pointconv1_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(pos4), feat,
-                                                            reinterpret_cast<const float4 *>(qpos4), rowptr, col, Q, w, out);
+        pointconv_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(pos4), feat,
+                                                              reinterpret_cast<const float4 *>(qpos4), rowptr, col, Q, w, out);
     } else if (level == 2) {
         W_SA2 w;
         if (int rc = load_weights(w, w_host, nw)) return rc;
-        pointconv2_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(pos4), feat,
-                                                            reinterpret_cast<const float4 *>(qpos4), rowptr, col, Q, w, out);
+        pointconv_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(pos4), feat,
+                                                              reinterpret_cast<const float4 *>(qpos4), rowptr, col, Q, w, out);
     } else {
         return SN2_EINVAL;
     }

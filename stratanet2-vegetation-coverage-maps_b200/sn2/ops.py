@@ -119,6 +119,37 @@ def pointconv_fwd(level: int, pos4, feat, qpos4, rowptr, col, w_host: torch.Tens
     return out
 
 
+def build_grid(pos4, B: int, N: int, r: float):
+    """xy cell grid of B plots of N points -> (hdr, cell_start, sorted4)."""
+    lib = _lib.load()
+    dev = pos4.device
+    hdr = torch.empty(B * GRID_HDR, dtype=torch.float32, device=dev)
+    cell_start = torch.empty(B * (GRID_CELLS + 1), dtype=torch.int32, device=dev)
+    sorted4 = torch.empty((B * N, 4), dtype=torch.float32, device=dev)
+    check(lib.sn2_grid_build(dptr(pos4, torch.float32), B, N, float(r), dptr(hdr), dptr(cell_start), dptr(sorted4),
+                             stream_ptr()), "sn2_grid_build")
+    _count(1)
+    return hdr, cell_start, sorted4
+
+
+def sa_fused_fwd(level: int, pos4, feat, qpos4, B: int, N: int, M: int, r: float, K: int, w_host, want_counts=False):
+    """Fused ball query + PointConv (eval).  -> out [B*M, 16|32] (+ neighbour counts int32 [B*M])."""
+    lib = _lib.load()
+    dev = pos4.device
+    hdr, cell_start, sorted4 = build_grid(pos4, B, N, r)
+    _, _, qsorted4 = build_grid(qpos4, B, M, r)  # only used as a cell-ordered permutation of the queries
+    cout = 16 if level == 1 else 32
+    out = torch.empty((B * M, cout), dtype=torch.float32, device=dev)
+    u = torch.empty((B * N, cout), dtype=torch.float32, device=dev)
+    cnt = torch.empty(B * M, dtype=torch.int32, device=dev) if want_counts else None
+    ovf = torch.empty(B * M + 1, dtype=torch.int32, device=dev)
+    check(lib.sn2_sa_fused_fwd(level, dptr(hdr), dptr(cell_start), dptr(sorted4), dptr(qsorted4), dptr(pos4, torch.float32),
+                               dptr(feat, torch.float32), dptr(u), dptr(ovf), B, N, M, r2_of(r), int(K), hptr(w_host),
+                               w_host.numel(), dptr(out), dptr(cnt), stream_ptr()), "sn2_sa_fused_fwd")
+    _count(4 if K < N else 3)
+    return (out, cnt) if want_counts else out
+
+
 def global_sa_fwd(x2, pos4, B: int, M: int, w_host):
     lib = _lib.load()
     g = torch.empty((B, 64), dtype=torch.float32, device=x2.device)

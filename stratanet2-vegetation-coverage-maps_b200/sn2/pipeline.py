@@ -93,18 +93,19 @@ def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_
     M1 = ops.m_of(N, sa1.ratio)
     with T.stage("fps1"):
         idx1, pos1 = ops.fps_dense(pos0, B, N, M1)
-    with T.stage("ball1"):
+    rowptr1 = col1 = rowptr2 = col2 = None
+    if trace is not None:  # neighbour lists only materialised for parity tests / backward
         rowptr1, col1 = ops.ball_query_dense(pos0, pos1, B, N, M1, sa1.r, max_num_neighbors)
-    with T.stage("pointconv1"):
-        x1 = ops.pointconv_fwd(1, pos0, feat0, pos1, rowptr1, col1, W["sa1"])
+    with T.stage("sa1_fused"):
+        x1 = ops.sa_fused_fwd(1, pos0, feat0, pos1, B, N, M1, sa1.r, max_num_neighbors, W["sa1"])
 
     M2 = ops.m_of(M1, sa2.ratio)
     with T.stage("fps2"):
         idx2, pos2 = ops.fps_dense(pos1, B, M1, M2)
-    with T.stage("ball2"):
+    if trace is not None:
         rowptr2, col2 = ops.ball_query_dense(pos1, pos2, B, M1, M2, sa2.r, max_num_neighbors)
-    with T.stage("pointconv2"):
-        x2 = ops.pointconv_fwd(2, pos1, x1, pos2, rowptr2, col2, W["sa2"])
+    with T.stage("sa2_fused"):
+        x2 = ops.sa_fused_fwd(2, pos1, x1, pos2, B, M1, M2, sa2.r, max_num_neighbors, W["sa2"])
 
     with T.stage("global_sa"):
         g = ops.global_sa_fwd(x2, pos2, B, M2, W["sa3"])

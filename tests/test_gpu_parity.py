@@ -231,3 +231,42 @@ def test_projections_parity(cuda_device, B, N):
     _, rpix = ops.project_rasters(data["cloud"].to(cuda_device), pred.to(cuda_device), "point_major", D, args.diam_meters, want_pix=True)
     wr = raster_pixel_ids(data["cloud"], D, args.diam_meters)
     assert torch.equal(rpix.cpu().view(B, N), (wr[:, 1] * D + wr[:, 0]).int())
+
+
+@pytest.mark.parametrize("N,K,variant", [(10000, 2000, "plain"), (10000, 64, "cm"), (6000, 16, "dup"), (16384, 48, "plain")])
+def test_sa_fused_equals_list_path(cuda_device, N, K, variant):
+    """Fused ball-query + PointConv vs materialised neighbour list + PointConv: the same edges take part
+    (identical neighbour counts, including when the cap K binds: canonical first-K-by-index subset) and
+    the values agree to fp32 rounding (the fused kernel factorises the first layer); both match the oracle."""
+    from oracle import thirdparty_ops as tp
+    from sn2 import ops, weights
+
+    B = 2
+    args, net, port = _make_models(N, cuda_device)
+    W = weights.pack_eval(net)
+    data = _plots(15, B, N, variant)
+    dev = cuda_device
+    pos0, feat0 = ops.ingest(data["xyz"].to(dev), data["cloud"].to(dev))
+    M1 = ops.m_of(N, 0.25)
+    _, pos1 = ops.fps_dense(pos0, B, N, M1)
+    r1, r2 = float(np.sqrt(2.0)), float(np.sqrt(8.0))
+    rowptr, col = ops.ball_query_dense(pos0, pos1, B, N, M1, r1, K)
+    x1_list = ops.pointconv_fwd(1, pos0, feat0, pos1, rowptr, col, W["sa1"])
+    x1_fused, cnt = ops.sa_fused_fwd(1, pos0, feat0, pos1, B, N, M1, r1, K, W["sa1"], want_counts=True)
+    assert torch.equal(cnt, rowptr[1:] - rowptr[:-1])
+    torch.testing.assert_close(x1_fused, x1_list, rtol=1e-4, atol=1e-5)
+    M2 = ops.m_of(M1, 0.25)
+    _, pos2 = ops.fps_dense(pos1, B, M1, M2)
+    rowptr2, col2 = ops.ball_query_dense(pos1, pos2, B, M1, M2, r2, K)
+    x2_list = ops.pointconv_fwd(2, pos1, x1_list, pos2, rowptr2, col2, W["sa2"])
+    x2_fused = ops.sa_fused_fwd(2, pos1, x1_list, pos2, B, M1, M2, r2, K, W["sa2"])
+    torch.testing.assert_close(x2_fused, x2_list, rtol=1e-4, atol=1e-5)
+    # oracle: PointConv on the oracle's capped edge list
+    posl, batch = _long(data["xyz"]), _batch(B, N)
+    x0 = data["cloud"].permute(0, 2, 1).reshape(B * N, -1)[:, 2:]
+    idx = tp.fps(posl, batch, ratio=0.25)
+    row, c = tp.radius(posl, posl[idx], r1, batch, batch[idx], max_num_neighbors=K)
+    with torch.no_grad():
+        msg = port.sa1_module.conv.local_nn(torch.cat([x0[c], posl[c] - posl[idx][row]], dim=1))
+        want = tp.scatter_max(msg, row, dim=0, dim_size=idx.numel())[0]
+    torch.testing.assert_close(x1_fused.cpu(), want, rtol=RTOL, atol=ATOL)
