@@ -159,6 +159,34 @@ int sn2_project_rasters(const float *cloud, const float *cov, long long cov_sb, 
                         long long cov_sc, int B, int N, int F, int D, float scale, float shift,
                         double *rasters, int *pix, void *stream);
 
+/* ================= training-path operators (forward + backward), csrc/train_ops.cu =================
+ * In training mode BatchNorm uses batch statistics over all edge messages of the batch, so
+ * the message matrix is materialised as in the reference and Linear/BatchNorm stay in torch; these entry
+ * points replace the torch_geometric / torch_scatter operators around them and their autograd. */
+
+/* PointConv.message (model/point_net2.py:27): msg [E, C+3] = [x[col[e]], pos[col[e]] - qpos[row(e)]]. */
+int sn2_edge_msg_fwd(const float *x, const float *pos4, const float *qpos4, const int *rowptr,
+                     const int *col, int Q, int C, float *msg, void *stream);
+/* dx [P, C] += dmsg[e][0:C] at row col[e] (dx zero-initialised by the caller; atomics). */
+int sn2_edge_msg_bwd(const float *dmsg, const int *col, long long E, int C, float *dx, void *stream);
+/* scatter max over CSR rows (PointConv aggr='max', global_max_pool): out [Q,C], arg [Q,C] = first edge
+ * attaining the max (-1 and value 0 for an empty row).  C in {16, 32, 64}. */
+int sn2_segment_max_fwd(const float *vals, const int *rowptr, int Q, int C, float *out, int *arg,
+                        void *stream);
+/* dvals [E,C] (zero-initialised) receives dout at the arg-max edges. */
+int sn2_segment_max_bwd(const float *dout, const int *arg, long long Q, int C, float *dvals, void *stream);
+/* knn_interpolate, k=3 (model/point_net2.py:63): y [Q,C] = ((w0 x0 + w1 x1) + w2 x2) / ((w0 + w1) + w2). */
+int sn2_interp3_fwd(const float *x, int ldx, const int *nbr, const float *w, long long Q, int C, float *y,
+                    void *stream);
+/* dx [S,C] (zero-initialised) += (dy / den) * w_k at rows nbr_k. */
+int sn2_interp3_bwd(const float *dy, const int *nbr, const float *w, long long Q, int C, float *dx,
+                    void *stream);
+/* knn_interpolate, k=1 from the single plot vector at the origin (fp3): y [B*M,C] = (g[b] * w) / w. */
+int sn2_interp_plot_fwd(const float *g, const float *pos4, int B, int M, int C, float *y, void *stream);
+int sn2_interp_plot_bwd(const float *dy, const float *pos4, int B, int M, int C, float *dg, void *stream);
+/* backward of sn2_project_plotwise: dpred [B*N,4] (zero-initialised) from dout [B,4] and parg [B,3,D,D]. */
+int sn2_project_plotwise_bwd(const float *dout, const int *parg, int B, int D, float *dpred, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,298 @@
+// Training-path graph operators with their backward passes.
+//
+// In training mode the MLP blocks run with batch statistics over ALL edge messages of the batch
+// (reference model/point_net2.py:45-53 inside PointConv), so the message matrix is
+// materialised like the reference does and the Linear/BatchNorm arithmetic stays in torch (cuBLAS);
+// what this file replaces is every torch_geometric / torch_scatter operator around it:
+//   edge_msg       x_j ++ (pos_j - pos_i) per edge of the CSR neighbour list        (PointConv.message)
+//   segment_max    per-row max over CSR rows + first-edge arg-max, arg-routed bwd   (scatter max, global_max_pool)
+//   interp3        k=3 inverse-squared-distance interpolation, scatter-add bwd      (knn_interpolate)
+//   interp_plot    k=1 broadcast of the plot vector (w*x)/w, per-plot sum bwd        (knn_interpolate, fp3)
+//   project_plotwise_bwd   arg-routed gradient of the occupied-pixel mean            (scatter_max + scatter_mean)
+#include "sn2_common.cuh"
+
+namespace sn2 {
+
+// ---- edge messages ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+edge_msg_fwd_kernel(const float *__restrict__ x, const float4 *__restrict__ pos, const float4 *__restrict__ qpos,
+                    const int *__restrict__ rowptr, const int *__restrict__ col, int Q, int C, float *__restrict__ msg)
+{
+    const int lane = threadIdx.x & 31;
+    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= Q) return;
+    const int s = __ldg(rowptr + q), e = __ldg(rowptr + q + 1);
+    const float4 qp = __ldg(qpos + q);
+    const int ld = C + 3;
+    for (int j = s + lane; j < e; j += 32) {
+        const int p = __ldg(col + j);
+        float *m = msg + (size_t)j * ld;
+        const float *xr = x + (size_t)p * C;
+        for (int c = 0; c < C; ++c) m[c] = __ldg(xr + c);
+        const float4 pp = __ldg(pos + p);
+        m[C] = pp.x - qp.x;
+        m[C + 1] = pp.y - qp.y;
+        m[C + 2] = pp.z - qp.z;
+    }
+}
+
+// dx[col[e]] += dmsg[e][0:C]   (positions are inputs: no gradient)
+__global__ void __launch_bounds__(256)
+edge_msg_bwd_kernel(const float *__restrict__ dmsg, const int *__restrict__ col, long long E, int C,
+                    float *__restrict__ dx)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= E * C) return;
+    const long long e = t / C;
+    const int c = (int)(t - e * C);
+    atomicAdd(dx + (size_t)__ldg(col + e) * C + c, __ldg(dmsg + (size_t)e * (C + 3) + c));
+}
+
+// ---- segment max with first-edge arg-max -------------------------------------------------------
+// one warp per row; lane l scans edges s+l, s+l+32, ... (ascending), strict '>' keeps the first
+template <int C>
+__global__ void __launch_bounds__(256)
+segment_max_fwd_kernel(const float *__restrict__ vals, const int *__restrict__ rowptr, int Q,
+                       float *__restrict__ out, int *__restrict__ arg)
+{
+    const int lane = threadIdx.x & 31;
+    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= Q) return;
+    const int s = __ldg(rowptr + q), e = __ldg(rowptr + q + 1);
+    constexpr int PER = (C + 31) / 32;  // channels handled per lane in the reduce phase
+    // phase 1: each lane keeps (best, edge) for every channel over its strided edges
+    float bv[C];
+    int be[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { bv[c] = -INFINITY; be[c] = 0x7fffffff; }
+    for (int j = s + lane; j < e; j += 32) {
+        const float *v = vals + (size_t)j * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float t = __ldg(v + c);
+            if (t > bv[c]) { bv[c] = t; be[c] = j; }
+        }
+    }
+    (void)PER;
+    // phase 2: warp arg-max per channel: max value, then lowest edge index among the ties
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const unsigned key = fkey(bv[c]);
+        const unsigned m = __reduce_max_sync(SN2_FULL, key);
+        const unsigned me = __reduce_min_sync(SN2_FULL, (key == m && be[c] != 0x7fffffff) ? (unsigned)be[c] : 0xffffffffu);
+        if (lane == (c & 31)) {
+            // torch_scatter: empty row -> value 0, arg = number of edges (we store -1)
+            out[(size_t)q * C + c] = e > s ? fkey_inv(m) : 0.f;
+            arg[(size_t)q * C + c] = e > s ? (int)me : -1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+segment_max_bwd_kernel(const float *__restrict__ dout, const int *__restrict__ arg, long long QC, int C,
+                       float *__restrict__ dvals)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= QC) return;
+    const int a = __ldg(arg + t);
+    if (a >= 0) dvals[(size_t)a * C + (int)(t % C)] = __ldg(dout + t);  // rows are disjoint: no conflict
+}
+
+// ---- k=3 interpolation ---------------------------------------------------------------------------
+__device__ __forceinline__ float interp_rn(float a0, float a1, float a2, float w0, float w1, float w2, float den)
+{
+    return __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(a0, w0), __fmul_rn(a1, w1)), __fmul_rn(a2, w2)), den);
+}
+
+__global__ void __launch_bounds__(256)
+interp3_fwd_kernel(const float *__restrict__ x, int ldx, const int *__restrict__ nbr, const float *__restrict__ w,
+                   long long Q, int C, float *__restrict__ y)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Q * C) return;
+    const long long q = t / C;
+    const int c = (int)(t - q * C);
+    const int i0 = __ldg(nbr + 3 * q), i1 = __ldg(nbr + 3 * q + 1), i2 = __ldg(nbr + 3 * q + 2);
+    const float w0 = __ldg(w + 3 * q), w1 = __ldg(w + 3 * q + 1), w2 = __ldg(w + 3 * q + 2);
+    const float den = __fadd_rn(__fadd_rn(w0, w1), w2);
+    y[t] = interp_rn(__ldg(x + (size_t)i0 * ldx + c), __ldg(x + (size_t)i1 * ldx + c), __ldg(x + (size_t)i2 * ldx + c), w0,
+                     w1, w2, den);
+}
+
+// dx[nbr_k] += (dy / den) * w_k   (the oracle's autograd: y = num / den, num = sum w*x)
+__global__ void __launch_bounds__(256)
+interp3_bwd_kernel(const float *__restrict__ dy, const int *__restrict__ nbr, const float *__restrict__ w,
+                   long long Q, int C, float *__restrict__ dx)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Q * C) return;
+    const long long q = t / C;
+    const int c = (int)(t - q * C);
+    const float w0 = __ldg(w + 3 * q), w1 = __ldg(w + 3 * q + 1), w2 = __ldg(w + 3 * q + 2);
+    const float g = __fdiv_rn(__ldg(dy + t), __fadd_rn(__fadd_rn(w0, w1), w2));
+    atomicAdd(dx + (size_t)__ldg(nbr + 3 * q) * C + c, g * w0);
+    atomicAdd(dx + (size_t)__ldg(nbr + 3 * q + 1) * C + c, g * w1);
+    atomicAdd(dx + (size_t)__ldg(nbr + 3 * q + 2) * C + c, g * w2);
+}
+
+// ---- k=1 interpolation of the plot vector (fp3) ----------------------------------------------------
+__global__ void __launch_bounds__(256)
+interp_plot_fwd_kernel(const float *__restrict__ g, const float4 *__restrict__ pos, long long Q, int M, int C,
+                       float *__restrict__ y)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Q * C) return;
+    const long long q = t / C;
+    const int c = (int)(t - q * C);
+    const float4 p = __ldg(pos + q);
+    const float w = __fdiv_rn(1.0f, fmaxf(dist2(0.f, 0.f, 0.f, p.x, p.y, p.z), 1e-16f));
+    y[t] = __fdiv_rn(__fmul_rn(__ldg(g + (size_t)(q / M) * C + c), w), w);
+}
+
+// dg[b][c] = sum over the plot's points of (dy / w) * w ; one CTA per (plot, channel), fixed-order tree
+__global__ void __launch_bounds__(256)
+interp_plot_bwd_kernel(const float *__restrict__ dy, const float4 *__restrict__ pos, int M, int C,
+                       float *__restrict__ dg)
+{
+    __shared__ float red[8];
+    const int b = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+    float s = 0.f;
+    for (int i = tid; i < M; i += 256) {
+        const size_t q = (size_t)b * M + i;
+        const float4 p = __ldg(pos + q);
+        const float w = __fdiv_rn(1.0f, fmaxf(dist2(0.f, 0.f, 0.f, p.x, p.y, p.z), 1e-16f));
+        s += __fmul_rn(__fdiv_rn(__ldg(dy + q * C + c), w), w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(SN2_FULL, s, o);
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int k = 0; k < 8; ++k) t += red[k];
+        dg[(size_t)b * C + c] = t;
+    }
+}
+
+// ---- plot-wise coverage backward --------------------------------------------------------------------
+// out[b] = [mean(low), mean(1-low), mean(med), mean(high)] over occupied pixels; grads go to the per-pixel
+// arg-max point of channels 0, 2, 3 (parg from the forward).  dpred must be zero-initialised.
+__global__ void __launch_bounds__(256)
+project_plotwise_bwd_kernel(const float *__restrict__ dout, const int *__restrict__ parg, int D,
+                            float *__restrict__ dpred)
+{
+    __shared__ int s_cnt;
+    const int b = blockIdx.x, tid = threadIdx.x, P = D * D;
+    const int *pa = parg + (size_t)b * 3 * P;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    int c = 0;
+    for (int p = tid; p < P; p += 256) c += pa[p] >= 0;
+    atomicAdd(&s_cnt, c);
+    __syncthreads();
+    const float inv = 1.0f / fmaxf((float)s_cnt, 1.f);
+    const float g_low = (dout[b * 4 + 0] - dout[b * 4 + 1]) * inv;  // bare = 1 - low
+    const float g_med = dout[b * 4 + 2] * inv, g_high = dout[b * 4 + 3] * inv;
+    for (int p = tid; p < P; p += 256) {
+        const int a0 = pa[p];
+        if (a0 < 0) continue;
+        // distinct pixels can share an arg-max point only across bands, which hit different columns
+        atomicAdd(dpred + (size_t)a0 * 4 + 0, g_low);
+        atomicAdd(dpred + (size_t)pa[P + p] * 4 + 2, g_med);
+        atomicAdd(dpred + (size_t)pa[2 * P + p] * 4 + 3, g_high);
+    }
+}
+
+static inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace sn2
+
+using namespace sn2;
+
+extern "C" int sn2_edge_msg_fwd(const float *x, const float *pos4, const float *qpos4, const int *rowptr,
+                                const int *col, int Q, int C, float *msg, void *stream)
+{
+    if (!x || !pos4 || !qpos4 || !rowptr || !col || !msg || Q <= 0 || C <= 0) return SN2_EINVAL;
+    edge_msg_fwd_kernel<<<blocks_for((long long)Q * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, reinterpret_cast<const float4 *>(pos4), reinterpret_cast<const float4 *>(qpos4), rowptr, col, Q, C, msg);
+    SN2_LAUNCH_CHECK("edge_msg_fwd_kernel");
+    return SN2_OK;
+}
+
+extern "C" int sn2_edge_msg_bwd(const float *dmsg, const int *col, long long E, int C, float *dx, void *stream)
+{
+    if (!dmsg || !col || !dx || E < 0 || C <= 0) return SN2_EINVAL;
+    if (E == 0) return SN2_OK;
+    edge_msg_bwd_kernel<<<blocks_for(E * C, 256), 256, 0, (cudaStream_t)stream>>>(dmsg, col, E, C, dx);
+    SN2_LAUNCH_CHECK("edge_msg_bwd_kernel");
+    return SN2_OK;
+}
+
+extern "C" int sn2_segment_max_fwd(const float *vals, const int *rowptr, int Q, int C, float *out, int *arg,
+                                   void *stream)
+{
+    if (!vals || !rowptr || !out || !arg || Q <= 0) return SN2_EINVAL;
+    const unsigned blocks = blocks_for((long long)Q * 32, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (C) {
+    case 16: segment_max_fwd_kernel<16><<<blocks, 256, 0, st>>>(vals, rowptr, Q, out, arg); break;
+    case 32: segment_max_fwd_kernel<32><<<blocks, 256, 0, st>>>(vals, rowptr, Q, out, arg); break;
+    case 64: segment_max_fwd_kernel<64><<<blocks, 256, 0, st>>>(vals, rowptr, Q, out, arg); break;
+    default: return SN2_EUNSUPPORTED;
+    }
+    SN2_LAUNCH_CHECK("segment_max_fwd_kernel");
+    return SN2_OK;
+}
+
+extern "C" int sn2_segment_max_bwd(const float *dout, const int *arg, long long Q, int C, float *dvals, void *stream)
+{
+    if (!dout || !arg || !dvals || Q <= 0 || C <= 0) return SN2_EINVAL;
+    segment_max_bwd_kernel<<<blocks_for(Q * C, 256), 256, 0, (cudaStream_t)stream>>>(dout, arg, Q * C, C, dvals);
+    SN2_LAUNCH_CHECK("segment_max_bwd_kernel");
+    return SN2_OK;
+}
+
+extern "C" int sn2_interp3_fwd(const float *x, int ldx, const int *nbr, const float *w, long long Q, int C, float *y,
+                               void *stream)
+{
+    if (!x || !nbr || !w || !y || Q <= 0 || C <= 0 || ldx < C) return SN2_EINVAL;
+    interp3_fwd_kernel<<<blocks_for(Q * C, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, nbr, w, Q, C, y);
+    SN2_LAUNCH_CHECK("interp3_fwd_kernel");
+    return SN2_OK;
+}
+
+extern "C" int sn2_interp3_bwd(const float *dy, const int *nbr, const float *w, long long Q, int C, float *dx,
+                               void *stream)
+{
+    if (!dy || !nbr || !w || !dx || Q <= 0 || C <= 0) return SN2_EINVAL;
+    interp3_bwd_kernel<<<blocks_for(Q * C, 256), 256, 0, (cudaStream_t)stream>>>(dy, nbr, w, Q, C, dx);
+    SN2_LAUNCH_CHECK("interp3_bwd_kernel");
+    return SN2_OK;
+}
+
+extern "C" int sn2_interp_plot_fwd(const float *g, const float *pos4, int B, int M, int C, float *y, void *stream)
+{
+    if (!g || !pos4 || !y || B <= 0 || M <= 0 || C <= 0) return SN2_EINVAL;
+    const long long Q = (long long)B * M;
+    interp_plot_fwd_kernel<<<blocks_for(Q * C, 256), 256, 0, (cudaStream_t)stream>>>(
+        g, reinterpret_cast<const float4 *>(pos4), Q, M, C, y);
+    SN2_LAUNCH_CHECK("interp_plot_fwd_kernel");
+    return SN2_OK;
+}
+
+extern "C" int sn2_interp_plot_bwd(const float *dy, const float *pos4, int B, int M, int C, float *dg, void *stream)
+{
+    if (!dy || !pos4 || !dg || B <= 0 || M <= 0 || C <= 0) return SN2_EINVAL;
+    interp_plot_bwd_kernel<<<dim3(B, C), 256, 0, (cudaStream_t)stream>>>(dy, reinterpret_cast<const float4 *>(pos4), M, C,
+                                                                        dg);
+    SN2_LAUNCH_CHECK("interp_plot_bwd_kernel");
+    return SN2_OK;
+}
+
+extern "C" int sn2_project_plotwise_bwd(const float *dout, const int *parg, int B, int D, float *dpred, void *stream)
+{
+    if (!dout || !parg || !dpred || B <= 0 || D <= 0) return SN2_EINVAL;
+    project_plotwise_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(dout, parg, D, dpred);
+    SN2_LAUNCH_CHECK("project_plotwise_bwd_kernel");
+    return SN2_OK;
+}

@@ -6,8 +6,12 @@ constructor arguments, same sub-module tree and therefore the same 53 ``state_di
 ``forward(cloud_data)`` contract.  The arithmetic is not torch: ``forward`` runs the fused sm_100a
 kernels of libsn2_b200.so (sn2/pipeline.py).  The nn.Module containers below only own parameters.
 
-Not supported (raises, never falls back): CPU execution (``args.cuda is None`` models can be built,
-saved and loaded, but not run), ragged plots, and -- until the backward kernels land -- training mode.
+Eval mode runs the fully fused kernels; training mode (autograd) materialises the edge messages like the
+reference (BatchNorm batch statistics need them), runs every graph operator and its backward in
+libsn2_b200.so and leaves Linear/BatchNorm to the model's own torch modules (sn2/pipeline.py).
+
+Not supported (raises, never falls back): CPU execution (``args.cuda is None`` models can be built, saved
+and loaded, but not run) and ragged plots.
 """
 from __future__ import annotations
 
@@ -108,14 +112,17 @@ class PointNet2(nn.Module):
         both (B*N,4) on the device, plot-major (reference :106-153)."""
         if self.cuda_device is None:
             raise RuntimeError("sn2 PointNet2.forward needs a CUDA device (args.cuda); this build has no CPU path")
-        if self.training:
-            raise NotImplementedError("sn2 PointNet2: training-mode forward/backward kernels are not built yet")
-        if self.drop and self.training:
-            raise NotImplementedError("sn2 PointNet2: dropout > 0 is not supported")
         device = torch.device("cuda", self.cuda_device)
         with torch.cuda.device(device):
-            cov, proba, g, cloud_dev = _pipeline.forward_eval(
-                self, cloud_data["xyz"], cloud_data["cloud"], device, SAModule.max_num_neighbors, trace, timer)
+            if self.training and torch.is_grad_enabled():
+                cov, proba, g, cloud_dev = _pipeline.forward_train(
+                    self, cloud_data["xyz"], cloud_data["cloud"], device, SAModule.max_num_neighbors, trace)
+            elif self.training:
+                raise RuntimeError("sn2 PointNet2: training mode under no_grad is not supported (BatchNorm batch "
+                                   "statistics are only implemented on the autograd path); call model.eval()")
+            else:
+                cov, proba, g, cloud_dev = _pipeline.forward_eval(
+                    self, cloud_data["xyz"], cloud_data["cloud"], device, SAModule.max_num_neighbors, trace, timer)
         if self.log_embeddings:
             self.last_G_tensor = g
         # device copy of the normalised cloud, reused by model.project_to_2d to skip a second H2D

@@ -27,10 +27,12 @@ def project_to_plotwise_coverages(pred_pointwise, clouds, args):
     """pred_pointwise (B*N,4) device, clouds (B,F,N) host or device -> (B,4) device fp32
     [low, bare = 1 - low, medium, high] (reference :7-55)."""
     dev = _device_of(args, pred_pointwise)
-    if pred_pointwise.requires_grad and torch.is_grad_enabled():
-        raise NotImplementedError("sn2 project_to_plotwise_coverages: backward kernel is not built yet")
     with torch.cuda.device(dev):
         clouds_d = clouds.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        if pred_pointwise.requires_grad and torch.is_grad_enabled():
+            from sn2.autograd_ops import ProjectPlotwise
+
+            return ProjectPlotwise.apply(pred_pointwise.to(device=dev, dtype=torch.float32), clouds_d, int(args.diam_pix))
         pred = pred_pointwise.detach().to(device=dev, dtype=torch.float32).contiguous()
         return _ops.project_plotwise(clouds_d, pred, int(args.diam_pix))
 

@@ -38,6 +38,15 @@ SIGNATURES = {
     "sn2_knn3_grid": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "sn2_fp2_fwd": [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp],
     "sn2_fp1_head_fwd": [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp],
+    "sn2_edge_msg_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp],
+    "sn2_edge_msg_bwd": [_vp, _vp, _ll, _i, _vp, _vp],
+    "sn2_segment_max_fwd": [_vp, _vp, _i, _i, _vp, _vp, _vp],
+    "sn2_segment_max_bwd": [_vp, _vp, _ll, _i, _vp, _vp],
+    "sn2_interp3_fwd": [_vp, _i, _vp, _vp, _ll, _i, _vp, _vp],
+    "sn2_interp3_bwd": [_vp, _vp, _vp, _ll, _i, _vp, _vp],
+    "sn2_interp_plot_fwd": [_vp, _vp, _i, _i, _i, _vp, _vp],
+    "sn2_interp_plot_bwd": [_vp, _vp, _i, _i, _i, _vp, _vp],
+    "sn2_project_plotwise_bwd": [_vp, _vp, _i, _i, _vp, _vp],
     "sn2_project_plotwise": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "sn2_project_rasters": [_vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp],
 }

@@ -1,0 +1,153 @@
+"""torch.autograd.Function wrappers of the training-path operators (csrc/train_ops.cu).
+
+Each Function calls one forward and one backward kernel of libsn2_b200.so; torch only carries the
+autograd graph and owns the memory.  Index tensors (neighbour lists, arg-max, kNN) are int32 and carry no
+gradient; positions are inputs and get none either (as in the reference, where they are leaf data).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, ops
+from ._lib import check, dptr, stream_ptr
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    return t.contiguous()
+
+
+class EdgeMsg(torch.autograd.Function):
+    """msg[e] = [x[col[e]], pos[col[e]] - qpos[row(e)]]  (PointConv.message)."""
+
+    @staticmethod
+    def forward(ctx, x, pos4, qpos4, rowptr, col):
+        lib = _lib.load()
+        x = _c(x)
+        E, C = col.numel(), x.shape[1]
+        msg = torch.empty((E, C + 3), dtype=torch.float32, device=x.device)
+        check(lib.sn2_edge_msg_fwd(dptr(x, torch.float32), dptr(pos4), dptr(qpos4), dptr(rowptr, torch.int32),
+                                   dptr(col, torch.int32), qpos4.shape[0], C, dptr(msg), stream_ptr()), "sn2_edge_msg_fwd")
+        ops._count(1)
+        ctx.save_for_backward(col)
+        ctx.shape = (x.shape[0], C)
+        return msg
+
+    @staticmethod
+    def backward(ctx, dmsg):
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None, None
+        lib = _lib.load()
+        (col,) = ctx.saved_tensors
+        P, C = ctx.shape
+        dx = torch.zeros((P, C), dtype=torch.float32, device=dmsg.device)
+        check(lib.sn2_edge_msg_bwd(dptr(_c(dmsg), torch.float32), dptr(col), col.numel(), C, dptr(dx), stream_ptr()),
+              "sn2_edge_msg_bwd")
+        ops._count(1)
+        return dx, None, None, None, None
+
+
+class SegmentMax(torch.autograd.Function):
+    """Per-row max over CSR rows with first-edge arg-max; gradient routed to the arg-max edges (A3, A4, A6)."""
+
+    @staticmethod
+    def forward(ctx, vals, rowptr):
+        lib = _lib.load()
+        vals = _c(vals)
+        Q, C = rowptr.numel() - 1, vals.shape[1]
+        out = torch.empty((Q, C), dtype=torch.float32, device=vals.device)
+        arg = torch.empty((Q, C), dtype=torch.int32, device=vals.device)
+        check(lib.sn2_segment_max_fwd(dptr(vals, torch.float32), dptr(rowptr, torch.int32), Q, C, dptr(out), dptr(arg),
+                                      stream_ptr()), "sn2_segment_max_fwd")
+        ops._count(1)
+        ctx.save_for_backward(arg)
+        ctx.E = vals.shape[0]
+        ctx.mark_non_differentiable(arg)
+        return out, arg
+
+    @staticmethod
+    def backward(ctx, dout, _darg):
+        lib = _lib.load()
+        (arg,) = ctx.saved_tensors
+        Q, C = arg.shape
+        dvals = torch.zeros((ctx.E, C), dtype=torch.float32, device=dout.device)
+        check(lib.sn2_segment_max_bwd(dptr(_c(dout), torch.float32), dptr(arg), Q, C, dptr(dvals), stream_ptr()),
+              "sn2_segment_max_bwd")
+        ops._count(1)
+        return dvals, None
+
+
+class Interp3(torch.autograd.Function):
+    """knn_interpolate with k = 3 on precomputed neighbours / weights (A5); gradient to the features only."""
+
+    @staticmethod
+    def forward(ctx, x, nbr, w):
+        lib = _lib.load()
+        x = _c(x)
+        Q, C = nbr.shape[0], x.shape[1]
+        y = torch.empty((Q, C), dtype=torch.float32, device=x.device)
+        check(lib.sn2_interp3_fwd(dptr(x, torch.float32), C, dptr(nbr, torch.int32), dptr(w, torch.float32), Q, C, dptr(y),
+                                  stream_ptr()), "sn2_interp3_fwd")
+        ops._count(1)
+        ctx.save_for_backward(nbr, w)
+        ctx.S = x.shape[0]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        nbr, w = ctx.saved_tensors
+        Q, C = dy.shape
+        dx = torch.zeros((ctx.S, C), dtype=torch.float32, device=dy.device)
+        check(lib.sn2_interp3_bwd(dptr(_c(dy), torch.float32), dptr(nbr), dptr(w), Q, C, dptr(dx), stream_ptr()),
+              "sn2_interp3_bwd")
+        ops._count(1)
+        return dx, None, None
+
+
+class InterpPlot(torch.autograd.Function):
+    """knn_interpolate with k = 1 from the single per-plot vector at the origin (fp3): y = (g * w) / w."""
+
+    @staticmethod
+    def forward(ctx, g, pos4, M):
+        lib = _lib.load()
+        g = _c(g)
+        B, C = g.shape
+        y = torch.empty((B * M, C), dtype=torch.float32, device=g.device)
+        check(lib.sn2_interp_plot_fwd(dptr(g, torch.float32), dptr(pos4), B, M, C, dptr(y), stream_ptr()), "sn2_interp_plot_fwd")
+        ops._count(1)
+        ctx.save_for_backward(pos4)
+        ctx.dims = (B, M, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        (pos4,) = ctx.saved_tensors
+        B, M, C = ctx.dims
+        dg = torch.empty((B, C), dtype=torch.float32, device=dy.device)
+        check(lib.sn2_interp_plot_bwd(dptr(_c(dy), torch.float32), dptr(pos4), B, M, C, dptr(dg), stream_ptr()),
+              "sn2_interp_plot_bwd")
+        ops._count(1)
+        return dg, None, None
+
+
+class ProjectPlotwise(torch.autograd.Function):
+    """project_to_plotwise_coverages with its arg-routed backward (A6 + A7)."""
+
+    @staticmethod
+    def forward(ctx, pred, cloud_dev, D):
+        out, _pix, _pmax, parg = ops.project_plotwise(cloud_dev, _c(pred.detach()), D, want_aux=True)
+        ctx.save_for_backward(parg)
+        ctx.n = pred.shape[0]
+        ctx.D = D
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        (parg,) = ctx.saved_tensors
+        dpred = torch.zeros((ctx.n, 4), dtype=torch.float32, device=dout.device)
+        check(lib.sn2_project_plotwise_bwd(dptr(_c(dout), torch.float32), dptr(parg), parg.shape[0], ctx.D, dptr(dpred),
+                                           stream_ptr()), "sn2_project_plotwise_bwd")
+        ops._count(1)
+        return dpred, None, None

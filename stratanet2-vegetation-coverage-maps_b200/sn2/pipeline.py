@@ -159,3 +159,53 @@ def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_
             nbr1=nbr1, w1=w1, M1=M1, M2=M2,
         )
     return cov, proba, g, cloud_d
+
+
+def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_neighbors: int = 2000,
+                  trace: ForwardTrace | None = None):
+    """Training-mode forward with autograd (reference :106-153 under ``model.train()``).
+
+    BatchNorm needs batch statistics over every edge message / point of the batch, so the
+    message matrices are materialised like the reference does and the Linear -> ReLU -> BatchNorm blocks are
+    the model's own torch modules (cuBLAS GEMMs, running-stat updates and SyncBatchNorm all behave exactly
+    as in the reference).  Everything the reference delegates to torch_cluster / torch_scatter /
+    torch_geometric -- FPS, ball query, kNN, message gather, max aggregation with arg-routed gradient,
+    interpolation -- runs in libsn2_b200.so (forward and backward)."""
+    import torch.nn.functional as F
+
+    from .autograd_ops import EdgeMsg, Interp3, InterpPlot, SegmentMax
+
+    B, Fc, N = cloud.shape
+    if N != model.subsample_size:
+        raise RuntimeError(f"PointNet2.forward: every plot must have subsample_size={model.subsample_size} points, got {N}")
+    xyz_d = xyz.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+    cloud_d = cloud.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+    sa1, sa2 = model.sa1_module, model.sa2_module
+    with torch.no_grad():
+        pos0, feat0 = ops.ingest(xyz_d, cloud_d)
+        M1 = ops.m_of(N, sa1.ratio)
+        M2 = ops.m_of(M1, sa2.ratio)
+        idx1, pos1 = ops.fps_dense(pos0, B, N, M1)
+        idx2, pos2 = ops.fps_dense(pos1, B, M1, M2)
+        rowptr1, col1 = ops.ball_query_dense(pos0, pos1, B, N, M1, sa1.r, max_num_neighbors)
+        rowptr2, col2 = ops.ball_query_dense(pos1, pos2, B, M1, M2, sa2.r, max_num_neighbors)
+        nbr2, w2 = ops.knn3_dense(pos2, pos1, B, M2, M1)
+        nbr1, w1 = ops.knn3_dense(pos1, pos0, B, M1, N)
+        plot_ptr = torch.arange(B + 1, dtype=torch.int32, device=device) * M2
+
+    x1, _ = SegmentMax.apply(sa1.conv.local_nn(EdgeMsg.apply(feat0, pos0, pos1, rowptr1, col1)), rowptr1)
+    x2, _ = SegmentMax.apply(sa2.conv.local_nn(EdgeMsg.apply(x1, pos1, pos2, rowptr2, col2)), rowptr2)
+    g, _ = SegmentMax.apply(model.sa3_module.nn(torch.cat([x2, pos2[:, :3]], dim=1)), plot_ptr)
+    f3 = model.fp3_module.nn(torch.cat([InterpPlot.apply(g, pos2, M2), x2], dim=1))
+    f2 = model.fp2_module.nn(torch.cat([Interp3.apply(f3, nbr2, w2), x1], dim=1))
+    f1 = model.fp1_module.nn(torch.cat([Interp3.apply(f2, nbr1, w1), feat0], dim=1))
+    h = F.relu(model.lin1(f1))
+    h = F.dropout(h, p=model.drop, training=True)
+    scores = model.lin2(h)
+    proba = torch.softmax(scores[:, :4], dim=1)
+    cov = proba * torch.sigmoid(scores[:, 4:5])
+    if trace is not None:
+        trace.tensors.update(cloud_dev=cloud_d, pos0=pos0, feat0=feat0, idx1=idx1, pos1=pos1, rowptr1=rowptr1, col1=col1,
+                             x1=x1, idx2=idx2, pos2=pos2, rowptr2=rowptr2, col2=col2, x2=x2, G=g, fp3=f3, fp2=f2, fp1=f1,
+                             nbr1=nbr1, w1=w1, nbr2=nbr2, w2=w2, M1=M1, M2=M2)
+    return cov, proba, g, cloud_d

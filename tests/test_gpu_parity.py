@@ -270,3 +270,80 @@ def test_sa_fused_equals_list_path(cuda_device, N, K, variant):
         msg = port.sa1_module.conv.local_nn(torch.cat([x0[c], posl[c] - posl[idx][row]], dim=1))
         want = tp.scatter_max(msg, row, dim=0, dim_size=idx.numel())[0]
     torch.testing.assert_close(x1_fused.cpu(), want, rtol=RTOL, atol=ATOL)
+
+
+def _train_loss(cov, proba, pw, gt, pdf):
+    """The reference training loss (learning/train.py:52-66, learning/loss_functions.py:9-57) with a
+    synthetic pdf tensor in place of the KDE mixture."""
+    mae = torch.sqrt((pw[:, [0, 2, 3]] - gt[:, [0, 2, 3]]) ** 2 + 1e-4).mean()
+    nll = -torch.log((proba[:, [0, 2, 3]].double() * pdf).sum(1) + 1e-6).mean().float()
+    p = proba[:, 2:]
+    ent = -(p * torch.log(p + 1e-6)).sum(1).mean()
+    return mae + 0.10 * nll + 0.04 * ent
+
+
+@pytest.mark.parametrize("B,N,variant", [(2, 2048, "plain"), (3, 1500, "cm")])
+def test_training_step_gradients_match_oracle(cuda_device, B, N, variant):
+    """Config-3-style step: train-mode forward (BatchNorm batch stats), plot-wise projection, reference loss,
+    backward.  All 32 parameter gradients, the running statistics and the loss match the CPU oracle."""
+    from model.project_to_2d import project_to_plotwise_coverages
+    from oracle.pointnet2_port import project_to_plotwise_coverages_port
+
+    args, net, port = _make_models(N, cuda_device)
+    from sn2.synth import randomize_bn_
+    net.train(); port.train()
+    data = _plots(3, B, N, variant)
+    g = torch.Generator().manual_seed(9)
+    gt = torch.rand(B, 4, generator=g)
+    z = data["xyz"][:, 2, :].reshape(-1, 1).double()
+    pdf = torch.cat([torch.exp(-z), 0.5 * torch.exp(-0.5 * (z - 1.0) ** 2), 0.1 + 0.05 * z], dim=1)
+
+    cov_o, proba_o = port(data)
+    loss_o = _train_loss(cov_o, proba_o, project_to_plotwise_coverages_port(cov_o, data["cloud"], default_args_cpu(N)), gt, pdf)
+    loss_o.backward()
+
+    cov, proba = net(data)
+    pw = project_to_plotwise_coverages(cov, data["cloud"], args)
+    loss = _train_loss(cov, proba, pw, gt.to(cuda_device), pdf.to(cuda_device))
+    loss.backward()
+
+    torch.testing.assert_close(loss.detach().cpu(), loss_o.detach(), rtol=RTOL, atol=ATOL)
+    go = dict(port.named_parameters())
+    checked = 0
+    for name, p in net.named_parameters():
+        want = go[name].grad
+        assert p.grad is not None, name
+        scale = want.abs().max().item() + 1e-12
+        err = (p.grad.cpu() - want).abs().max().item()
+        assert err <= 2e-3 * scale + 1e-7, f"{name}: max err {err:.3e} vs scale {scale:.3e}"
+        checked += 1
+    assert checked == 32
+    for (n1, b1), (n2, b2) in zip(net.named_buffers(), port.named_buffers()):
+        assert n1 == n2
+        torch.testing.assert_close(b1.cpu(), b2, rtol=RTOL, atol=1e-6, msg=n1)
+
+
+def default_args_cpu(N):
+    from sn2.config import default_args
+
+    return default_args(subsample_size=N)
+
+
+def test_training_ops_known_answers(cuda_device):
+    from sn2.autograd_ops import Interp3, SegmentMax
+
+    vals = torch.tensor([[1., 5.], [3., 5.], [3., -1.], [7., 0.]], device=cuda_device, requires_grad=True)
+    vals16 = torch.nn.functional.pad(vals, (0, 14), value=-9.0)
+    rowptr = torch.tensor([0, 3, 3, 4], dtype=torch.int32, device=cuda_device)
+    out, arg = SegmentMax.apply(vals16, rowptr)
+    assert out[:, :2].tolist() == [[3., 5.], [0., 0.], [7., 0.]]       # empty row -> 0
+    assert arg[:, :2].tolist() == [[1, 0], [-1, -1], [3, 3]]           # ties -> first edge
+    (out[:, :2] * torch.tensor([[1., 10.], [100., 1000.], [1e4, 1e5]], device=cuda_device)).sum().backward()
+    assert vals.grad.tolist() == [[0., 10.], [1., 0.], [0., 0.], [1e4, 1e5]]
+    x = torch.tensor([[1.], [2.], [6.], [100.]], device=cuda_device, requires_grad=True)
+    nbr = torch.tensor([[0, 1, 2]], dtype=torch.int32, device=cuda_device)
+    w = torch.ones(1, 3, device=cuda_device)
+    y = Interp3.apply(x, nbr, w)
+    assert torch.allclose(y, torch.tensor([[3.]], device=cuda_device))
+    y.sum().backward()
+    assert torch.allclose(x.grad.view(-1), torch.tensor([1 / 3, 1 / 3, 1 / 3, 0.], device=cuda_device))
