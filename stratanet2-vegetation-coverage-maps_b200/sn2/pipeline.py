@@ -162,7 +162,7 @@ def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_
 
 
 def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_neighbors: int = 2000,
-                  trace: ForwardTrace | None = None):
+                  trace: ForwardTrace | None = None, timer=None):
     """Training-mode forward with autograd (reference :106-153 under ``model.train()``).
 
     BatchNorm needs batch statistics over every edge message / point of the batch, so the
@@ -181,16 +181,23 @@ def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num
     xyz_d = xyz.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
     cloud_d = cloud.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
     sa1, sa2 = model.sa1_module, model.sa2_module
+    T = timer if timer is not None else _NOTIMER
     with torch.no_grad():
-        pos0, feat0 = ops.ingest(xyz_d, cloud_d)
+        with T.stage("ingest"):
+            pos0, feat0 = ops.ingest(xyz_d, cloud_d)
         M1 = ops.m_of(N, sa1.ratio)
         M2 = ops.m_of(M1, sa2.ratio)
-        idx1, pos1 = ops.fps_dense(pos0, B, N, M1)
-        idx2, pos2 = ops.fps_dense(pos1, B, M1, M2)
-        rowptr1, col1 = ops.ball_query_dense(pos0, pos1, B, N, M1, sa1.r, max_num_neighbors)
-        rowptr2, col2 = ops.ball_query_dense(pos1, pos2, B, M1, M2, sa2.r, max_num_neighbors)
-        nbr2, w2 = ops.knn3_dense(pos2, pos1, B, M2, M1)
-        nbr1, w1 = ops.knn3_dense(pos1, pos0, B, M1, N)
+        with T.stage("fps1"):
+            idx1, pos1 = ops.fps_dense(pos0, B, N, M1)
+        with T.stage("fps2"):
+            idx2, pos2 = ops.fps_dense(pos1, B, M1, M2)
+        with T.stage("ball1"):
+            rowptr1, col1 = ops.ball_query_dense(pos0, pos1, B, N, M1, sa1.r, max_num_neighbors)
+        with T.stage("ball2"):
+            rowptr2, col2 = ops.ball_query_dense(pos1, pos2, B, M1, M2, sa2.r, max_num_neighbors)
+        with T.stage("knn"):
+            nbr2, w2 = ops.knn3_dense(pos2, pos1, B, M2, M1)
+            nbr1, w1 = ops.knn3_dense(pos1, pos0, B, M1, N)
         plot_ptr = torch.arange(B + 1, dtype=torch.int32, device=device) * M2
 
     x1, _ = SegmentMax.apply(sa1.conv.local_nn(EdgeMsg.apply(feat0, pos0, pos1, rowptr1, col1)), rowptr1)

@@ -347,3 +347,19 @@ def test_training_ops_known_answers(cuda_device):
     assert torch.allclose(y, torch.tensor([[3.]], device=cuda_device))
     y.sum().backward()
     assert torch.allclose(x.grad.view(-1), torch.tensor([1 / 3, 1 / 3, 1 / 3, 0.], device=cuda_device))
+
+
+def test_data_parallel_training_matches_single_gpu(cuda_device):
+    """2-rank NCCL run (skipped on a 1-GPU box): sharded plots + SyncBatchNorm + one flat gradient all-reduce
+    reproduce the single-GPU full-batch gradients and running statistics."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29731", os.path.join(root, "tests", "dist_train_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert "DIST_TRAIN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
