@@ -169,7 +169,7 @@ def run_reference(opts, cfg):
     from sn2.synth import synth_batch
 
     N = cfg["N"]
-    plots = 2  # bounded sample: each step = 2 plots of the same workload
+    plots = 8  # bounded sample: each step = 8 plots of the same workload (OpenMP over plots / queries)
     torch.set_num_threads(os.cpu_count())
     kind, net, plotwise, raster, args = cpu_model(N)
     data = synth_batch(opts.config, plots, N)
@@ -456,7 +456,7 @@ def main():
         "roofline": roof,
     }
     if rank == 0 and world == 1 and not opts.no_cpu_baseline:
-        sample_plots = 2
+        sample_plots = 16 if cfg["B"] >= 16 else cfg["B"]
         kind, v, best = time_cpu(N, opts.config, sample_plots, repeats=2)
         out["cpu_baseline"] = {"value": v, "unit": "plots/s", "cores": os.cpu_count(), "kind": kind,
                                "sample": f"{sample_plots} plots x {N} pts, best of 2 after 1 warm-up ({best:.2f} s); "

@@ -20,6 +20,7 @@ import os
 import torch
 import torch.nn as nn
 
+from sn2 import ops as _ops
 from sn2 import pipeline as _pipeline
 
 
@@ -32,6 +33,10 @@ class PointConv(nn.Module):
         if add_self_loops or global_nn is not None:
             raise NotImplementedError("sn2 PointConv: only add_self_loops=False, global_nn=None (the reference setting)")
         self.local_nn = local_nn
+
+    def forward(self, x, pos, edge_index):
+        """Operator-level form (reference :27): message MLP over the edges + max aggregation, differentiable."""
+        return _ops.pointconv(self.local_nn, x, pos, edge_index)
 
 
 def MLP(channels, batch_norm=True):
@@ -55,6 +60,14 @@ class SAModule(nn.Module):
         self.r = r
         self.conv = PointConv(nn, add_self_loops=False)
 
+    def forward(self, x, pos, batch):
+        """Operator-level form of reference :21-29 on (x, pos, batch) long-form tensors (dense batches).
+        ``PointNet2.forward`` does not go through here: it runs the fused kernels (sn2/pipeline.py)."""
+        idx = _ops.fps(pos, batch, ratio=self.ratio)
+        row, col = _ops.radius(pos, pos[idx], self.r, batch, batch[idx], max_num_neighbors=self.max_num_neighbors)
+        x = self.conv(x, (pos, pos[idx]), torch.stack([col, row], dim=0))
+        return x, pos[idx], batch[idx]
+
 
 class GlobalSAModule(nn.Module):
     """MLP on [x, pos] then per-plot max (reference :32-42)."""
@@ -62,6 +75,11 @@ class GlobalSAModule(nn.Module):
     def __init__(self, nn):
         super().__init__()
         self.nn = nn
+
+    def forward(self, x, pos, batch):
+        """Operator-level form of reference :37-42."""
+        x = _ops.global_max_pool(self.nn(torch.cat([x, pos], dim=1)), batch)
+        return x, pos.new_zeros((x.size(0), 3)), torch.arange(x.size(0), device=batch.device)
 
 
 class FPModule(nn.Module):
@@ -71,6 +89,13 @@ class FPModule(nn.Module):
         super().__init__()
         self.k = k
         self.nn = nn
+
+    def forward(self, x, pos, batch, x_skip, pos_skip, batch_skip):
+        """Operator-level form of reference :62-67."""
+        x = _ops.knn_interpolate(x, pos, pos_skip, batch, batch_skip, k=self.k)
+        if x_skip is not None:
+            x = torch.cat([x, x_skip], dim=1)
+        return self.nn(x), pos_skip, batch_skip
 
 
 class PointNet2(nn.Module):

@@ -326,3 +326,50 @@ def knn(x, y, k, batch_x=None, batch_y=None, cosine=False, num_workers=1):
     nbr, _ = knn3_dense(to_pos4(x), to_pos4(y), B, ms, nq)
     row = torch.arange(B * nq, device=x.device, dtype=torch.int64).repeat_interleave(3)
     return torch.stack([row, nbr.reshape(-1).to(torch.int64)], dim=0)
+
+
+def knn_interpolate(x, pos_x, pos_y, batch_x=None, batch_y=None, k=3, num_workers=1):
+    """Drop-in for torch_geometric ``knn_interpolate`` (/root/reference/model/point_net2.py:63), differentiable
+    w.r.t. ``x``.  k = 3 (general sources) or k = 1 with a single source per plot (the fp3 broadcast)."""
+    from .autograd_ops import Interp3, InterpPlot
+
+    B, ms = _dense_shape(batch_x, pos_x.shape[0])
+    By, nq = _dense_shape(batch_y, pos_y.shape[0])
+    if B != By:
+        raise RuntimeError("sn2: batch_x and batch_y describe different numbers of plots")
+    if k == 1 and ms == 1:
+        if bool((pos_x != 0).any()):
+            raise RuntimeError("sn2: k=1 interpolation is implemented for a single source at the origin (GlobalSAModule output)")
+        return InterpPlot.apply(x, to_pos4(pos_y), nq)
+    if k != 3:
+        raise RuntimeError("sn2: knn_interpolate supports k=3, or k=1 from one source per plot")
+    with torch.no_grad():
+        nbr, w = knn3_dense(to_pos4(pos_x), to_pos4(pos_y), B, ms, nq)
+    return Interp3.apply(x, nbr, w)
+
+
+def global_max_pool(x, batch, size=None):
+    """Drop-in for torch_geometric ``global_max_pool`` (/root/reference/model/point_net2.py:39), differentiable."""
+    from .autograd_ops import SegmentMax
+
+    B, m = _dense_shape(batch, x.shape[0])
+    ptr = torch.arange(B + 1, dtype=torch.int32, device=x.device) * m
+    return SegmentMax.apply(x, ptr)[0]
+
+
+def pointconv(local_nn, x, pos, edge_index):
+    """torch_geometric ``PointConv(local_nn, add_self_loops=False)(x, (pos_src, pos_dst), edge_index)`` with
+    ``edge_index = [source point ; target centroid]`` grouped by target as ``radius`` returns it
+    (/root/reference/model/point_net2.py:26-27).  Differentiable w.r.t. x and the parameters of local_nn."""
+    from .autograd_ops import EdgeMsg, SegmentMax
+
+    pos_src, pos_dst = pos if isinstance(pos, (tuple, list)) else (pos, pos)
+    src, dst = edge_index[0], edge_index[1]
+    if dst.numel() > 1 and bool((dst[1:] < dst[:-1]).any()):
+        raise RuntimeError("sn2 PointConv: edges must be grouped by target (the layout radius() returns)")
+    Q = pos_dst.shape[0]
+    cnt = torch.bincount(dst, minlength=Q)
+    rowptr = torch.zeros(Q + 1, dtype=torch.int32, device=dst.device)
+    rowptr[1:] = torch.cumsum(cnt, 0).to(torch.int32)
+    msg = EdgeMsg.apply(x, to_pos4(pos_src), to_pos4(pos_dst), rowptr, src.to(torch.int32).contiguous())
+    return SegmentMax.apply(local_nn(msg), rowptr)[0]

@@ -363,3 +363,34 @@ def test_data_parallel_training_matches_single_gpu(cuda_device):
            "--master-port", "29731", os.path.join(root, "tests", "dist_train_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "DIST_TRAIN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_submodule_forward_matches_reference_modules(cuda_device):
+    """SAModule / GlobalSAModule / FPModule called on their own (operator level, reference :21-67) agree with the
+    oracle's modules: bit-exact sampled indices, rtol 1e-3 features, gradients flow."""
+    from oracle import thirdparty_ops as tp
+
+    N, B = 2048, 2
+    args, net, port = _make_models(N, cuda_device)
+    data = _plots(6, B, N)
+    pos = _long(data["xyz"])
+    x0 = data["cloud"].permute(0, 2, 1).reshape(B * N, -1)[:, 2:].contiguous()
+    batch = _batch(B, N)
+    d = cuda_device
+    with torch.no_grad():
+        x1, pos1, b1 = net.sa1_module(x0.to(d), pos.to(d), batch.to(d))
+        x2, pos2, b2 = net.sa2_module(x1, pos1, b1)
+        g, posg, bg = net.sa3_module(x2, pos2, b2)
+        f3, _, _ = net.fp3_module(g, posg, bg, x2, pos2, b2)
+        f2, _, _ = net.fp2_module(f3, pos2, b2, x1, pos1, b1)
+        cov_o, _ = port(data, trace=True)
+    o = port.trace
+    assert torch.equal(b1.cpu(), batch[o["sa1_idx"]])
+    torch.testing.assert_close(pos1.cpu(), pos[o["sa1_idx"]])
+    for name, got, want in (("x1", x1, o["sa1_x"]), ("x2", x2, o["sa2_x"]), ("G", g, o["G"]), ("fp3", f3, o["fp3"]), ("fp2", f2, o["fp2"])):
+        torch.testing.assert_close(got.cpu(), want, rtol=RTOL, atol=ATOL, msg=lambda m, n=name: f"{n}: {m}")
+    net.train()
+    xin = x0.to(d).requires_grad_(True)
+    y, _, _ = net.sa1_module(xin, pos.to(d), batch.to(d))
+    y.square().sum().backward()
+    assert xin.grad is not None and net.sa1_module.conv.local_nn[0][0].weight.grad is not None
