@@ -425,11 +425,17 @@ def main():
         "ingest": 4 * 13 * N + 4 * 12 * N,
     }
     hbm_peak, peak_src = peaks()
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic_cfg2.json")
+    if opts.config == 2 and os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic = {"fps1": tj.get("fps_bucket_kernel<8, 32, 0>"), "fps2": tj.get("fps_kernel<512, 8, 1>"),
+                   "fp1_head": tj.get("fp1_head_kernel")}.get(dom)
     roof = None
     if dom in alg_bytes:
         ach = alg_bytes[dom] * B / (per_step[dom] / 1e3) / 1e9
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "ms_per_launch": per_step[dom],
+                "traffic": traffic, "peak_source": peak_src, "ms_per_launch": per_step[dom],
                 "algorithmic_bytes_per_launch": alg_bytes[dom] * B}
         if dom.startswith("fps"):
             n, m = (N, M1) if dom == "fps1" else (M1, M2)
