@@ -46,9 +46,9 @@ enum {
 #define SN2_C3 64  /* SA3 MLP [35,64], FP3 MLP [96,64]                      (:81, :88)  */
 #define SN2_CF 34  /* FP2 MLP [80,34], FP1 MLP [42,34]                      (:89-90)    */
 #define SN2_CF_LD 36 /* row stride (floats) of 34-wide feature buffers: 16-byte aligned rows */
-#define SN2_GRID_MAX 64                       /* max cells per axis of the per-plot xy grid */
+#define SN2_GRID_MAX 64                       /* max cells per x / y axis of the per-plot grid */
 #define SN2_GRID_CELLS (SN2_GRID_MAX * SN2_GRID_MAX)
-#define SN2_GRID_HDR 8                        /* floats per plot in the grid header */
+#define SN2_GRID_HDR 12                       /* floats per plot in the grid header */
 
 int sn2_abi_version(void);
 const char *sn2_error_string(int code);
@@ -76,7 +76,7 @@ int sn2_fps_algo(const float *pos4, int B, int N, int M, const int *start, int *
                  float *pos4_out, int algo, void *stream);
 
 /* ---- a3/a4: radius ball query.  Replaces torch_cluster radius (model/point_net2.py:23-25).
- * Step 1: bin the N points of every plot into an xy grid whose cell edge is >= r.
+ * Step 1: bin the N points of every plot into an xyz grid (<= SN2_GRID_CELLS cells) whose cell edge is >= r.
  *   grid_hdr [B*SN2_GRID_HDR] float, cell_start [B*(SN2_GRID_CELLS+1)] int32,
  *   sorted4 [B*N] float4 (x, y, z, local index as int bits). */
 int sn2_grid_build(const float *pos4, int B, int N, float r, float *grid_hdr, int *cell_start,
@@ -110,7 +110,9 @@ int sn2_pointconv_fwd(int level, const float *pos4, const float *feat, const flo
 int sn2_sa_fused_fwd(int level, const float *grid_hdr, const int *cell_start, const float *sorted4,
                      const float *qsorted4, const float *pos4, const float *feat, float *u_scratch,
                      int *ovf_scratch, int B, int N, int M, float r2, int K, const float *w_host, int nw,
-                     float *out, int *cnt_out, void *stream);
+                     float *out, int *cnt_out, int tensor_core, void *stream);
+/* tensor_core != 0 (level 1 only): the 16x16 second layer runs as tcgen05.mma kind::tf32 tiles (one private
+ * M=128 tile per warp, accumulators in TMEM) with a 3xTF32 operand split, so the product keeps fp32 accuracy. */
 
 /* ---- a5: global set abstraction.  Replaces MLP[35,64] + global_max_pool (model/point_net2.py:37-42).
  * x2 [B*M,32], pos4 [B*M] -> g [B,64]. */

@@ -1,10 +1,12 @@
 // K2 radius ball query: grid-binned search, canonical
 // index-ordered neighbour lists capped at K, CSR output (no [M, cap] scratch).
 //
-//   grid_build : one CTA per plot: xy bounding box -> cell histogram -> scan -> scatter of
+//   grid_build : one CTA per plot: bounding box -> cell histogram -> scan -> scatter of
 //                (x, y, z, local index) into cell order.  Cell edge = max(r*(1+1e-4), extent/64), so
-//                any two points closer than r lie in the same or adjacent cells (3x3 search) even
-//                after fp32 rounding of the cell coordinate.
+//                any two points closer than r lie in the same or adjacent cells (3x3x3 search) even
+//                after fp32 rounding of the cell coordinate.  The grid is 3-D (z layers of the same
+//                edge, as many as fit in 4096 cells): FPS centroids are mostly sparse canopy points
+//                whose xy column is full of ground points -- the z layers cut their candidates ~20x.
 //   ball_count : one warp per query: scans the 3 cell-row ranges, counts d2 < r2 -> min(count, K).
 //   rowptr_scan: per-plot block scan + plot bases -> CSR row pointer.
 //   ball_fill  : one warp per query: same search, hits set bits in a per-warp bitmap over the plot's
@@ -26,32 +28,38 @@ __global__ void __launch_bounds__(GB_THREADS, 1)
 grid_build_kernel(const float4 *__restrict__ pos, int N, float r, float *__restrict__ grid_hdr,
                   int *__restrict__ cell_start, float4 *__restrict__ sorted)
 {
-    __shared__ float red[4][32];
+    __shared__ float red[6][32];
     __shared__ int hist[SN2_GRID_CELLS];
     __shared__ int wsum[32];
-    __shared__ float s_hdr[4];
-    __shared__ int s_g[2];
+    __shared__ float s_hdr[6];
+    __shared__ int s_g[3];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float4 *p = pos + (size_t)b * N;
 
     // 1. bounding box
-    float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY, mnz = INFINITY, mxz = -INFINITY;
     for (int i = tid; i < N; i += GB_THREADS) {
         float4 v = __ldg(p + i);
         mnx = fminf(mnx, v.x);
         mxx = fmaxf(mxx, v.x);
         mny = fminf(mny, v.y);
         mxy = fmaxf(mxy, v.y);
+        mnz = fminf(mnz, v.z);
+        mxz = fmaxf(mxz, v.z);
     }
     mnx = -warp_max(-mnx);
     mny = -warp_max(-mny);
+    mnz = -warp_max(-mnz);
     mxx = warp_max(mxx);
     mxy = warp_max(mxy);
+    mxz = warp_max(mxz);
     if (lane == 0) {
         red[0][warp] = mnx;
         red[1][warp] = mny;
         red[2][warp] = mxx;
         red[3][warp] = mxy;
+        red[4][warp] = mnz;
+        red[5][warp] = mxz;
     }
     for (int c = tid; c < SN2_GRID_CELLS; c += GB_THREADS) hist[c] = 0;
     __syncthreads();
@@ -60,6 +68,8 @@ grid_build_kernel(const float4 *__restrict__ pos, int N, float r, float *__restr
         mny = -warp_max(-red[1][lane]);
         mxx = warp_max(red[2][lane]);
         mxy = warp_max(red[3][lane]);
+        mnz = -warp_max(-red[4][lane]);
+        mxz = warp_max(red[5][lane]);
         if (lane == 0) {
             float ext = fmaxf(mxx - mnx, mxy - mny);
             // r > 0: cell edge just above r (3x3 search is exhaustive for radius r);
@@ -70,11 +80,26 @@ grid_build_kernel(const float4 *__restrict__ pos, int N, float r, float *__restr
             float inv = 1.0f / cs;
             int gx = min(SN2_GRID_MAX, (int)floorf((mxx - mnx) * inv) + 1);
             int gy = min(SN2_GRID_MAX, (int)floorf((mxy - mny) * inv) + 1);
+            // z layers (ball-query grids only): same edge as xy when they fit in the cell budget, else thicker
+            int gz = 1;
+            float invz = 0.f, csz = INFINITY;
+            const float zext = mxz - mnz;
+            const int gzmax = SN2_GRID_CELLS / (gx * gy);
+            if (r > 0.f && gzmax > 1 && zext > 0.f) {
+                const int need = (int)floorf(zext / cs) + 1;
+                if (need <= gzmax) { gz = need; csz = cs; }
+                else { gz = gzmax; csz = zext / ((float)gz - 0.5f); }  // floor(zext / csz) = gz - 1, csz > cs
+                invz = 1.0f / csz;
+                gz = min(gz, (int)floorf(zext * invz) + 1);
+            }
             s_hdr[0] = mnx;
             s_hdr[1] = mny;
             s_hdr[2] = inv;
+            s_hdr[3] = mnz;
+            s_hdr[4] = invz;
             s_g[0] = gx;
             s_g[1] = gy;
+            s_g[2] = gz;
             float *h = grid_hdr + (size_t)b * SN2_GRID_HDR;
             h[0] = mnx;
             h[1] = mny;
@@ -82,18 +107,22 @@ grid_build_kernel(const float4 *__restrict__ pos, int N, float r, float *__restr
             h[3] = cs;
             h[4] = __int_as_float(gx);
             h[5] = __int_as_float(gy);
-            h[6] = 0.f;
-            h[7] = 0.f;
+            h[6] = mnz;
+            h[7] = invz;
+            h[8] = __int_as_float(gz);
+            h[9] = csz;
+            h[10] = 0.f;
+            h[11] = 0.f;
         }
     }
     __syncthreads();
-    const float ox = s_hdr[0], oy = s_hdr[1], inv = s_hdr[2];
-    const int gx = s_g[0], gy = s_g[1];
+    const float ox = s_hdr[0], oy = s_hdr[1], inv = s_hdr[2], oz = s_hdr[3], invz = s_hdr[4];
+    const int gx = s_g[0], gy = s_g[1], gz = s_g[2];
 
     // 2. histogram
     for (int i = tid; i < N; i += GB_THREADS) {
         float4 v = __ldg(p + i);
-        int c = cell_coord(v.y, oy, inv, gy) * gx + cell_coord(v.x, ox, inv, gx);
+        int c = (cell_coord(v.z, oz, invz, gz) * gy + cell_coord(v.y, oy, inv, gy)) * gx + cell_coord(v.x, ox, inv, gx);
         atomicAdd(&hist[c], 1);
     }
     __syncthreads();
@@ -141,7 +170,7 @@ grid_build_kernel(const float4 *__restrict__ pos, int N, float r, float *__restr
     float4 *so = sorted + (size_t)b * N;
     for (int i = tid; i < N; i += GB_THREADS) {
         float4 v = __ldg(p + i);
-        int c = cell_coord(v.y, oy, inv, gy) * gx + cell_coord(v.x, ox, inv, gx);
+        int c = (cell_coord(v.z, oz, invz, gz) * gy + cell_coord(v.y, oy, inv, gy)) * gx + cell_coord(v.x, ox, inv, gx);
         int dst = atomicAdd(&hist[c], 1);
         so[dst] = make_float4(v.x, v.y, v.z, __int_as_float(i));
     }
@@ -152,17 +181,19 @@ template <typename F>
 __device__ __forceinline__ void ball_search(const float *__restrict__ hdr, const int *__restrict__ cs,
                                             const float4 *__restrict__ so, float4 q, float r2, int lane, F f)
 {
-    const float ox = hdr[0], oy = hdr[1], inv = hdr[2];
-    const int gx = __float_as_int(hdr[4]), gy = __float_as_int(hdr[5]);
-    const int ix = cell_coord(q.x, ox, inv, gx), iy = cell_coord(q.y, oy, inv, gy);
+    const float ox = hdr[0], oy = hdr[1], inv = hdr[2], oz = hdr[6], invz = hdr[7];
+    const int gx = __float_as_int(hdr[4]), gy = __float_as_int(hdr[5]), gz = __float_as_int(hdr[8]);
+    const int ix = cell_coord(q.x, ox, inv, gx), iy = cell_coord(q.y, oy, inv, gy), iz = cell_coord(q.z, oz, invz, gz);
     const int x0 = max(ix - 1, 0), x1 = min(ix + 1, gx - 1);
-    for (int y = max(iy - 1, 0); y <= min(iy + 1, gy - 1); ++y) {
-        const int s = __ldg(cs + y * gx + x0), e = __ldg(cs + y * gx + x1 + 1);
-        for (int j = s + lane; j < e; j += 32) {
-            float4 v = __ldg(so + j);
-            if (dist2(v.x, v.y, v.z, q.x, q.y, q.z) < r2) f(__float_as_int(v.w));
+    for (int z = max(iz - 1, 0); z <= min(iz + 1, gz - 1); ++z)
+        for (int y = max(iy - 1, 0); y <= min(iy + 1, gy - 1); ++y) {
+            const int row = (z * gy + y) * gx;
+            const int s = __ldg(cs + row + x0), e = __ldg(cs + row + x1 + 1);
+            for (int j = s + lane; j < e; j += 32) {
+                float4 v = __ldg(so + j);
+                if (dist2(v.x, v.y, v.z, q.x, q.y, q.z) < r2) f(__float_as_int(v.w));
+            }
         }
-    }
 }
 
 __global__ void __launch_bounds__(256)

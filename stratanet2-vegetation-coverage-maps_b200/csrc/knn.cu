@@ -1,4 +1,4 @@
-// K4 search part: exact 3-nearest-neighbour search on the per-plot xy grid (SURVEY.md §8a a7/a8,
+// K4 search part: exact 3-nearest-neighbour search on the per-plot xy grid (grid_build with r < 0: one z layer) (SURVEY.md §8a a7/a8,
 // Appendix A5).  One thread per query; the sources of a plot are binned by grid_build (auto cell edge,
 // ~3 sources per cell).  The search visits the 3x3 block around the query's cell, then square rings,
 // and stops as soon as the 3rd best squared distance is strictly below the squared xy-distance to the

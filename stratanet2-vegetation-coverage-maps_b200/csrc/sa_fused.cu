@@ -65,8 +65,31 @@ sa_pre_kernel(const float4 *__restrict__ pos, const float *__restrict__ feat, lo
     for (int v = 0; v < C / 4; ++v) o4[v] = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
 }
 
-template <int LEVEL, bool REDO>
-__global__ void __launch_bounds__(SF_WARPS * 32, REDO ? 1 : (LEVEL == 1 ? 3 : 2))
+// ---- tensor-core (tcgen05) helpers for the level-1 second layer ---------------------------------------
+// K-major, no-swizzle canonical operand layout: core matrix = 8 rows x 16 bytes (128 contiguous bytes);
+// LBO = bytes between core matrices adjacent in K, SBO = between core matrices adjacent in M/N.
+// Element (row r, k) of a [rows x 16] fp32 operand sits at (r/8)*512 + (k/4)*128 + (r%8)*16 + (k%4)*4.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned long long umma_desc(unsigned saddr)
+{
+    return (unsigned long long)((saddr >> 4) & 0x3fff) | ((unsigned long long)(128 >> 4) << 16) |
+           ((unsigned long long)(512 >> 4) << 32) | (1ull << 46);  // LBO 128 B, SBO 512 B, version 1, SWIZZLE_NONE
+}
+// kind::tf32, D = F32, A/B = TF32 K-major, N = 16, M = 128
+constexpr unsigned UMMA_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned acc)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem_d), "l"(da),
+                 "l"(db), "r"(UMMA_IDESC), "r"(acc), "r"(0), "r"(0), "r"(0), "r"(0));
+}
+constexpr int TC_PAD = 6144;                                  // an M=128 operand window around a 32-row region
+constexpr int TC_A_BYTES = TC_PAD + SF_WARPS * 8192 + 8192;   // per warp: 2 stages x (2 KB hi rows + 2 KB lo rows)
+constexpr int TC_SMEM = TC_A_BYTES + 2 * 1024 + 256;          // + W2 hi / lo tiles + mbarriers
+constexpr int TC_TMEM_COLS = SF_WARPS * 32;                   // 2 stages x 16 accumulator columns per warp
+
+template <int LEVEL, bool REDO, int DBG = 0, int TC = 0>  // TC: 0 SIMT, 1 tcgen05 3xTF32 (fp32-accurate), 2 tcgen05 plain TF32
+__global__ void __launch_bounds__(SF_WARPS * 32, REDO ? 1 : (LEVEL == 1 ? (TC ? 2 : 3) : 2))
 sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell_start,
                 const float4 *__restrict__ sorted, const float4 *__restrict__ qsorted,
                 const float *__restrict__ u, int N, int M, float r2, int K, int words,
@@ -84,6 +107,42 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
     unsigned *pre = bm + words;  // inclusive popc prefix (REDO only)
     const unsigned lt = (1u << lane) - 1u;
 
+    // ---- tensor-core state (TC): per-warp operand rows, W2 tiles, per-warp mbarrier, TMEM accumulators ----
+    static_assert(!TC || (LEVEL == 1 && !REDO), "the tcgen05 path covers the level-1 streaming kernel");
+    unsigned char *tc_base = sf_smem + SF_WARPS * RING * sizeof(int);  // 1024-byte aligned (ring = 8 KB)
+    unsigned char *a_st = tc_base + TC_PAD + warp * 8192;  // stage s: hi rows at a_st + s*4096, lo rows 2 KB after
+    float *b_hi = reinterpret_cast<float *>(tc_base + TC_A_BYTES), *b_lo = b_hi + 256;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(tc_base + TC_A_BYTES + 2048);
+    __shared__ unsigned s_tmem;
+    unsigned tmem_d = 0, tc_parity = 0;  // tc_parity: bit s = phase parity of stage s's mbarrier
+    unsigned long long d_a0 = 0, d_bhi = 0, d_blo = 0;
+    if constexpr (TC) {
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)),
+                         "r"(TC_TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+        }
+        if (lane < 2) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bars[2 * warp + lane])));
+        {   // W2 as the B operand [N = 16 (o) x K = 16 (k)], split into tf32 hi + lo (3xTF32: fp32-accurate product)
+            const int o = threadIdx.x >> 4, k = threadIdx.x & 15;
+            const float wv = W.l2.w[k][o];
+            const float hi = __uint_as_float(__float_as_uint(wv) & 0xffffe000u);
+            const int off = (o >> 3) * 128 + (k >> 2) * 32 + (o & 7) * 4 + (k & 3);  // in floats
+            b_hi[off] = TC == 1 ? hi : wv;
+            b_lo[off] = wv - hi;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;\n");
+        const int qd = warp & 3;  // TMEM lane quarter this warp can read = rows 32*qd.. of its M=128 tile
+        tmem_d = s_tmem + ((unsigned)(32 * qd) << 16) + (unsigned)(32 * warp);
+        d_a0 = umma_desc(smem_u32(a_st) - qd * 2048);  // stage s: +4096 B (= +256 in the address field); lo: +2048 B
+        d_bhi = umma_desc(smem_u32(b_hi));
+        d_blo = umma_desc(smem_u32(b_lo));
+    }
+
     // work items: streaming = one (plot, cell-ordered query) per warp; redo = entries of the overflow list
     long long item = REDO ? (long long)blockIdx.x * SF_WARPS + warp : 0;
     const long long n_items = REDO ? (long long)ovf[0] : 1;
@@ -96,7 +155,7 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
         } else {
             b = blockIdx.y;
             j = blockIdx.x * SF_WARPS + warp;
-            if (j >= M) return;
+            if (j >= M) break;  // (no early return: the TC variant frees tensor memory after the loop)
         }
         const float *hdr = grid_hdr + (size_t)b * SN2_GRID_HDR;
         const int *cs = cell_start + (size_t)b * (SN2_GRID_CELLS + 1);
@@ -105,11 +164,15 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
         const int qloc = __float_as_int(q.w);
         const float *ub = u + (size_t)b * N * C;
 
-        const float ox = hdr[0], oy = hdr[1], inv = hdr[2];
-        const int gx = __float_as_int(hdr[4]), gy = __float_as_int(hdr[5]);
+        const float ox = hdr[0], oy = hdr[1], inv = hdr[2], oz = hdr[6], invz = hdr[7];
+        const int gx = __float_as_int(hdr[4]), gy = __float_as_int(hdr[5]), gz = __float_as_int(hdr[8]);
         const int ix = cell_coord_c(q.x, ox, inv, gx), iy = cell_coord_c(q.y, oy, inv, gy);
+        const int iz = cell_coord_c(q.z, oz, invz, gz);
         const int x0 = max(ix - 1, 0), x1 = min(ix + 1, gx - 1);
         const int y0 = max(iy - 1, 0), y1 = min(iy + 1, gy - 1);
+        const int z0 = max(iz - 1, 0), z1 = min(iz + 1, gz - 1);
+        const int ny = y1 - y0 + 1, nrows = ny * (z1 - z0 + 1);  // (layer, cell row) pairs to scan
+        auto row_of = [&](int t) { return ((z0 + t / ny) * gy + (y0 + t % ny)) * gx; };
 
         // c_i = b1 - W1p q  (the per-centroid half of the first layer)
         float c[C];
@@ -156,11 +219,104 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
             }
         };
 
+        // Tensor-core form of one 32-edge batch, split in two halves so the MMA latency hides under the next
+        // batch's search + gather (two operand / accumulator stages per warp):
+        //   tc_issue  : layer 1 in registers, rows -> this warp's private operand region, 6 x tcgen05.mma
+        //               (128x16x8 TF32; 3xTF32 split A_hi B_hi + A_lo B_hi + A_hi B_lo keeps fp32 accuracy;
+        //               the rows of the other three lane quarters of the M=128 tile are don't-care), commit.
+        //   tc_consume: wait for that stage's mbarrier, tcgen05.ld the 32 rows x 16 columns, ReLU/BN/max.
+        auto tc_issue = [&](const int id, const int take, const int st) {
+            if constexpr (TC) {
+                float h1[C];
+#pragma unroll
+                for (int o = 0; o < C; ++o) h1[o] = 0.f;
+                if (lane < take) {
+                    const float *ur = ub + (size_t)id * C;
+#pragma unroll
+                    for (int g = 0; g < C / 4; ++g) {
+                        const float4 t4 = ldg4(ur + 4 * g);
+                        h1[4 * g] = t4.x + c[4 * g];
+                        h1[4 * g + 1] = t4.y + c[4 * g + 1];
+                        h1[4 * g + 2] = t4.z + c[4 * g + 2];
+                        h1[4 * g + 3] = t4.w + c[4 * g + 3];
+                    }
+                    relu_bn(W.l1, h1);
+                }
+                unsigned char *ah = a_st + st * 4096 + (lane >> 3) * 512 + (lane & 7) * 16;
+#pragma unroll
+                for (int kc = 0; kc < 4; ++kc) {
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        hi[t] = __uint_as_float(__float_as_uint(h1[4 * kc + t]) & 0xffffe000u);
+                        lo[t] = h1[4 * kc + t] - hi[t];
+                    }
+                    if (TC == 1) {
+                        *reinterpret_cast<float4 *>(ah + kc * 128) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<float4 *>(ah + 2048 + kc * 128) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    } else {  // plain TF32: the tensor core truncates the low 13 mantissa bits itself
+                        *reinterpret_cast<float4 *>(ah + kc * 128) =
+                            make_float4(h1[4 * kc], h1[4 * kc + 1], h1[4 * kc + 2], h1[4 * kc + 3]);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("tcgen05.fence::after_thread_sync;\n");
+                    const unsigned dcol = s_tmem + (unsigned)(32 * warp + 16 * st);  // all 128 lanes, this stage's 16 columns
+                    const unsigned long long ahi = d_a0 + (unsigned long long)(st * 256), alo = ahi + 128;
+                    // K = 16 = two K=8 steps: +256 bytes (2 core matrices, +16 in the address field) on both operands
+                    umma_tf32(dcol, ahi, d_bhi, 0u);
+                    umma_tf32(dcol, ahi + 16, d_bhi + 16, 1u);
+                    if (TC == 1) {
+                        umma_tf32(dcol, alo, d_bhi, 1u);
+                        umma_tf32(dcol, alo + 16, d_bhi + 16, 1u);
+                        umma_tf32(dcol, ahi, d_blo, 1u);
+                        umma_tf32(dcol, ahi + 16, d_blo + 16, 1u);
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
+                                     smem_u32(&bars[2 * warp + st]))
+                                 : "memory");
+                }
+                __syncwarp();
+            }
+        };
+        auto tc_consume = [&](const int take, const int st) {
+            if constexpr (TC) {
+                unsigned done = 0;
+                for (int spin = 0; spin < (1 << 24) && !done; ++spin)
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                 "selp.u32 %0, 1, 0, p;\n\t}\n"
+                                 : "=r"(done)
+                                 : "r"(smem_u32(&bars[2 * warp + st])), "r"((tc_parity >> st) & 1u)
+                                 : "memory");
+                if (!done) __trap();  // the MMA never completed: fail loudly instead of hanging the GPU
+                tc_parity ^= 1u << st;
+                asm volatile("tcgen05.fence::after_thread_sync;\n");
+                unsigned d[16];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                             : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]),
+                               "=r"(d[8]), "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15])
+                             : "r"(tmem_d + (unsigned)(16 * st)));
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;\n");
+                if (lane < take) {
+#pragma unroll
+                    for (int o = 0; o < C; ++o) {
+                        const float h2 = fmaf(fmaxf(__uint_as_float(d[o]) + W.l2.b[o], 0.f), W.l2.s[o], W.l2.t[o]);
+                        mx[o] = fmaxf(mx[o], h2);
+                    }
+                }
+                __syncwarp();
+            }
+        };
+        int tc_stage = 0, tc_pending = 0;  // tc_pending = rows of the batch in flight on stage tc_stage ^ 1 (0: none)
+
         if (REDO) {  // hit set as a bitmap over the plot's point indices + inclusive popcount prefix
             for (int w = lane; w < words; w += 32) bm[w] = 0u;
             __syncwarp();
-            for (int yy = y0; yy <= y1; ++yy) {
-                const int s2 = __ldg(cs + yy * gx + x0), e2 = __ldg(cs + yy * gx + x1 + 1);
+            for (int t = 0; t < nrows; ++t) {
+                const int s2 = __ldg(cs + row_of(t) + x0), e2 = __ldg(cs + row_of(t) + x1 + 1);
                 for (int i = s2 + lane; i < e2; i += 32) {
                     const float4 v = __ldg(so + i);
                     if (dist2(v.x, v.y, v.z, q.x, q.y, q.z) < r2) {
@@ -189,7 +345,7 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
         // ---- producer / consumer loop with ONE call site of the message MLP (keeps the loop in I-cache) ----
         int cnt = 0;
         int head = 0, tail = 0;          // warp-uniform ring cursors
-        int y = y0, base = 0, e = 0;     // streaming iterator: current cell row and candidate range
+        int y = 0, base = 0, e = 0;      // streaming iterator: current (layer, cell row) and candidate range
         bool open_row = false;
         int rank = 0;                    // redo iterator: next rank of the set bits to extract
         bool more = true;
@@ -197,9 +353,9 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
             while (more && tail - head < 32) {
                 if (!REDO) {
                     if (!open_row) {
-                        if (y > y1) { more = false; break; }
-                        base = __ldg(cs + y * gx + x0);
-                        e = __ldg(cs + y * gx + x1 + 1);
+                        if (y >= nrows) { more = false; break; }
+                        base = __ldg(cs + row_of(y) + x0);
+                        e = __ldg(cs + row_of(y) + x1 + 1);
                         open_row = true;
                     }
                     float4 vv[UNR];
@@ -210,11 +366,13 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
                     }
 #pragma unroll
                     for (int t = 0; t < UNR; ++t) {
-                        const float4 v = vv[t];
-                        const bool hit = (base + t * 32 + lane < e) && dist2(v.x, v.y, v.z, q.x, q.y, q.z) < r2;
-                        const unsigned bal = __ballot_sync(SN2_FULL, hit);
-                        if (hit) ring[(tail + __popc(bal & lt)) & (RING - 1)] = __float_as_int(v.w);
-                        tail += __popc(bal);
+                        if (base + t * 32 < e) {  // warp-uniform: short runs (3-D cells) cost one sub-batch, not UNR
+                            const float4 v = vv[t];
+                            const bool hit = (base + t * 32 + lane < e) && dist2(v.x, v.y, v.z, q.x, q.y, q.z) < r2;
+                            const unsigned bal = __ballot_sync(SN2_FULL, hit);
+                            if (hit) ring[(tail + __popc(bal & lt)) & (RING - 1)] = __float_as_int(v.w);
+                            tail += __popc(bal);
+                        }
                     }
                     base += 32 * UNR;
                     if (base >= e) { open_row = false; ++y; }
@@ -243,9 +401,17 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
             head += take;
             cnt += take;
             __syncwarp();
-            if (lane < take) edge(id);
+            if (TC) {
+                tc_issue(id, take, tc_stage);
+                if (tc_pending) tc_consume(tc_pending, tc_stage ^ 1);
+                tc_pending = take;
+                tc_stage ^= 1;
+            } else if (DBG != 1 && lane < take) {
+                edge(id);  // DBG 1: search only (profiling)
+            }
         }
 
+        if (TC && tc_pending) tc_consume(tc_pending, tc_stage ^ 1);
         const size_t row = (size_t)b * M + qloc;
         if (!REDO && cnt > K) {  // the cap binds: leave this centroid to the exact redo launch
             if (lane == 0) ovf[1 + atomicAdd(ovf, 1)] = b * M + j;
@@ -269,6 +435,12 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
             if (cnt_out) cnt_out[row] = cnt;
         }
     }
+    if constexpr (TC) {  // release tensor memory once every warp is done with it
+        asm volatile("tcgen05.fence::before_thread_sync;\n");
+        __syncthreads();
+        if (warp == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(s_tmem), "r"(TC_TMEM_COLS));
+    }
 }
 
 __global__ void zero_int_kernel(int *p) { *p = 0; }
@@ -276,7 +448,7 @@ __global__ void zero_int_kernel(int *p) { *p = 0; }
 template <int LEVEL>
 static int launch_sa_fused(const float *grid_hdr, const int *cell_start, const float *sorted4, const float *qsorted4,
                            const float *pos4, const float *feat, float *u_scratch, int *ovf, int B, int N, int M,
-                           float r2, int K, const float *w_host, int nw, float *out, int *cnt_out, cudaStream_t st)
+                           float r2, int K, const float *w_host, int nw, float *out, int *cnt_out, int tc, cudaStream_t st)
 {
     typename SAEdge<LEVEL>::W w;
     if (int rc = load_weights(w, w_host, nw)) return rc;
@@ -287,9 +459,20 @@ static int launch_sa_fused(const float *grid_hdr, const int *cell_start, const f
     SN2_LAUNCH_CHECK("sa_pre_kernel");
     const int words = (N + 31) / 32;
     const size_t smem_ring = (size_t)SF_WARPS * 256 * sizeof(int);
-    {
+    dim3 grid((M + SF_WARPS - 1) / SF_WARPS, B);
+    if constexpr (LEVEL == 1) {
+        if (tc) {  // second layer on the tensor cores (tcgen05): 1 = 3xTF32, 2 = plain TF32
+            auto kern = tc == 1 ? sa_fused_kernel<1, false, 0, 1> : sa_fused_kernel<1, false, 0, 2>;
+            const size_t smem_tc = smem_ring + TC_SMEM;
+            SN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc), "sa_fused_tc attr");
+            kern<<<grid, SF_WARPS * 32, smem_tc, st>>>(grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4),
+                                                       reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, 0, w,
+                                                       out, cnt_out, ovf);
+            SN2_LAUNCH_CHECK("sa_fused_kernel<tc>");
+        }
+    }
+    if (!(LEVEL == 1 && tc)) {
         auto kern = sa_fused_kernel<LEVEL, false>;
-        dim3 grid((M + SF_WARPS - 1) / SF_WARPS, B);
         kern<<<grid, SF_WARPS * 32, smem_ring, st>>>(grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4),
                                                      reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, 0, w,
                                                      out, cnt_out, ovf);
@@ -310,10 +493,26 @@ static int launch_sa_fused(const float *grid_hdr, const int *cell_start, const f
 
 }  // namespace sn2
 
+// Debug/profiling entry (not part of the product ABI): level-1 streaming kernel with the message MLP disabled.
+extern "C" int sn2_debug_sa_search_only(const float *grid_hdr, const int *cell_start, const float *sorted4,
+                                        const float *qsorted4, const float *u, int *ovf, int B, int N, int M, float r2,
+                                        int K, const float *w_host, int nw, float *out, int *cnt_out, void *stream)
+{
+    using namespace sn2;
+    W_SA1 w;
+    if (int rc = load_weights(w, w_host, nw)) return rc;
+    dim3 grid((M + SF_WARPS - 1) / SF_WARPS, B);
+    sa_fused_kernel<1, false, 1><<<grid, SF_WARPS * 32, SF_WARPS * 256 * sizeof(int), (cudaStream_t)stream>>>(
+        grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4), reinterpret_cast<const float4 *>(qsorted4), u, N, M,
+        r2, K, 0, w, out, cnt_out, ovf);
+    SN2_LAUNCH_CHECK("sa_fused_kernel<dbg>");
+    return SN2_OK;
+}
+
 extern "C" int sn2_sa_fused_fwd(int level, const float *grid_hdr, const int *cell_start, const float *sorted4,
                                 const float *qsorted4, const float *pos4, const float *feat, float *u_scratch,
                                 int *ovf_scratch, int B, int N, int M, float r2, int K, const float *w_host, int nw,
-                                float *out, int *cnt_out, void *stream)
+                                float *out, int *cnt_out, int tensor_core, void *stream)
 {
     if (!grid_hdr || !cell_start || !sorted4 || !qsorted4 || !pos4 || !feat || !u_scratch || !ovf_scratch || !out ||
         B <= 0 || N <= 0 || M <= 0 || K <= 0)
@@ -321,9 +520,9 @@ extern "C" int sn2_sa_fused_fwd(int level, const float *grid_hdr, const int *cel
     cudaStream_t st = (cudaStream_t)stream;
     if (level == 1)
         return sn2::launch_sa_fused<1>(grid_hdr, cell_start, sorted4, qsorted4, pos4, feat, u_scratch, ovf_scratch, B, N, M,
-                                       r2, K, w_host, nw, out, cnt_out, st);
+                                       r2, K, w_host, nw, out, cnt_out, tensor_core == 2 ? 2 : (tensor_core ? 1 : 0), st);
     if (level == 2)
         return sn2::launch_sa_fused<2>(grid_hdr, cell_start, sorted4, qsorted4, pos4, feat, u_scratch, ovf_scratch, B, N, M,
-                                       r2, K, w_host, nw, out, cnt_out, st);
+                                       r2, K, w_host, nw, out, cnt_out, 0, st);
     return SN2_EINVAL;
 }

@@ -31,7 +31,7 @@ SIGNATURES = {
     "sn2_rowptr_scan": [_vp, _i, _i, _vp, _vp, _vp],
     "sn2_ball_fill": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp],
     "sn2_pointconv_fwd": [_i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp],
-    "sn2_sa_fused_fwd": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _i, _vp, _vp, _vp],
+    "sn2_sa_fused_fwd": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _i, _vp, _vp, _i, _vp],
     "sn2_global_sa_fwd": [_vp, _vp, _i, _i, _vp, _i, _vp, _vp],
     "sn2_fp3_fwd": [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp],
     "sn2_knn3": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],

@@ -30,7 +30,7 @@ def _count(n: int = 1) -> None:
 
 
 GRID_CELLS = 64 * 64
-GRID_HDR = 8
+GRID_HDR = 12
 CF_LD = 36
 
 
@@ -132,7 +132,8 @@ def build_grid(pos4, B: int, N: int, r: float):
     return hdr, cell_start, sorted4
 
 
-def sa_fused_fwd(level: int, pos4, feat, qpos4, B: int, N: int, M: int, r: float, K: int, w_host, want_counts=False):
+def sa_fused_fwd(level: int, pos4, feat, qpos4, B: int, N: int, M: int, r: float, K: int, w_host, want_counts=False,
+                 tensor_core: int = 0):
     """Fused ball query + PointConv (eval).  -> out [B*M, 16|32] (+ neighbour counts int32 [B*M])."""
     lib = _lib.load()
     dev = pos4.device
@@ -145,7 +146,8 @@ def sa_fused_fwd(level: int, pos4, feat, qpos4, B: int, N: int, M: int, r: float
     ovf = torch.empty(B * M + 1, dtype=torch.int32, device=dev)
     check(lib.sn2_sa_fused_fwd(level, dptr(hdr), dptr(cell_start), dptr(sorted4), dptr(qsorted4), dptr(pos4, torch.float32),
                                dptr(feat, torch.float32), dptr(u), dptr(ovf), B, N, M, r2_of(r), int(K), hptr(w_host),
-                               w_host.numel(), dptr(out), dptr(cnt), stream_ptr()), "sn2_sa_fused_fwd")
+                               w_host.numel(), dptr(out), dptr(cnt), int(tensor_core) if level == 1 else 0, stream_ptr()),
+          "sn2_sa_fused_fwd")
     _count(4 if K < N else 3)
     return (out, cnt) if want_counts else out
 

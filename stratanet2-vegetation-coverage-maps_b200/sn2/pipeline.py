@@ -6,6 +6,7 @@ synchronisations are the two edge-count read-backs that size the neighbour lists
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -64,6 +65,8 @@ class ForwardTrace:
     tensors: dict = field(default_factory=dict)
 
 
+# SA1's second layer on tcgen05 (3xTF32, fp32-accurate) instead of SIMT FFMA; PointNet2.sn2_tensor_core overrides
+TENSOR_CORE_DEFAULT = int(os.environ.get("SN2_TENSOR_CORE", "0"))  # 0 SIMT fp32, 1 tcgen05 3xTF32, 2 tcgen05 TF32
 _SIDE = {}
 
 
@@ -136,7 +139,8 @@ def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_
     if trace is not None:  # neighbour lists only materialised for parity tests / backward
         rowptr1, col1 = ops.ball_query_dense(pos0, pos1, B, N, M1, sa1.r, max_num_neighbors)
     with T.stage("sa1_fused"):
-        x1 = ops.sa_fused_fwd(1, pos0, feat0, pos1, B, N, M1, sa1.r, max_num_neighbors, W["sa1"])
+        x1 = ops.sa_fused_fwd(1, pos0, feat0, pos1, B, N, M1, sa1.r, max_num_neighbors, W["sa1"],
+                              tensor_core=int(getattr(model, "sn2_tensor_core", TENSOR_CORE_DEFAULT)))
     join(side_a, idx2, pos2, nbr2, w2)
     if trace is not None:
         rowptr2, col2 = ops.ball_query_dense(pos1, pos2, B, M1, M2, sa2.r, max_num_neighbors)

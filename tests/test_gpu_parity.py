@@ -255,6 +255,13 @@ def test_sa_fused_equals_list_path(cuda_device, N, K, variant):
     x1_fused, cnt = ops.sa_fused_fwd(1, pos0, feat0, pos1, B, N, M1, r1, K, W["sa1"], want_counts=True)
     assert torch.equal(cnt, rowptr[1:] - rowptr[:-1])
     torch.testing.assert_close(x1_fused, x1_list, rtol=1e-4, atol=1e-5)
+    # tensor-core variant (tcgen05.mma kind::tf32 with the 3xTF32 split): fp32-accurate, same edges
+    x1_tc, cnt_tc = ops.sa_fused_fwd(1, pos0, feat0, pos1, B, N, M1, r1, K, W["sa1"], want_counts=True, tensor_core=1)
+    assert torch.equal(cnt_tc, cnt)
+    torch.testing.assert_close(x1_tc, x1_list, rtol=1e-4, atol=1e-5)
+    # plain TF32 operands (what torch 1.8 + cuBLAS did on the reference's Ampere GPUs): stated looser bound
+    x1_tf32 = ops.sa_fused_fwd(1, pos0, feat0, pos1, B, N, M1, r1, K, W["sa1"], tensor_core=2)
+    torch.testing.assert_close(x1_tf32, x1_list, rtol=1e-2, atol=5e-3)
     M2 = ops.m_of(M1, 0.25)
     _, pos2 = ops.fps_dense(pos1, B, M1, M2)
     rowptr2, col2 = ops.ball_query_dense(pos1, pos2, B, M1, M2, r2, K)
