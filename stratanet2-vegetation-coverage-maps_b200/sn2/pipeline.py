@@ -87,7 +87,7 @@ def _packed(model) -> dict:
 
 
 def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_neighbors: int = 2000,
-                 trace: ForwardTrace | None = None, timer=None):
+                 trace: ForwardTrace | None = None, timer=None, side_streams=None):
     """xyz (B,3,N), cloud (B,10,N) fp32 (host or device) -> coverages (B*N,4), proba (B*N,4) on device."""
     if cloud.dim() != 3 or xyz.dim() != 3 or xyz.shape[1] != 3 or cloud.shape[0] != xyz.shape[0] \
             or cloud.shape[2] != xyz.shape[2]:
@@ -102,7 +102,7 @@ def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_
 
     T = timer if timer is not None else _NOTIMER
     main = torch.cuda.current_stream(device)
-    side_a, side_b = _side_streams(device)
+    side_a, side_b = side_streams if side_streams is not None else _side_streams(device)
 
     def fork(stream):
         ev = torch.cuda.Event()
@@ -220,3 +220,64 @@ def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num
                              x1=x1, idx2=idx2, pos2=pos2, rowptr2=rowptr2, col2=col2, x2=x2, G=g, fp3=f3, fp2=f2, fp1=f1,
                              nbr1=nbr1, w1=w1, nbr2=nbr2, w2=w2, M1=M1, M2=M2)
     return cov, proba, g, cloud_d
+
+
+class InferencePipeline:
+    """Batches in flight: `depth` independent stream sets, each running H2D -> forward -> both projections ->
+    D2H for one batch.  FPS is a serial chain that occupies one SM per plot (64 of 148 SMs at config 2) for
+    ~40 % of a batch's latency; with two batches in flight the next batch's copy and FPS run under the current
+    batch's SA / FP kernels.  Per-batch results are identical to the serial path (same kernels, same order
+    inside a batch).
+
+        pipe = InferencePipeline(model, args, depth=2)
+        for batch in loader:
+            slot = pipe.submit(batch)          # returns immediately
+            ... pipe.result(prev_slot) ...     # (plot-wise coverages [B,4], rasters [B,3,D,D]) on the host
+    """
+
+    def __init__(self, model, args, depth: int = 2):
+        self.model, self.args, self.depth = model, args, depth
+        self.device = torch.device("cuda", model.cuda_device)
+        mk = lambda: torch.cuda.Stream(device=self.device)  # noqa: E731
+        self.sets = [(mk(), mk(), mk()) for _ in range(depth)]
+        self.done = [None] * depth
+        self.out = [None] * depth
+        self.k = 0
+
+    def submit(self, cloud_data: dict, keep_on_device: bool = False) -> int:
+        from . import ops as _ops
+
+        slot = self.k % self.depth
+        self.k += 1
+        if self.done[slot] is not None:
+            self.done[slot].synchronize()  # the slot's previous batch (and its pinned buffers) must be finished
+        main, a, b = self.sets[slot]
+        D = int(self.args.diam_pix)
+        launch = torch.cuda.current_stream(self.device)
+        main.wait_stream(launch)
+        with torch.cuda.stream(main), torch.no_grad():
+            cov, proba, g, cloud_d = forward_eval(self.model, cloud_data["xyz"], cloud_data["cloud"], self.device,
+                                                  2000, None, None, side_streams=(a, b))
+            pw = _ops.project_plotwise(cloud_d, cov, D)
+            rs = _ops.project_rasters(cloud_d, cov, "point_major", D, int(self.args.diam_meters))
+            if keep_on_device:
+                self.out[slot] = (pw, rs)
+            else:
+                if self.out[slot] is None or self.out[slot][0].shape != pw.shape or self.out[slot][0].is_cuda:
+                    self.out[slot] = (torch.empty(pw.shape, dtype=pw.dtype).pin_memory(),
+                                      torch.empty(rs.shape, dtype=rs.dtype).pin_memory())
+                self.out[slot][0].copy_(pw, non_blocking=True)
+                self.out[slot][1].copy_(rs, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(main)
+        self.done[slot] = ev
+        return slot
+
+    def result(self, slot: int):
+        self.done[slot].synchronize()
+        return self.out[slot]
+
+    def drain(self):
+        for ev in self.done:
+            if ev is not None:
+                ev.synchronize()
