@@ -161,7 +161,7 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
 template <int NW, int KB, bool PROF = false>
-__global__ void __launch_bounds__(NW * 32, 1)
+__global__ void __launch_bounds__(NW * 32, PROF ? 1 : 2)
 fps_bucket_kernel(const float4 *__restrict__ pos, int N, int M, int P2, const int *__restrict__ start,
                   int *__restrict__ idx_out, float4 *__restrict__ pos_out, long long *__restrict__ prof)
 {
@@ -255,55 +255,60 @@ fps_bucket_kernel(const float4 *__restrict__ pos, int N, int M, int P2, const in
     }
 
     // ---- 3. ownership: thread owns positions (k*NW+warp)*64 + h*32 + lane ----------------------
+    // Pass A parks the sorted original indices in this warp's TMEM key columns (the sort keys share
+    // shared memory with the coordinates and are about to be overwritten); pass B reads them back one
+    // bucket at a time.  No per-thread index array: the kernel stays under 128 registers, so CTAs of
+    // other kernels (SA / FP of another batch in flight) fit on the SM beside the FPS CTA.
     const unsigned st = start ? (unsigned)start[b] : 0u;
     float bv = 0.f;                                             // lane k: current max of bucket slot k
     unsigned bkey = FB_PAD;                                     // lane k: key of the point holding that max
     float blo[3] = {0.f, 0.f, 0.f}, bhi[3] = {0.f, 0.f, 0.f};  // lane k: box of bucket slot k
-    {
-        unsigned orig[KB][2];
-#pragma unroll
-        for (int k = 0; k < KB; ++k)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int pp = ((k * NW + warp) * 64) + h * 32 + lane;
-                orig[k][h] = pp < P2 ? (unsigned)(keys[pp] & 0xffffffffull) : FB_PAD;
-            }
-        __syncthreads();  // keys are dead from here: the region becomes sx/sy/sz
-#pragma unroll
-        for (int k = 0; k < KB; ++k) {
-            float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-            unsigned kk[2];
-            float dd[2];
-            bool any = false;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int pp = ((k * NW + warp) * 64) + h * 32 + lane;
-                const unsigned o = orig[k][h];
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                kk[h] = FB_PAD;
-                if (o != FB_PAD) {
-                    v = __ldg(p + o);
-                    mn[0] = fminf(mn[0], v.x); mx[0] = fmaxf(mx[0], v.x);
-                    mn[1] = fminf(mn[1], v.y); mx[1] = fmaxf(mx[1], v.y);
-                    mn[2] = fminf(mn[2], v.z); mx[2] = fmaxf(mx[2], v.z);
-                    any = true;
-                    if (o == st) s_last = pp;
-                    kk[h] = (o << 16) | (unsigned)pp;
-                }
-                dd[h] = o != FB_PAD ? INFINITY : 0.f;  // padding: dist 0 forever, key PAD -> never wins
-                sx[pp] = v.x; sy[pp] = v.y; sz[pp] = v.z;
-            }
-            tmem_st4(wbase + 4 * k, __float_as_uint(dd[0]), __float_as_uint(dd[1]), kk[0], kk[1]);
-            const bool bany = __any_sync(SN2_FULL, any);
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const float l = -warp_max(-mn[a]), h2 = warp_max(mx[a]);
-                if (lane == k) { blo[a] = l; bhi[a] = h2; }  // empty bucket: (+inf, -inf) -> lb = inf, never active
-            }
-            if (lane == k) bv = bany ? INFINITY : 0.f;
-        }
-        tmem_wait_st();
+#pragma unroll 4
+    for (int k = 0; k < KB; ++k) {
+        const int p0 = ((k * NW + warp) * 64) + lane, p1 = p0 + 32;
+        const unsigned o0 = p0 < P2 ? (unsigned)(keys[p0] & 0xffffffffull) : FB_PAD;
+        const unsigned o1 = p1 < P2 ? (unsigned)(keys[p1] & 0xffffffffull) : FB_PAD;
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};\n" ::"r"(wbase + 4 * k + 2), "r"(o0), "r"(o1));
     }
+    tmem_wait_st();
+    __syncthreads();  // keys are dead from here: the region becomes sx/sy/sz
+#pragma unroll 2
+    for (int k = 0; k < KB; ++k) {
+        unsigned oo[2];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n" : "=r"(oo[0]), "=r"(oo[1]) : "r"(wbase + 4 * k + 2));
+        tmem_wait_ld();
+        float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        unsigned kk[2];
+        float dd[2];
+        bool any = false;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int pp = ((k * NW + warp) * 64) + h * 32 + lane;
+            const unsigned o = oo[h];
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            kk[h] = FB_PAD;
+            if (o != FB_PAD) {
+                v = __ldg(p + o);
+                mn[0] = fminf(mn[0], v.x); mx[0] = fmaxf(mx[0], v.x);
+                mn[1] = fminf(mn[1], v.y); mx[1] = fmaxf(mx[1], v.y);
+                mn[2] = fminf(mn[2], v.z); mx[2] = fmaxf(mx[2], v.z);
+                any = true;
+                if (o == st) s_last = pp;
+                kk[h] = (o << 16) | (unsigned)pp;
+            }
+            dd[h] = o != FB_PAD ? INFINITY : 0.f;  // padding: dist 0 forever, key PAD -> never wins
+            sx[pp] = v.x; sy[pp] = v.y; sz[pp] = v.z;
+        }
+        tmem_st4(wbase + 4 * k, __float_as_uint(dd[0]), __float_as_uint(dd[1]), kk[0], kk[1]);
+        const bool bany = __any_sync(SN2_FULL, any);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float l = -warp_max(-mn[a]), h2 = warp_max(mx[a]);
+            if (lane == k) { blo[a] = l; bhi[a] = h2; }  // empty bucket: (+inf, -inf) -> lb = inf, never active
+        }
+        if (lane == k) bv = bany ? INFINITY : 0.f;
+    }
+    tmem_wait_st();
     __syncthreads();
     int last = s_last;
     if (tid == 0) {

@@ -401,3 +401,32 @@ def test_submodule_forward_matches_reference_modules(cuda_device):
     y, _, _ = net.sa1_module(xin, pos.to(d), batch.to(d))
     y.square().sum().backward()
     assert xin.grad is not None and net.sa1_module.conv.local_nn[0][0].weight.grad is not None
+
+
+def test_inference_pipeline_matches_serial(cuda_device):
+    """Batches in flight on independent stream sets give exactly the serial results."""
+    from model.project_to_2d import project_to_2d_rasters_batched, project_to_plotwise_coverages
+    from sn2.pipeline import InferencePipeline
+
+    N, B = 4096, 3
+    args, net, _ = _make_models(N, cuda_device)
+    batches = [_plots(30 + i, B, N) for i in range(5)]
+    want = []
+    with torch.no_grad():
+        for d in batches:
+            cov, _ = net(d)
+            want.append((project_to_plotwise_coverages(cov, d["cloud"], args).cpu(),
+                         project_to_2d_rasters_batched(d["cloud"], cov, args).cpu()))
+    pipe = InferencePipeline(net, args, depth=3)
+    slots = []
+    got = [None] * len(batches)
+    for i, d in enumerate(batches):
+        if len(slots) == 3:  # collect the oldest before its slot is reused
+            j, s = slots.pop(0)
+            got[j] = tuple(t.clone() for t in pipe.result(s))
+        slots.append((i, pipe.submit(d)))
+    for j, s in slots:
+        got[j] = tuple(t.clone() for t in pipe.result(s))
+    for (pw, rs), (pw0, rs0) in zip(got, want):
+        assert torch.equal(pw, pw0)
+        assert torch.equal(torch.nan_to_num(rs, nan=-1.0), torch.nan_to_num(rs0, nan=-1.0))
