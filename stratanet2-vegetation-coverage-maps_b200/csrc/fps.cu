@@ -8,8 +8,10 @@
 // the candidate indices), one __syncthreads over double-buffered per-warp slots, and every warp
 // re-reduces the slots itself, so there is exactly one barrier per sample.
 #include "sn2_common.cuh"
+#include <cooperative_groups.h>
 
 namespace sn2 {
+namespace cg = cooperative_groups;
 
 __global__ void ingest_kernel(const float *__restrict__ xyz, const float *__restrict__ cloud, int B, int N,
                               int F, float4 *__restrict__ pos4, float4 *__restrict__ feat)
@@ -160,11 +162,16 @@ __device__ __forceinline__ void tmem_st2(unsigned addr, unsigned a, unsigned b)
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
-template <int NW, int KB, bool PROF = false>
-__global__ void __launch_bounds__(NW * 32, PROF ? 1 : 2)
+// CL > 1: a thread-block CLUSTER of CL CTAs shares one plot (N up to CL * 16384): CTA r owns the points
+// [r*NL, (r+1)*NL) with its own Morton order, buckets, shared-memory coordinates and TMEM distances; every
+// warp of every CTA publishes its candidate (value, key, xyz) into the slot table of ALL CTAs through
+// distributed shared memory, one cluster barrier per sample, then every warp reduces the CL*NW candidates.
+template <int NW, int KB, bool PROF = false, int CL = 1>
+__global__ void __launch_bounds__(NW * 32, (PROF || CL > 1) ? 1 : 2)
 fps_bucket_kernel(const float4 *__restrict__ pos, int N, int M, int P2, const int *__restrict__ start,
                   int *__restrict__ idx_out, float4 *__restrict__ pos_out, long long *__restrict__ prof)
 {
+    static_assert(CL * NW <= 32, "one candidate per lane in the final reduction");
     static_assert(KB >= 1 && KB <= 32, "one bucket slot per lane at most");
     static_assert(NW % 4 == 0 && NW <= 32, "whole warpgroups");
     constexpr int THREADS = NW * 32;
@@ -177,13 +184,18 @@ fps_bucket_kernel(const float4 *__restrict__ pos, int N, int M, int P2, const in
     float *sx = reinterpret_cast<float *>(fb_smem);
     float *sy = sx + CAP;
     float *sz = sy + CAP;
-    __shared__ uint2 slot[2][32];
+    __shared__ uint2 slot[2][32];      // (max dist bits, key) per candidate
+    __shared__ float4 slot_xyz[2][32];  // its coordinates
     __shared__ float red[6][32];
-    __shared__ int s_last;
     __shared__ unsigned s_tmem;
 
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float4 *p = pos + (size_t)b * N;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x / CL, rank = blockIdx.x % CL;  // cluster rank == blockIdx.x % CL for 1-D clusters
+    const float4 *pplot = pos + (size_t)b * N;
+    const int NL = (N + CL - 1) / CL;              // points per CTA of the cluster
+    const int i0 = rank * NL;                      // this CTA owns original indices [i0, i0 + n)
+    const int n = max(0, min(NL, N - i0));
+    const float4 *p = pplot + i0;
 
     // ---- 0. tensor-memory scratch ---------------------------------------------------------------
     if (warp == 0) {
@@ -194,7 +206,7 @@ fps_bucket_kernel(const float4 *__restrict__ pos, int N, int M, int P2, const in
 
     // ---- 1. plot bounding box -> Morton keys -------------------------------------------------
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int i = tid; i < N; i += THREADS) {
+    for (int i = tid; i < n; i += THREADS) {
         const float4 v = __ldg(p + i);
         lo[0] = fminf(lo[0], v.x); hi[0] = fmaxf(hi[0], v.x);
         lo[1] = fminf(lo[1], v.y); hi[1] = fmaxf(hi[1], v.y);
@@ -228,13 +240,13 @@ fps_bucket_kernel(const float4 *__restrict__ pos, int N, int M, int P2, const in
     };
     for (int i = tid; i < P2; i += THREADS) {
         unsigned long long k = ~0ull;
-        if (i < N) {
+        if (i < n) {
             const float4 v = __ldg(p + i);
             const unsigned qx = min(1023u, (unsigned)((v.x - lo[0]) * scale));
             const unsigned qy = min(1023u, (unsigned)((v.y - lo[1]) * scale));
             const unsigned qz = min(1023u, (unsigned)((v.z - lo[2]) * scale));
             const unsigned code = spread(qx) | (spread(qy) << 1) | (spread(qz) << 2);
-            k = ((unsigned long long)code << 32) | (unsigned)i;
+            k = ((unsigned long long)code << 32) | (unsigned)(i0 + i);  // original index within the plot
         }
         keys[i] = k;
     }
@@ -288,12 +300,11 @@ fps_bucket_kernel(const float4 *__restrict__ pos, int N, int M, int P2, const in
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             kk[h] = FB_PAD;
             if (o != FB_PAD) {
-                v = __ldg(p + o);
+                v = __ldg(pplot + o);
                 mn[0] = fminf(mn[0], v.x); mx[0] = fmaxf(mx[0], v.x);
                 mn[1] = fminf(mn[1], v.y); mx[1] = fmaxf(mx[1], v.y);
                 mn[2] = fminf(mn[2], v.z); mx[2] = fmaxf(mx[2], v.z);
                 any = true;
-                if (o == st) s_last = pp;
                 kk[h] = (o << 16) | (unsigned)pp;
             }
             dd[h] = o != FB_PAD ? INFINITY : 0.f;  // padding: dist 0 forever, key PAD -> never wins
@@ -310,11 +321,16 @@ fps_bucket_kernel(const float4 *__restrict__ pos, int N, int M, int P2, const in
     }
     tmem_wait_st();
     __syncthreads();
-    int last = s_last;
-    if (tid == 0) {
-        idx_out[(size_t)b * M] = b * N + (int)st;
-        if (pos_out) pos_out[(size_t)b * M] = __ldg(p + st);
+    float lx, ly, lz;  // coordinates of the latest sample (carried through the candidate slots)
+    {
+        const float4 v0 = __ldg(pplot + st);
+        lx = v0.x; ly = v0.y; lz = v0.z;
     }
+    if (tid == 0 && rank == 0) {
+        idx_out[(size_t)b * M] = b * N + (int)st;
+        if (pos_out) pos_out[(size_t)b * M] = make_float4(lx, ly, lz, 0.f);
+    }
+    if constexpr (CL > 1) cg::this_cluster().sync();  // every CTA's slot tables exist before remote writes
 
     // ---- 4. sampling loop ---------------------------------------------------------------------
     int buf = 0;
@@ -323,7 +339,6 @@ fps_bucket_kernel(const float4 *__restrict__ pos, int N, int M, int P2, const in
 #define FB_TICK(i) if (PROF) { long long t_ = clock64(); pt[i] += t_ - tprev; tprev = t_; }
     if (PROF) tprev = clock64();
     for (int it = 1; it < M; ++it) {
-        const float lx = sx[last], ly = sy[last], lz = sz[last];
         bool act = false;
         if (lane < KB) {
             const float cx = fminf(fmaxf(lx, blo[0]), bhi[0]);
@@ -354,32 +369,53 @@ fps_bucket_kernel(const float4 *__restrict__ pos, int N, int M, int P2, const in
         }
         tmem_wait_st();
         FB_TICK(1)
-        // warp arg-max over this warp's bucket slots
+        // warp arg-max over this warp's bucket slots, plus the coordinates of its candidate
         const unsigned vb = lane < KB ? __float_as_uint(bv) : 0u;
         const unsigned wm = __reduce_max_sync(SN2_FULL, vb);
         const unsigned wk = __reduce_min_sync(SN2_FULL, (lane < KB && vb == wm) ? bkey : FB_PAD);
         FB_TICK(2)
-        if (lane == 0) slot[buf][warp] = make_uint2(wm, wk);
-        __syncthreads();
+        if constexpr (CL == 1) {
+            if (lane == 0) slot[buf][warp] = make_uint2(wm, wk);
+            __syncthreads();
+        } else {
+            const int wp = wk == FB_PAD ? 0 : (int)(wk & 0xffffu);
+            const float4 wxyz = make_float4(sx[wp], sy[wp], sz[wp], 0.f);  // peers cannot read this CTA's coordinates
+            if (lane < CL) {  // lane r writes this warp's candidate into CTA r's table (distributed shared memory)
+                cg::cluster_group cluster = cg::this_cluster();
+                uint2 *rs = cluster.map_shared_rank(&slot[buf][rank * NW + warp], lane);
+                float4 *rx = cluster.map_shared_rank(&slot_xyz[buf][rank * NW + warp], lane);
+                *rs = make_uint2(wm, wk);
+                *rx = wxyz;
+            }
+            cg::this_cluster().sync();
+        }
         FB_TICK(3)
-        const uint2 sl = lane < NW ? slot[buf][lane] : make_uint2(0u, FB_PAD);
+        const uint2 sl = lane < CL * NW ? slot[buf][lane] : make_uint2(0u, FB_PAD);
         const unsigned gm = __reduce_max_sync(SN2_FULL, sl.x);
-        const unsigned gk = __reduce_min_sync(SN2_FULL, (lane < NW && sl.x == gm) ? sl.y : FB_PAD);
-        last = (int)(gk & 0xffffu);
-        if (tid == 0) {
+        const unsigned gk = __reduce_min_sync(SN2_FULL, (lane < CL * NW && sl.x == gm) ? sl.y : FB_PAD);
+        if constexpr (CL == 1) {
+            const int gp = (int)(gk & 0xffffu);  // position of the winner in this CTA's bucket order
+            lx = sx[gp]; ly = sy[gp]; lz = sz[gp];
+        } else {
+            const unsigned who = __ballot_sync(SN2_FULL, lane < CL * NW && sl.x == gm && sl.y == gk);
+            const float4 gx = slot_xyz[buf][who ? __ffs(who) - 1 : 0];
+            lx = gx.x; ly = gx.y; lz = gx.z;
+        }
+        if (tid == 0 && rank == 0) {
             idx_out[(size_t)b * M + it] = b * N + (int)(gk >> 16);
-            if (pos_out) pos_out[(size_t)b * M + it] = make_float4(sx[last], sy[last], sz[last], 0.f);
+            if (pos_out) pos_out[(size_t)b * M + it] = make_float4(lx, ly, lz, 0.f);
         }
         buf ^= 1;
         FB_TICK(4)
     }
-    if (PROF && prof && lane == 0) {
+    if (PROF && prof && lane == 0 && rank == 0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) prof[((size_t)b * NW + warp) * 8 + i] = pt[i];
     }
 #undef FB_TICK
     // ---- 5. release tensor memory ---------------------------------------------------------------
     asm volatile("tcgen05.fence::before_thread_sync;\n");
+    if constexpr (CL > 1) cg::this_cluster().sync();  // no CTA leaves while a peer may still write its slots
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TCOLS));
 }
@@ -397,6 +433,36 @@ static int launch_fps_bucket(const float4 *pos, int B, int N, int M, const int *
     SN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fps_bucket attr");
     kern<<<B, NW * 32, smem, st>>>(pos, N, M, P2, start, idx, pos_out, nullptr);
     SN2_LAUNCH_CHECK("fps_bucket_kernel");
+    return SN2_OK;
+}
+
+// N in (16384, 65536]: clusters of 4 CTAs (8 warps, 32 bucket slots per warp each) share a plot
+static int launch_fps_cluster4(const float4 *pos, int B, int N, int M, const int *start, int *idx, float4 *pos_out,
+                               cudaStream_t st)
+{
+    constexpr int CL = 4, NW = 8, KB = 32;
+    const int NL = (N + CL - 1) / CL;
+    if (NL > NW * KB * 64) return SN2_EUNSUPPORTED;
+    int P2 = 64;
+    while (P2 < NL) P2 <<= 1;
+    const size_t cap = (size_t)NW * KB * 64;
+    const size_t smem = 3 * cap * 4 > (size_t)P2 * 8 ? 3 * cap * 4 : (size_t)P2 * 8;
+    auto kern = fps_bucket_kernel<NW, KB, false, CL>;
+    SN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "fps_cluster attr");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B * CL);
+    cfg.blockDim = dim3(NW * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    long long *noprof = nullptr;
+    SN2_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, pos, N, M, P2, start, idx, pos_out, noprof), "fps_cluster launch");
     return SN2_OK;
 }
 
@@ -427,7 +493,7 @@ static int launch_fps(const float4 *pos, int B, int N, int M, const int *start, 
 
 }  // namespace sn2
 
-extern "C" int sn2_fps_max_points(void) { return 16384; }
+extern "C" int sn2_fps_max_points(void) { return 65536; }
 
 extern "C" int sn2_ingest(const float *xyz, const float *cloud, int B, int N, int F, float *pos4, float *feat,
                           void *stream)
@@ -454,6 +520,10 @@ extern "C" int sn2_fps_algo(const float *pos4, int B, int N, int M, const int *s
     using namespace sn2;
     // measured on B200 (tools/bench_fps.py): pruning wins above ~4k points, the plain scan below
     if (algo == SN2_FPS_AUTO) algo = (N > 4096) ? SN2_FPS_BUCKETED : SN2_FPS_BRUTE;
+    if (N > 16384) {  // one CTA holds at most 16384 points (196 KB of coordinates): 4-CTA cluster per plot
+        if (algo == SN2_FPS_BRUTE) return SN2_EUNSUPPORTED;
+        return launch_fps_cluster4(p, B, N, M, start, idx_out, po, st);
+    }
     if (algo == SN2_FPS_BUCKETED) return dispatch_fps_bucket<8>(p, B, N, M, start, idx_out, po, st);
     if (algo == SN2_FPS_BUCKETED16) return dispatch_fps_bucket<16>(p, B, N, M, start, idx_out, po, st);
     if (algo != SN2_FPS_BRUTE) return SN2_EINVAL;

@@ -41,6 +41,19 @@ def test_fps_bit_exact(cuda_device, N, variant):
         assert torch.equal(got.cpu(), want), f"algo {algo}"
 
 
+@pytest.mark.parametrize("B,N,variant", [(2, 20000, "plain"), (2, 40000, "cm"), (1, 65536, "plain"), (3, 16385, "dup")])
+def test_fps_cluster_bit_exact(cuda_device, B, N, variant):
+    """N > 16384: a 4-CTA thread-block cluster per plot (distributed shared memory candidate exchange)."""
+    from oracle import thirdparty_ops as tp
+    from sn2 import ops
+
+    data = _plots(16, B, N, variant)
+    pos, batch = _long(data["xyz"]), _batch(B, N)
+    want = tp.fps(pos, batch, ratio=0.25)
+    got = ops.fps(pos.to(cuda_device), batch.to(cuda_device), ratio=0.25)
+    assert torch.equal(got.cpu(), want)
+
+
 def test_fps_bucketed_degenerate_inputs(cuda_device):
     from oracle import thirdparty_ops as tp
     from sn2 import ops
