@@ -103,8 +103,7 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
     extern __shared__ __align__(16) unsigned char sf_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int *ring = reinterpret_cast<int *>(sf_smem) + warp * RING;
-    unsigned *bm = reinterpret_cast<unsigned *>(sf_smem + SF_WARPS * RING * sizeof(int)) + (size_t)warp * 2 * words;
-    unsigned *pre = bm + words;  // inclusive popc prefix (REDO only)
+    unsigned *bm = reinterpret_cast<unsigned *>(sf_smem + SF_WARPS * RING * sizeof(int)) + (size_t)warp * words;  // REDO only
     const unsigned lt = (1u << lane) - 1u;
 
     // ---- tensor-core state (TC): per-warp operand rows, W2 tiles, per-warp mbarrier, TMEM accumulators ----
@@ -312,7 +311,7 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
         };
         int tc_stage = 0, tc_pending = 0;  // tc_pending = rows of the batch in flight on stage tc_stage ^ 1 (0: none)
 
-        if (REDO) {  // hit set as a bitmap over the plot's point indices + inclusive popcount prefix
+        if (REDO) {  // hit set as a bitmap over the plot's point indices
             for (int w = lane; w < words; w += 32) bm[w] = 0u;
             __syncwarp();
             for (int t = 0; t < nrows; ++t) {
@@ -326,20 +325,6 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
                 }
             }
             __syncwarp();
-            int run = 0;
-            for (int w0 = 0; w0 < words; w0 += 32) {
-                const int w = w0 + lane;
-                const int c1 = w < words ? __popc(bm[w]) : 0;
-                int inc = c1;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(SN2_FULL, inc, o);
-                    if (lane >= o) inc += t;
-                }
-                if (w < words) pre[w] = run + inc;
-                run += __shfl_sync(SN2_FULL, inc, 31);
-            }
-            __syncwarp();
         }
 
         // ---- producer / consumer loop with ONE call site of the message MLP (keeps the loop in I-cache) ----
@@ -347,7 +332,8 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
         int head = 0, tail = 0;          // warp-uniform ring cursors
         int y = 0, base = 0, e = 0;      // streaming iterator: current (layer, cell row) and candidate range
         bool open_row = false;
-        int rank = 0;                    // redo iterator: next rank of the set bits to extract
+        int emitted = 0, wblk = 0;       // redo iterator: set bits emitted so far, next 32-word block of the bitmap
+        unsigned wmask = 0u, wword = 0u; //   non-empty words left in the current block, this lane's word of the block
         bool more = true;
         while (true) {
             while (more && tail - head < 32) {
@@ -377,20 +363,24 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
                     base += 32 * UNR;
                     if (base >= e) { open_row = false; ++y; }
                 } else {
-                    const int rk = rank + lane;  // rank of the set bit this lane extracts (K < #set bits here)
-                    if (rk < K) {
-                        int lo_w = 0, hi_w = words - 1;  // first word with pre[w] > rk
-                        while (lo_w < hi_w) {
-                            const int mid = (lo_w + hi_w) >> 1;
-                            if ((int)pre[mid] > rk) hi_w = mid; else lo_w = mid + 1;
-                        }
-                        const int before = lo_w ? (int)pre[lo_w - 1] : 0;
-                        ring[(tail + lane) & (RING - 1)] = (lo_w << 5) + __fns(bm[lo_w], 0, rk - before + 1);
+                    // first K set bits of the hit bitmap in ascending point index: 32-word blocks, empty words
+                    // skipped by ballot, one word (<= 32 ids) per step, every lane places its own bit by popc rank
+                    if (!wmask) {
+                        if (emitted >= K || wblk >= words) { more = false; break; }
+                        wword = wblk + lane < words ? bm[wblk + lane] : 0u;
+                        wmask = __ballot_sync(SN2_FULL, wword != 0u);
+                        if (!wmask) { wblk += 32; continue; }
                     }
-                    const int n = min(32, K - rank);
+                    const int wl = __ffs(wmask) - 1;
+                    wmask &= wmask - 1;
+                    const unsigned bits = __shfl_sync(SN2_FULL, wword, wl);
+                    const int rk = __popc(bits & lt);
+                    if (((bits >> lane) & 1u) && emitted + rk < K) ring[(tail + rk) & (RING - 1)] = ((wblk + wl) << 5) + lane;
+                    const int n = min(__popc(bits), K - emitted);
                     tail += n;
-                    rank += n;
-                    if (rank >= K) more = false;
+                    emitted += n;
+                    if (!wmask) wblk += 32;
+                    if (emitted >= K) more = false;
                 }
                 __syncwarp();
             }
@@ -444,6 +434,13 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
 }
 
 __global__ void zero_int_kernel(int *p) { *p = 0; }
+// every centroid goes straight to the exact path (small caps bind for most centroids: streaming first is wasted work)
+__global__ void all_overflow_kernel(int *ovf, int total)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) ovf[0] = total;
+    if (i < total) ovf[1 + i] = i;
+}
 
 template <int LEVEL>
 static int launch_sa_fused(const float *grid_hdr, const int *cell_start, const float *sorted4, const float *qsorted4,
@@ -460,8 +457,13 @@ static int launch_sa_fused(const float *grid_hdr, const int *cell_start, const f
     const int words = (N + 31) / 32;
     const size_t smem_ring = (size_t)SF_WARPS * 256 * sizeof(int);
     dim3 grid((M + SF_WARPS - 1) / SF_WARPS, B);
+    const bool exact_only = K < 256 && K < N;
+    if (exact_only) {
+        all_overflow_kernel<<<(B * M + 255) / 256, 256, 0, st>>>(ovf, B * M);
+        tc = 0;
+    }
     if constexpr (LEVEL == 1) {
-        if (tc) {  // second layer on the tensor cores (tcgen05): 1 = 3xTF32, 2 = plain TF32
+        if (tc && !exact_only) {  // second layer on the tensor cores (tcgen05): 1 = 3xTF32, 2 = plain TF32
             auto kern = tc == 1 ? sa_fused_kernel<1, false, 0, 1> : sa_fused_kernel<1, false, 0, 2>;
             const size_t smem_tc = smem_ring + TC_SMEM;
             SN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc), "sa_fused_tc attr");
@@ -471,7 +473,7 @@ static int launch_sa_fused(const float *grid_hdr, const int *cell_start, const f
             SN2_LAUNCH_CHECK("sa_fused_kernel<tc>");
         }
     }
-    if (!(LEVEL == 1 && tc)) {
+    if (!(LEVEL == 1 && tc) && !exact_only) {
         auto kern = sa_fused_kernel<LEVEL, false>;
         kern<<<grid, SF_WARPS * 32, smem_ring, st>>>(grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4),
                                                      reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, 0, w,
@@ -479,7 +481,7 @@ static int launch_sa_fused(const float *grid_hdr, const int *cell_start, const f
         SN2_LAUNCH_CHECK("sa_fused_kernel");
     }
     if (K < N) {  // the cap can bind: exact redo of the overflow list (exits at once when the list is empty)
-        const size_t smem = smem_ring + (size_t)SF_WARPS * 2 * words * sizeof(unsigned);
+        const size_t smem = smem_ring + (size_t)SF_WARPS * words * sizeof(unsigned);
         if (smem > 200 * 1024) return SN2_EUNSUPPORTED;
         auto kern = sa_fused_kernel<LEVEL, true>;
         SN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sa_fused attr");

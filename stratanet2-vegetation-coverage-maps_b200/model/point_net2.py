@@ -52,7 +52,7 @@ def MLP(channels, batch_norm=True):
 
 class SAModule(nn.Module):
     """Set abstraction: fps -> radius (cap 2000) -> PointConv max (reference :14-29)."""
-    max_num_neighbors = 2000  # hard-coded at reference :24
+    max_num_neighbors = 2000  # hard-coded at reference :24 (set the attribute on an instance to change the cap)
 
     def __init__(self, ratio, r, nn):
         super().__init__()
@@ -141,13 +141,13 @@ class PointNet2(nn.Module):
         with torch.cuda.device(device):
             if self.training and torch.is_grad_enabled():
                 cov, proba, g, cloud_dev = _pipeline.forward_train(
-                    self, cloud_data["xyz"], cloud_data["cloud"], device, SAModule.max_num_neighbors, trace, timer)
+                    self, cloud_data["xyz"], cloud_data["cloud"], device, self.sa1_module.max_num_neighbors, trace, timer)
             elif self.training:
                 raise RuntimeError("sn2 PointNet2: training mode under no_grad is not supported (BatchNorm batch "
                                    "statistics are only implemented on the autograd path); call model.eval()")
             else:
                 cov, proba, g, cloud_dev = _pipeline.forward_eval(
-                    self, cloud_data["xyz"], cloud_data["cloud"], device, SAModule.max_num_neighbors, trace, timer)
+                    self, cloud_data["xyz"], cloud_data["cloud"], device, self.sa1_module.max_num_neighbors, trace, timer)
         if self.log_embeddings:
             self.last_G_tensor = g
         # device copy of the normalised cloud, reused by model.project_to_2d to skip a second H2D

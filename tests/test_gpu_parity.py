@@ -175,14 +175,18 @@ def _make_models(N, device):
     return args, net, port
 
 
-@pytest.mark.parametrize("B,N,variant", [(1, 10000, "plain"), (3, 4096, "cm"), (2, 16384, "plain"), (2, 10000, "dup")])
-def test_forward_parity(cuda_device, B, N, variant):
+@pytest.mark.parametrize("B,N,variant,K", [(1, 10000, "plain", 2000), (3, 4096, "cm", 2000), (2, 16384, "plain", 2000),
+                                           (2, 10000, "dup", 2000), (1, 32768, "plain", 64), (1, 65536, "cm", 64)])
+def test_forward_parity(cuda_device, B, N, variant, K):
+    """Whole eval forward vs the oracle.  K = 64 with 32k / 64k-point plots is BASELINE config 5's dense-cloud
+    setting: the cap binds for most centroids (exact first-K-by-index redo) and FPS runs on 4-CTA clusters."""
     from sn2.pipeline import ForwardTrace
 
     args, net, port = _make_models(N, cuda_device)
+    net.sa1_module.max_num_neighbors = K
     data = _plots(1, B, N, variant)
     with torch.no_grad():
-        cov_o, proba_o = port(data, trace=True)
+        cov_o, proba_o = port(data, max_num_neighbors=K, trace=True)
         tr = ForwardTrace()
         cov, proba = net(data, trace=tr)
     t, o = tr.tensors, port.trace
