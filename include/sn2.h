@@ -189,6 +189,17 @@ int sn2_interp_plot_bwd(const float *dy, const float *pos4, int B, int M, int C,
 /* backward of sn2_project_plotwise: dpred [B*N,4] (zero-initialised) from dout [B,4] and parg [B,3,D,D]. */
 int sn2_project_plotwise_bwd(const float *dout, const int *parg, int B, int D, float *dpred, void *stream);
 
+/* ================= local-map fusion (BASELINE config 4), csrc/fusion.cu =============
+ * Weighted-average mosaic of per-plot rasters into the parcel grid; replaces add_weights_band_to_rasters +
+ * rasterio.merge(method=_weighted_average_of_rasters) (inference/geotiff_raster.py:103-118, 199-235, 294-347).
+ * rasters [P,3,D,D] float64 (NaN = no value), offsets [P,2] int32 = (row, col) of each plot's top-left pixel in
+ * the parcel grid; num/den [3,H,W] and wsum [H,W] float64 accumulators (zero-initialised by the caller; may be
+ * all-reduced across ranks before finalize).  out [4,H,W]: 3 averaged bands + sum of weights, NaN where empty. */
+int sn2_fuse_accumulate(const double *rasters, const int *offsets, int P, int D, int H, int W, double *num,
+                        double *den, double *wsum, void *stream);
+int sn2_fuse_finalize(const double *num, const double *den, const double *wsum, int H, int W, double *out,
+                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -447,3 +447,46 @@ def test_inference_pipeline_matches_serial(cuda_device):
     for (pw, rs), (pw0, rs0) in zip(got, want):
         assert torch.equal(pw, pw0)
         assert torch.equal(torch.nan_to_num(rs, nan=-1.0), torch.nan_to_num(rs0, nan=-1.0))
+
+
+def test_local_map_fusion_matches_reference_rule(cuda_device):
+    """GPU weighted-average mosaic == the reference's pairwise rasterio.merge rule (restated) on a grid of
+    overlapping plots whose in-disk pixels all carry a value; plus the order-independent definition when some
+    in-disk pixels are NaN."""
+    from oracle.fusion_port import fuse_sequential, weight_image
+    from sn2.fusion import MapFusion, mosaic_frame, plot_centers
+
+    D = 20
+    centers = plot_centers(0.0, 60.0, 0.0, 45.0)
+    left, top, H, W, offsets = mosaic_frame(centers)
+    P = centers.shape[0]
+    rng = np.random.default_rng(0)
+    disk = ~np.isnan(weight_image(D))
+    rasters = rng.random((P, 3, D, D))
+    rasters[:, :, ~disk] = np.nan
+    want = fuse_sequential(rasters, offsets, H, W)
+    fus = MapFusion(H, W, D, cuda_device)
+    half = P // 2  # two calls, as two batches / ranks would contribute
+    fus.add(torch.from_numpy(rasters[:half]).to(cuda_device), torch.from_numpy(offsets[:half]).to(cuda_device))
+    fus.add(torch.from_numpy(rasters[half:]).to(cuda_device), torch.from_numpy(offsets[half:]).to(cuda_device))
+    got = fus.finalize().cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    np.testing.assert_allclose(np.nan_to_num(got), np.nan_to_num(want), rtol=1e-10, atol=1e-12)
+    # with holes inside the disks the definition is sum(s*w)/sum(w over plots that have a value)
+    rasters2 = rasters.copy()
+    holes = rng.random((P, D, D)) < 0.2
+    rasters2[np.broadcast_to(holes[:, None], rasters2.shape)] = np.nan
+    w = weight_image(D)
+    num = np.zeros((3, H, W)); den = np.zeros((3, H, W))
+    for p in range(P):
+        r0, c0 = offsets[p]
+        ok = ~np.isnan(rasters2[p]) & disk
+        num[:, r0:r0 + D, c0:c0 + D] += np.where(ok, rasters2[p] * w, 0.0)
+        den[:, r0:r0 + D, c0:c0 + D] += np.where(ok, w, 0.0)
+    fus = MapFusion(H, W, D, cuda_device)
+    fus.add(torch.from_numpy(rasters2).to(cuda_device), torch.from_numpy(offsets).to(cuda_device))
+    got2 = fus.finalize().cpu().numpy()[:3]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        want2 = np.where(den > 0, num / den, np.nan)
+    assert np.array_equal(np.isnan(got2), np.isnan(want2))
+    np.testing.assert_allclose(np.nan_to_num(got2), np.nan_to_num(want2), rtol=1e-10, atol=1e-12)
