@@ -397,7 +397,9 @@ def run_parcel(opts, cfg):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_res, ms_e2e = float(t[0]), float(t[1])
-    covered = float((~torch.isnan(one_pass(pool_dev, False)[3])).float().mean()) if rank == 0 else 0.0
+    with torch.no_grad():
+        last = one_pass(pool_dev, False)  # every rank takes part in the all-reduce inside finalize()
+    covered = float((~torch.isnan(last[3])).float().mean())
     out = {
         "metric": "plots/sec (parcel inference: PointNet2 eval forward + rasters + local-map fusion)", "value": P / (ms_res / 1e3),
         "unit": "plots/s", "n_gpus": world, "steps": reps, "warmup": 2, "ms_per_step": ms_res,
