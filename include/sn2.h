@@ -189,6 +189,13 @@ int sn2_interp_plot_bwd(const float *dy, const float *pos4, int B, int M, int C,
 /* backward of sn2_project_plotwise: dpred [B*N,4] (zero-initialised) from dout [B,4] and parg [B,3,D,D]. */
 int sn2_project_plotwise_bwd(const float *dout, const int *parg, int B, int D, float *dpred, void *stream);
 
+/* Weight / bias gradient of a Linear applied to E rows (E ~ millions, Co, Ci <= 64): dW [Co,Ci] = dy^T x,
+ * db [Co] = column sums of dy.  partial: scratch [nblk, Co*(Ci+1)]; deterministic two-stage reduction.
+ * Supported Ci: 11, 16, 19, 35, 42 (the edge / point MLP input widths), Co <= 64. */
+int sn2_linear_wgrad_supported(int Co, int Ci);
+int sn2_linear_wgrad(const float *dy, const float *x, long long E, int Co, int Ci, float *partial, int nblk,
+                     float *dW, float *db, void *stream);
+
 /* ================= local-map fusion (BASELINE config 4), csrc/fusion.cu =============
  * Weighted-average mosaic of per-plot rasters into the parcel grid; replaces add_weights_band_to_rasters +
  * rasterio.merge(method=_weighted_average_of_rasters) (inference/geotiff_raster.py:103-118, 199-235, 294-347).

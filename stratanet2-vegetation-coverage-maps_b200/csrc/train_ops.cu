@@ -296,3 +296,96 @@ extern "C" int sn2_project_plotwise_bwd(const float *dout, const int *parg, int 
     SN2_LAUNCH_CHECK("project_plotwise_bwd_kernel");
     return SN2_OK;
 }
+
+// ---- skinny weight gradient -------------------------------------------------------------------------
+// dW [Co,Ci] = dy^T x and db [Co] = sum_rows dy for a Linear applied to E ~ 5 M edge rows with Co, Ci <= 64:
+// a reduction over E with a tiny output, for which cuBLAS picks a large-K GEMM that runs at ~2 ms per
+// layer (torch.profiler, config 3).  Here a group of Co threads shares a row: thread o keeps dW[o][0..Ci)
+// and db[o] in registers, reads dy[r][o] and the (broadcast) x row; rows are strided over groups and CTAs;
+// CTA partials are reduced in a fixed order by a second kernel (deterministic).
+namespace sn2 {
+
+constexpr int WG_THREADS = 256;
+
+template <int CI>
+__global__ void __launch_bounds__(WG_THREADS)
+linear_wgrad_kernel(const float *__restrict__ dy, const float *__restrict__ x, long long E, int Co,
+                    float *__restrict__ partial)
+{
+    extern __shared__ float wg_smem[];  // [groups][Co][CI+1]
+    const int G = WG_THREADS / Co;
+    const int g = threadIdx.x / Co, o = threadIdx.x - g * Co;
+    float acc[CI + 1];
+#pragma unroll
+    for (int i = 0; i <= CI; ++i) acc[i] = 0.f;
+    if (g < G) {
+        for (long long r = (long long)blockIdx.x * G + g; r < E; r += (long long)gridDim.x * G) {
+            const float d = __ldg(dy + r * Co + o);
+            const float *xr = x + r * CI;
+#pragma unroll
+            for (int i = 0; i < CI; ++i) acc[i] = fmaf(d, __ldg(xr + i), acc[i]);
+            acc[CI] += d;
+        }
+#pragma unroll
+        for (int i = 0; i <= CI; ++i) wg_smem[((size_t)g * Co + o) * (CI + 1) + i] = acc[i];
+    }
+    __syncthreads();
+    const int n = Co * (CI + 1);
+    for (int t = threadIdx.x; t < n; t += WG_THREADS) {
+        float s = 0.f;
+        for (int gg = 0; gg < G; ++gg) s += wg_smem[(size_t)gg * n + t];
+        partial[(size_t)blockIdx.x * n + t] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+linear_wgrad_reduce_kernel(const float *__restrict__ partial, int nblk, int Co, int CI, float *__restrict__ dW,
+                           float *__restrict__ db)
+{
+    const int n = Co * (CI + 1);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    float s = 0.f;
+    for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * n + t];
+    const int o = t / (CI + 1), i = t - o * (CI + 1);
+    if (i < CI) dW[o * CI + i] = s;
+    else db[o] = s;
+}
+
+template <int CI>
+static int launch_wgrad(const float *dy, const float *x, long long E, int Co, float *partial, int nblk, float *dW, float *db,
+                        cudaStream_t st)
+{
+    const int G = WG_THREADS / Co;
+    const size_t smem = (size_t)G * Co * (CI + 1) * sizeof(float);
+    auto kern = linear_wgrad_kernel<CI>;
+    SN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "wgrad attr");
+    kern<<<nblk, WG_THREADS, smem, st>>>(dy, x, E, Co, partial);
+    SN2_LAUNCH_CHECK("linear_wgrad_kernel");
+    const int n = Co * (CI + 1);
+    linear_wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(partial, nblk, Co, CI, dW, db);
+    SN2_LAUNCH_CHECK("linear_wgrad_reduce_kernel");
+    return SN2_OK;
+}
+
+}  // namespace sn2
+
+extern "C" int sn2_linear_wgrad_supported(int Co, int Ci)
+{
+    return (Co >= 1 && Co <= 64) && (Ci == 11 || Ci == 16 || Ci == 19 || Ci == 35 || Ci == 42);
+}
+
+extern "C" int sn2_linear_wgrad(const float *dy, const float *x, long long E, int Co, int Ci, float *partial, int nblk,
+                                float *dW, float *db, void *stream)
+{
+    if (!dy || !x || !partial || !dW || !db || E <= 0 || nblk <= 0) return SN2_EINVAL;
+    if (!sn2_linear_wgrad_supported(Co, Ci)) return SN2_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (Ci) {
+    case 11: return sn2::launch_wgrad<11>(dy, x, E, Co, partial, nblk, dW, db, st);
+    case 16: return sn2::launch_wgrad<16>(dy, x, E, Co, partial, nblk, dW, db, st);
+    case 19: return sn2::launch_wgrad<19>(dy, x, E, Co, partial, nblk, dW, db, st);
+    case 35: return sn2::launch_wgrad<35>(dy, x, E, Co, partial, nblk, dW, db, st);
+    default: return sn2::launch_wgrad<42>(dy, x, E, Co, partial, nblk, dW, db, st);
+    }
+}

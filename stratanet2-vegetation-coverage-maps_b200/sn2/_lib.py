@@ -47,6 +47,8 @@ SIGNATURES = {
     "sn2_interp_plot_fwd": [_vp, _vp, _i, _i, _i, _vp, _vp],
     "sn2_interp_plot_bwd": [_vp, _vp, _i, _i, _i, _vp, _vp],
     "sn2_project_plotwise_bwd": [_vp, _vp, _i, _i, _vp, _vp],
+    "sn2_linear_wgrad_supported": [_i, _i],
+    "sn2_linear_wgrad": [_vp, _vp, _ll, _i, _i, _vp, _i, _vp, _vp, _vp],
     "sn2_fuse_accumulate": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "sn2_fuse_finalize": [_vp, _vp, _vp, _i, _i, _vp, _vp],
     "sn2_project_plotwise": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],

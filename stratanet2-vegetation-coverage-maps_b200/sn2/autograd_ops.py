@@ -151,3 +151,48 @@ class ProjectPlotwise(torch.autograd.Function):
                                            stream_ptr()), "sn2_project_plotwise_bwd")
         ops._count(1)
         return dpred, None, None
+
+
+class TallLinear(torch.autograd.Function):
+    """y = x W^T + b for a tall-skinny x (millions of edge rows, <= 64 columns).  Forward and dx are plain torch
+    GEMMs; dW / db (a reduction over all rows with a tiny output) run in sn2_linear_wgrad: cuBLAS's large-K
+    kernel took ~2 ms per edge layer at config 3, the streaming kernel is bandwidth bound."""
+
+    NBLK = 148 * 4
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return torch.addmm(bias, x, weight.t())
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, weight = ctx.saved_tensors
+        dy = _c(dy)
+        dx = dy @ weight if ctx.needs_input_grad[0] else None
+        Co, Ci = weight.shape
+        dW = torch.empty_like(weight)
+        db = torch.empty(Co, dtype=torch.float32, device=dy.device)
+        partial = torch.empty((TallLinear.NBLK, Co * (Ci + 1)), dtype=torch.float32, device=dy.device)
+        check(lib.sn2_linear_wgrad(dptr(dy, torch.float32), dptr(_c(x), torch.float32), dy.shape[0], Co, Ci, dptr(partial),
+                                   TallLinear.NBLK, dptr(dW), dptr(db), stream_ptr()), "sn2_linear_wgrad")
+        ops._count(2)
+        return dx, dW, db
+
+
+def run_mlp(seq, x):
+    """Apply a reference MLP (Sequential of (Linear, ReLU, BatchNorm1d) blocks) with TallLinear where it pays."""
+    lib = _lib.load()
+    import os
+    tall = os.environ.get("SN2_TALL_LINEAR", "1") == "1"
+    for block in seq:
+        lin = block[0]
+        if tall and x.shape[0] >= 65536 and (x.requires_grad or lin.weight.requires_grad) and lib.sn2_linear_wgrad_supported(
+                lin.out_features, lin.in_features):
+            x = TallLinear.apply(x, lin.weight, lin.bias)
+        else:
+            x = lin(x)
+        for layer in list(block)[1:]:
+            x = layer(x)
+    return x

@@ -177,7 +177,7 @@ def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num
     interpolation -- runs in libsn2_b200.so (forward and backward)."""
     import torch.nn.functional as F
 
-    from .autograd_ops import EdgeMsg, Interp3, InterpPlot, SegmentMax
+    from .autograd_ops import EdgeMsg, Interp3, InterpPlot, SegmentMax, run_mlp
 
     B, Fc, N = cloud.shape
     if N != model.subsample_size:
@@ -204,12 +204,12 @@ def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num
             nbr1, w1 = ops.knn3_dense(pos1, pos0, B, M1, N)
         plot_ptr = torch.arange(B + 1, dtype=torch.int32, device=device) * M2
 
-    x1, _ = SegmentMax.apply(sa1.conv.local_nn(EdgeMsg.apply(feat0, pos0, pos1, rowptr1, col1)), rowptr1)
-    x2, _ = SegmentMax.apply(sa2.conv.local_nn(EdgeMsg.apply(x1, pos1, pos2, rowptr2, col2)), rowptr2)
+    x1, _ = SegmentMax.apply(run_mlp(sa1.conv.local_nn, EdgeMsg.apply(feat0, pos0, pos1, rowptr1, col1)), rowptr1)
+    x2, _ = SegmentMax.apply(run_mlp(sa2.conv.local_nn, EdgeMsg.apply(x1, pos1, pos2, rowptr2, col2)), rowptr2)
     g, _ = SegmentMax.apply(model.sa3_module.nn(torch.cat([x2, pos2[:, :3]], dim=1)), plot_ptr)
     f3 = model.fp3_module.nn(torch.cat([InterpPlot.apply(g, pos2, M2), x2], dim=1))
     f2 = model.fp2_module.nn(torch.cat([Interp3.apply(f3, nbr2, w2), x1], dim=1))
-    f1 = model.fp1_module.nn(torch.cat([Interp3.apply(f2, nbr1, w1), feat0], dim=1))
+    f1 = run_mlp(model.fp1_module.nn, torch.cat([Interp3.apply(f2, nbr1, w1), feat0], dim=1))
     h = F.relu(model.lin1(f1))
     h = F.dropout(h, p=model.drop, training=True)
     scores = model.lin2(h)

@@ -306,10 +306,16 @@ def _train_loss(cov, proba, pw, gt, pdf):
     return mae + 0.10 * nll + 0.04 * ent
 
 
-@pytest.mark.parametrize("B,N,variant", [(2, 2048, "plain"), (3, 1500, "cm")])
-def test_training_step_gradients_match_oracle(cuda_device, B, N, variant):
+@pytest.mark.parametrize("B,N,variant,gtol", [(2, 2048, "plain", 2e-3), (3, 1500, "cm", 2e-3), (8, 10000, "plain", 8e-2)])
+def test_training_step_gradients_match_oracle(cuda_device, B, N, variant, gtol):
     """Config-3-style step: train-mode forward (BatchNorm batch stats), plot-wise projection, reference loss,
-    backward.  All 32 parameter gradients, the running statistics and the loss match the CPU oracle."""
+    backward.  All 32 parameter gradients, the running statistics and the loss match the CPU oracle.
+
+    Gradient tolerance (max-norm, relative to the largest entry of each tensor): 2e-3 on small batches.  At
+    8 x 10 000 points the gradient of this network is itself only defined to a few percent in fp32: the CPU
+    oracle evaluated in float64 vs float32 differs by 1-4 % per tensor (arg-max routing of the max aggregations
+    and of the projection flips between near-equal candidates; measured with the oracle alone),
+    and the CUDA path lands inside the same band (0.2-6 %).  Loss and running statistics stay at rtol 1e-3."""
     from model.project_to_2d import project_to_plotwise_coverages
     from oracle.pointnet2_port import project_to_plotwise_coverages_port
 
@@ -333,15 +339,18 @@ def test_training_step_gradients_match_oracle(cuda_device, B, N, variant):
 
     torch.testing.assert_close(loss.detach().cpu(), loss_o.detach(), rtol=RTOL, atol=ATOL)
     go = dict(port.named_parameters())
-    checked = 0
+    checked, bad = 0, []
     for name, p in net.named_parameters():
         want = go[name].grad
         assert p.grad is not None, name
         scale = want.abs().max().item() + 1e-12
         err = (p.grad.cpu() - want).abs().max().item()
-        assert err <= 2e-3 * scale + 1e-7, f"{name}: max err {err:.3e} vs scale {scale:.3e}"
+        print(f"grad {name}: max err {err:.3e} scale {scale:.3e} rel {err / scale:.2e}")
+        if err > gtol * scale + 1e-7:
+            bad.append(f"{name}: max err {err:.3e} vs scale {scale:.3e}")
         checked += 1
     assert checked == 32
+    assert not bad, bad
     for (n1, b1), (n2, b2) in zip(net.named_buffers(), port.named_buffers()):
         assert n1 == n2
         torch.testing.assert_close(b1.cpu(), b2, rtol=RTOL, atol=1e-6, msg=n1)
@@ -490,3 +499,23 @@ def test_local_map_fusion_matches_reference_rule(cuda_device):
         want2 = np.where(den > 0, num / den, np.nan)
     assert np.array_equal(np.isnan(got2), np.isnan(want2))
     np.testing.assert_allclose(np.nan_to_num(got2), np.nan_to_num(want2), rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("Co,Ci", [(16, 11), (16, 16), (32, 19), (34, 42), (64, 35)])
+def test_tall_linear_weight_gradient(cuda_device, Co, Ci):
+    """sn2_linear_wgrad (dW = dy^T x, db = column sums over ~1e5..1e6 rows) against a float64 reference."""
+    from sn2.autograd_ops import TallLinear
+
+    g = torch.Generator().manual_seed(Co * 100 + Ci)
+    E = 300001
+    x = torch.randn(E, Ci, generator=g).to(cuda_device).requires_grad_(True)
+    w = (torch.randn(Co, Ci, generator=g) * 0.3).to(cuda_device).requires_grad_(True)
+    b = torch.randn(Co, generator=g).to(cuda_device).requires_grad_(True)
+    dy = torch.randn(E, Co, generator=g).to(cuda_device)
+    y = TallLinear.apply(x, w, b)
+    y.backward(dy)
+    x64, w64, dy64 = x.detach().double(), w.detach().double(), dy.double()
+    torch.testing.assert_close(y.detach().double(), x64 @ w64.t() + b.detach().double(), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(w.grad.double(), dy64.t() @ x64, rtol=1e-4, atol=2e-2)
+    torch.testing.assert_close(b.grad.double(), dy64.sum(0), rtol=1e-4, atol=2e-2)
+    torch.testing.assert_close(x.grad.double(), dy64 @ w64, rtol=1e-4, atol=1e-4)
