@@ -353,7 +353,7 @@ def test_training_step_gradients_match_oracle(cuda_device, B, N, variant, gtol):
     assert not bad, bad
     for (n1, b1), (n2, b2) in zip(net.named_buffers(), port.named_buffers()):
         assert n1 == n2
-        torch.testing.assert_close(b1.cpu(), b2, rtol=RTOL, atol=1e-6, msg=n1)
+        torch.testing.assert_close(b1.cpu(), b2, rtol=RTOL, atol=2e-5, msg=n1)  # running stats, fp32 means over ~1e6 rows
 
 
 def default_args_cpu(N):
