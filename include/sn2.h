@@ -70,8 +70,9 @@ int sn2_fps(const float *pos4, int B, int N, int M, const int *start, int *idx_o
             float *pos4_out, void *stream);
 /* Same contract with an explicit algorithm: both produce identical indices.
  * BRUTE: every point updated every iteration; BUCKETED: Morton-sorted 64-point buckets with exact
- * bounding-box pruning (csrc/fps.cu); AUTO picks BUCKETED for N >= 1024. */
-enum { SN2_FPS_AUTO = 0, SN2_FPS_BRUTE = 1, SN2_FPS_BUCKETED = 2 /* 8 warps */, SN2_FPS_BUCKETED16 = 3 /* 16 warps */ };
+ * bounding-box pruning (csrc/fps.cu); AUTO picks BUCKETED above 4096 points, BRUTE below. */
+enum { SN2_FPS_AUTO = 0, SN2_FPS_BRUTE = 1, SN2_FPS_BUCKETED = 2,
+       SN2_FPS_BUCKETED_SPEC4 = 3 /* experimental: speculative 4-sample rounds, same indices, currently slower */ };
 int sn2_fps_algo(const float *pos4, int B, int N, int M, const int *start, int *idx_out,
                  float *pos4_out, int algo, void *stream);
 

@@ -35,7 +35,7 @@ def test_fps_bit_exact(cuda_device, N, variant):
     data = _plots(11, B, N, variant)
     pos, batch = _long(data["xyz"]), _batch(B, N)
     want = tp.fps(pos, batch, ratio=0.25)
-    for algo in (ops.FPS_BRUTE, ops.FPS_BUCKETED, ops.FPS_BUCKETED16, ops.FPS_AUTO):
+    for algo in (ops.FPS_BRUTE, ops.FPS_BUCKETED, ops.FPS_BUCKETED_SPEC4, ops.FPS_AUTO):
         got = ops.fps(pos.to(cuda_device), batch.to(cuda_device), ratio=0.25, algo=algo)
         assert got.dtype == torch.int64
         assert torch.equal(got.cpu(), want), f"algo {algo}"
@@ -63,7 +63,7 @@ def test_fps_bucketed_degenerate_inputs(cuda_device):
              torch.tensor([[0., 0, 0], [1, 1, 1], [5, 0, 2]]).repeat(700, 1)]
     for pos in cases:
         want = tp.fps(pos, None, ratio=0.25)
-        for algo in (ops.FPS_BRUTE, ops.FPS_BUCKETED, ops.FPS_BUCKETED16):
+        for algo in (ops.FPS_BRUTE, ops.FPS_BUCKETED, ops.FPS_BUCKETED_SPEC4):
             got = ops.fps(pos.to(cuda_device), None, ratio=0.25, algo=algo).cpu()
             assert torch.equal(got, want), f"algo {algo}"
 

@@ -20,7 +20,7 @@ for B, N in ((64, 16384), (32, 10000), (1, 10000), (64, 4096), (64, 2500)):
     pos0, _ = ops.ingest(data["xyz"].to(dev), data["cloud"].to(dev))
     M = ops.m_of(N, 0.25)
     ref = None
-    for name, algo in (("brute", 1), ("bucket8", 2), ("bucket16", 3)):
+    for name, algo in (("brute", 1), ("bucket", 2), ("bucket_spec4", 3)):
         ms = t(lambda: ops.fps_dense(pos0, B, N, M, None, algo))
         idx, _ = ops.fps_dense(pos0, B, N, M, None, algo)
         same = True if ref is None else bool(torch.equal(idx, ref))

@@ -12,14 +12,17 @@ for B, N in ((8, 16384), (8, 4096)):
     data = synth_batch(2, B, N)
     pos0, _ = ops.ingest(data["xyz"].to(dev), data["cloud"].to(dev))
     M = ops.m_of(N, 0.25)
-    for nw in (8, 16):
+    for nw in (8,):
         idx = torch.empty(B * M, dtype=torch.int32, device=dev)
         prof = torch.zeros(B * nw * 8, dtype=torch.int64, device=dev)
         rc = lib.sn2_debug_fps_profile(vp(pos0.data_ptr()), B, N, M, vp(idx.data_ptr()), vp(prof.data_ptr()), nw, None)
         torch.cuda.synchronize()
-        p = prof.view(B, nw, 8).double().cpu() / (M - 1)
-        names = ["test+ballot", "updates", "warp argmax", "barrier", "block argmax", "-", "active/warp", "-"]
-        print(f"N={N} nw={nw} rc={rc}: per-iteration cycles (mean over warps of plot 0 | max over warps)")
+        raw = prof.view(B, nw, 8).double().cpu()
+        rounds = raw[0, 0, 5].item()
+        print(f"rounds {rounds:.0f} for {M - 1} samples -> {(M - 1) / rounds:.2f} accepted per round")
+        p = raw / rounds
+        names = ["test+ballot", "updates", "warp top-4", "barrier", "global top-4", "rounds", "active/warp", "-"]
+        print(f"N={N} nw={nw} rc={rc}: cycles per ROUND (mean / min / max over the warps of plot 0)")
         for k, nme in enumerate(names):
             if nme != "-":
                 print(f"   {nme:14s} mean {p[0,:,k].mean():8.1f}   min {p[0,:,k].min():8.1f}   max {p[0,:,k].max():8.1f}")
