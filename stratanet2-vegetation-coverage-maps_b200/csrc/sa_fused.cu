@@ -174,17 +174,23 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
         auto row_of = [&](int t) { return ((z0 + t / ny) * gy + (y0 + t % ny)) * gx; };
 
         // c_i = b1 - W1p q  (the per-centroid half of the first layer)
-        float c[C];
+        // level 1: every lane keeps all C channels (lane = edge); level 2: lane = channel (C == 32), so the
+        // running max / min, c_i and the BN affine are per-lane scalars and u_j rows are read fully coalesced
+        constexpr int CL_ = LEVEL == 1 ? C : 1;
+        float c[CL_];
+        float mx[CL_], mn[1];
+        if constexpr (LEVEL == 1) {
 #pragma unroll
-        for (int o = 0; o < C; ++o)
-            c[o] = W.l1.b[o] - (W.l1.w[E::CIN][o] * q.x + W.l1.w[E::CIN + 1][o] * q.y + W.l1.w[E::CIN + 2][o] * q.z);
-        // level 1: mx = running max of the layer-2 output; level 2: mx / mn = running max / min of u_j
-        float mx[C], mn[LEVEL == 2 ? C : 1];
+            for (int o = 0; o < C; ++o)
+                c[o] = W.l1.b[o] - (W.l1.w[E::CIN][o] * q.x + W.l1.w[E::CIN + 1][o] * q.y + W.l1.w[E::CIN + 2][o] * q.z);
 #pragma unroll
-        for (int o = 0; o < C; ++o) mx[o] = -INFINITY;
-        if (LEVEL == 2) {
-#pragma unroll
-            for (int o = 0; o < C; ++o) mn[o] = INFINITY;
+            for (int o = 0; o < C; ++o) mx[o] = -INFINITY;
+            mn[0] = 0.f;
+        } else {
+            static_assert(LEVEL == 1 || C == 32, "level 2 maps one channel to each lane");
+            c[0] = W.l1.b[lane] - (W.l1.w[E::CIN][lane] * q.x + W.l1.w[E::CIN + 1][lane] * q.y + W.l1.w[E::CIN + 2][lane] * q.z);
+            mx[0] = -INFINITY;
+            mn[0] = INFINITY;
         }
         auto edge = [&](const int id) {
             const float *ur = ub + (size_t)id * C;
@@ -206,15 +212,6 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
                 relu_bn(W.l2, h2);
 #pragma unroll
                 for (int o = 0; o < C; ++o) mx[o] = fmaxf(mx[o], h2[o]);
-            } else {
-#pragma unroll
-                for (int g = 0; g < C / 4; ++g) {
-                    const float4 t4 = ldg4(ur + 4 * g);
-                    mx[4 * g] = fmaxf(mx[4 * g], t4.x);         mn[4 * g] = fminf(mn[4 * g], t4.x);
-                    mx[4 * g + 1] = fmaxf(mx[4 * g + 1], t4.y); mn[4 * g + 1] = fminf(mn[4 * g + 1], t4.y);
-                    mx[4 * g + 2] = fmaxf(mx[4 * g + 2], t4.z); mn[4 * g + 2] = fminf(mn[4 * g + 2], t4.z);
-                    mx[4 * g + 3] = fmaxf(mx[4 * g + 3], t4.w); mn[4 * g + 3] = fminf(mn[4 * g + 3], t4.w);
-                }
             }
         };
 
@@ -396,6 +393,22 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
                 if (tc_pending) tc_consume(tc_pending, tc_stage ^ 1);
                 tc_pending = take;
                 tc_stage ^= 1;
+            } else if (LEVEL == 2) {
+                // lane = channel: one coalesced 128-byte read of u_j per neighbour, ids broadcast by shuffle
+                int t = 0;
+                for (; t + 4 <= take; t += 4) {
+                    const float v0 = __ldg(ub + (size_t)__shfl_sync(SN2_FULL, id, t) * C + lane);
+                    const float v1 = __ldg(ub + (size_t)__shfl_sync(SN2_FULL, id, t + 1) * C + lane);
+                    const float v2 = __ldg(ub + (size_t)__shfl_sync(SN2_FULL, id, t + 2) * C + lane);
+                    const float v3 = __ldg(ub + (size_t)__shfl_sync(SN2_FULL, id, t + 3) * C + lane);
+                    mx[0] = fmaxf(fmaxf(mx[0], fmaxf(v0, v1)), fmaxf(v2, v3));
+                    mn[0] = fminf(fminf(mn[0], fminf(v0, v1)), fminf(v2, v3));
+                }
+                for (; t < take; ++t) {
+                    const float v0 = __ldg(ub + (size_t)__shfl_sync(SN2_FULL, id, t) * C + lane);
+                    mx[0] = fmaxf(mx[0], v0);
+                    mn[0] = fminf(mn[0], v0);
+                }
             } else if (DBG != 1 && lane < take) {
                 edge(id);  // DBG 1: search only (profiling)
             }
@@ -407,21 +420,20 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
             if (lane == 0) ovf[1 + atomicAdd(ovf, 1)] = b * M + j;
             continue;
         }
+        if constexpr (LEVEL == 1) {
 #pragma unroll
-        for (int o = 0; o < C; ++o) {
-            if constexpr (LEVEL == 1) {
-                mx[o] = cnt > 0 ? warp_max(mx[o]) : 0.f;
-            } else {
-                // out = max_j f(u_j) = f(max u) if s >= 0 else f(min u): f is monotone in u
-                const float hi = warp_max(mx[o]), lo = -warp_max(-mn[o]);
-                const float sel = W.l1.s[o] >= 0.f ? hi : lo;
-                mx[o] = cnt > 0 ? fmaf(fmaxf(sel + c[o], 0.f), W.l1.s[o], W.l1.t[o]) : 0.f;
+            for (int o = 0; o < C; ++o) mx[o] = cnt > 0 ? warp_max(mx[o]) : 0.f;
+            if (lane == 0) {
+                float4 *o4 = reinterpret_cast<float4 *>(out + row * C);
+#pragma unroll
+                for (int v = 0; v < C / 4; ++v) o4[v] = make_float4(mx[4 * v], mx[4 * v + 1], mx[4 * v + 2], mx[4 * v + 3]);
             }
+        } else {
+            // out = max_j f(u_j) = f(max u) if s >= 0 else f(min u): f is monotone in u (lane = channel)
+            const float sc = W.l1.s[lane], sel = sc >= 0.f ? mx[0] : mn[0];
+            out[row * C + lane] = cnt > 0 ? fmaf(fmaxf(sel + c[0], 0.f), sc, W.l1.t[lane]) : 0.f;
         }
         if (lane == 0) {
-            float4 *o4 = reinterpret_cast<float4 *>(out + row * C);
-#pragma unroll
-            for (int v = 0; v < C / 4; ++v) o4[v] = make_float4(mx[4 * v], mx[4 * v + 1], mx[4 * v + 2], mx[4 * v + 3]);
             if (cnt_out) cnt_out[row] = cnt;
         }
     }
