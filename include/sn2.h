@@ -134,7 +134,9 @@ int sn2_knn3(const float *spos4, const float *qpos4, int B, int Ms, int Nq, int 
 /* Same result from the xy grid of the SOURCES (sn2_grid_build(spos4, B, Ms, r = -3.0f, ...)): ring search
  * with an exact termination bound, ~100x fewer distance evaluations than the scan above. */
 int sn2_knn3_grid(const float *grid_hdr, const int *cell_start, const float *sorted4, const float *qpos4,
-                  int B, int Ms, int Nq, int *nbr, float *w, void *stream);
+                  int B, int Ms, int Nq, int *nbr, float *w, int q_sorted, void *stream);
+/* q_sorted != 0: qpos4 is a cell-ordered copy of the queries with the original local index in .w (the sorted4
+ * array of an sn2_grid_build of the queries); rows of nbr / w are still indexed by the original query. */
 
 /* ---- a7: FP2 = interpolate(f3 [B*Ms,64]) ++ x1 [B*Nq,16] -> MLP[80,34] -> out [B*Nq, SN2_CF_LD]. */
 int sn2_fp2_fwd(const float *f3, const int *nbr, const float *w, const float *x1, int Q,

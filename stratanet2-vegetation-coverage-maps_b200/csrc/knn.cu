@@ -43,17 +43,20 @@ constexpr int KG_THREADS = 128;
 __global__ void __launch_bounds__(KG_THREADS)
 knn3_grid_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell_start,
                  const float4 *__restrict__ sorted, const float4 *__restrict__ qpos, int Ms, int Nq,
-                 int *__restrict__ nbr, float *__restrict__ wgt)
+                 int *__restrict__ nbr, float *__restrict__ wgt, int q_sorted)
 {
     const int b = blockIdx.y;
-    const int qi = blockIdx.x * KG_THREADS + threadIdx.x;
+    int qi = blockIdx.x * KG_THREADS + threadIdx.x;
     if (qi >= Nq) return;
     const float *hdr = grid_hdr + (size_t)b * SN2_GRID_HDR;
     const int *cs = cell_start + (size_t)b * (SN2_GRID_CELLS + 1);
     const float4 *so = sorted + (size_t)b * Ms;
     const float ox = hdr[0], oy = hdr[1], inv = hdr[2], cell = hdr[3];
     const int gx = __float_as_int(hdr[4]), gy = __float_as_int(hdr[5]);
+    // q_sorted: qpos is a cell-ordered copy of the queries (x, y, z, original local index): neighbouring lanes
+    // then walk the same cells (coherent loads, similar trip counts); results go to the original rows.
     const float4 q = __ldg(qpos + (size_t)b * Nq + qi);
+    if (q_sorted) qi = __float_as_int(q.w);
 
     // unclamped cell of the query and its distance to the nearest edge of that cell
     const float ux = (q.x - ox) * inv, uy = (q.y - oy) * inv;
@@ -103,13 +106,13 @@ knn3_grid_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cel
 }  // namespace sn2
 
 extern "C" int sn2_knn3_grid(const float *grid_hdr, const int *cell_start, const float *sorted4, const float *qpos4,
-                             int B, int Ms, int Nq, int *nbr, float *w, void *stream)
+                             int B, int Ms, int Nq, int *nbr, float *w, int q_sorted, void *stream)
 {
     if (!grid_hdr || !cell_start || !sorted4 || !qpos4 || !nbr || !w || B <= 0 || Ms < 3 || Nq <= 0) return SN2_EINVAL;
     dim3 grid((Nq + sn2::KG_THREADS - 1) / sn2::KG_THREADS, B);
     sn2::knn3_grid_kernel<<<grid, sn2::KG_THREADS, 0, (cudaStream_t)stream>>>(
         grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4), reinterpret_cast<const float4 *>(qpos4), Ms, Nq,
-        nbr, w);
+        nbr, w, q_sorted);
     SN2_LAUNCH_CHECK("knn3_grid_kernel");
     return SN2_OK;
 }

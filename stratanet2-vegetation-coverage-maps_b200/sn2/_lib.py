@@ -35,7 +35,7 @@ SIGNATURES = {
     "sn2_global_sa_fwd": [_vp, _vp, _i, _i, _vp, _i, _vp, _vp],
     "sn2_fp3_fwd": [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp],
     "sn2_knn3": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
-    "sn2_knn3_grid": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "sn2_knn3_grid": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp],
     "sn2_fp2_fwd": [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp],
     "sn2_fp1_head_fwd": [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp],
     "sn2_edge_msg_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp],

@@ -133,11 +133,12 @@ def build_grid(pos4, B: int, N: int, r: float):
 
 
 def sa_fused_fwd(level: int, pos4, feat, qpos4, B: int, N: int, M: int, r: float, K: int, w_host, want_counts=False,
-                 tensor_core: int = 0):
-    """Fused ball query + PointConv (eval).  -> out [B*M, 16|32] (+ neighbour counts int32 [B*M])."""
+                 tensor_core: int = 0, grid=None):
+    """Fused ball query + PointConv (eval).  -> out [B*M, 16|32] (+ neighbour counts int32 [B*M]).
+    grid: optional prebuilt (hdr, cell_start, sorted4) = build_grid(pos4, B, N, r)."""
     lib = _lib.load()
     dev = pos4.device
-    hdr, cell_start, sorted4 = build_grid(pos4, B, N, r)
+    hdr, cell_start, sorted4 = grid if grid is not None else build_grid(pos4, B, N, r)
     _, _, qsorted4 = build_grid(qpos4, B, M, r)  # only used as a cell-ordered permutation of the queries
     cout = 16 if level == 1 else 32
     out = torch.empty((B * M, cout), dtype=torch.float32, device=dev)
@@ -173,9 +174,10 @@ def fp3_fwd(g, x2, pos4, B: int, M: int, w_host):
 KNN_AUTO, KNN_BRUTE, KNN_GRID = 0, 1, 2
 
 
-def knn3_dense(spos4, qpos4, B: int, Ms: int, Nq: int, algo: int = KNN_AUTO):
+def knn3_dense(spos4, qpos4, B: int, Ms: int, Nq: int, algo: int = KNN_AUTO, qsorted4=None):
     """-> nbr int32 [B*Nq,3] (global source rows, ascending distance), w fp32 [B*Nq,3].
-    KNN_GRID bins the sources (one extra kernel) and ring-searches; KNN_BRUTE scans all sources."""
+    KNN_GRID bins the sources (one extra kernel) and ring-searches; KNN_BRUTE scans all sources.
+    qsorted4: optional cell-ordered copy of the queries (sorted4 of build_grid(qpos4, ...)) for coherent warps."""
     lib = _lib.load()
     dev = spos4.device
     nbr = torch.empty((B * Nq, 3), dtype=torch.int32, device=dev)
@@ -194,8 +196,9 @@ def knn3_dense(spos4, qpos4, B: int, Ms: int, Nq: int, algo: int = KNN_AUTO):
     check(lib.sn2_grid_build(dptr(spos4, torch.float32), B, Ms, -3.0, dptr(hdr), dptr(cell_start), dptr(sorted4), st),
           "sn2_grid_build")
     _count(1)
-    check(lib.sn2_knn3_grid(dptr(hdr), dptr(cell_start), dptr(sorted4), dptr(qpos4, torch.float32), B, Ms, Nq, dptr(nbr),
-                            dptr(w), st), "sn2_knn3_grid")
+    qsrc = qsorted4 if qsorted4 is not None else qpos4
+    check(lib.sn2_knn3_grid(dptr(hdr), dptr(cell_start), dptr(sorted4), dptr(qsrc, torch.float32), B, Ms, Nq, dptr(nbr),
+                            dptr(w), int(qsorted4 is not None), st), "sn2_knn3_grid")
     _count(1)
     return nbr, w
 

@@ -120,6 +120,7 @@ def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_
         pos0, feat0 = ops.ingest(xyz_d, cloud_d)
     M1 = ops.m_of(N, sa1.ratio)
     M2 = ops.m_of(M1, sa2.ratio)
+    grid0 = ops.build_grid(pos0, B, N, sa1.r)  # cell order of the raw points: SA1's search grid AND knn1's query order
     with T.stage("fps1"):
         idx1, pos1 = ops.fps_dense(pos0, B, N, M1)
     # The plot-level dependency graph (reference :131-139) has three independent branches after fps1:
@@ -134,13 +135,13 @@ def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_
             nbr2, w2 = ops.knn3_dense(pos2, pos1, B, M2, M1)
     with torch.cuda.stream(side_b):
         with T.stage("knn1"):
-            nbr1, w1 = ops.knn3_dense(pos1, pos0, B, M1, N)
+            nbr1, w1 = ops.knn3_dense(pos1, pos0, B, M1, N, qsorted4=grid0[2])
     rowptr1 = col1 = rowptr2 = col2 = None
     if trace is not None:  # neighbour lists only materialised for parity tests / backward
         rowptr1, col1 = ops.ball_query_dense(pos0, pos1, B, N, M1, sa1.r, max_num_neighbors)
     with T.stage("sa1_fused"):
         x1 = ops.sa_fused_fwd(1, pos0, feat0, pos1, B, N, M1, sa1.r, max_num_neighbors, W["sa1"],
-                              tensor_core=int(getattr(model, "sn2_tensor_core", TENSOR_CORE_DEFAULT)))
+                              tensor_core=int(getattr(model, "sn2_tensor_core", TENSOR_CORE_DEFAULT)), grid=grid0)
     join(side_a, idx2, pos2, nbr2, w2)
     if trace is not None:
         rowptr2, col2 = ops.ball_query_dense(pos1, pos2, B, M1, M2, sa2.r, max_num_neighbors)

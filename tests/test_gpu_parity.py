@@ -132,10 +132,15 @@ def test_knn3_bit_exact(cuda_device, Ms, Nq, variant):
     s, bs = q[src_idx], bq[src_idx]
     want_idx, want_d2 = tp.knn_raw(s, q, 3, bs, bq)
     want_w = 1.0 / torch.clamp(want_d2, min=1e-16)
+    q4 = ops.to_pos4(q.to(cuda_device))
     for algo in (ops.KNN_BRUTE, ops.KNN_GRID):
-        nbr, w = ops.knn3_dense(ops.to_pos4(s.to(cuda_device)), ops.to_pos4(q.to(cuda_device)), B, Ms, Nq, algo)
+        nbr, w = ops.knn3_dense(ops.to_pos4(s.to(cuda_device)), q4, B, Ms, Nq, algo)
         assert torch.equal(nbr.cpu().to(torch.int64), want_idx), f"algo {algo}"
         assert torch.equal(w.cpu(), want_w), f"algo {algo}"
+    # queries visited in cell order (coherent warps), rows still indexed by the original query
+    _, _, qsorted = ops.build_grid(q4, B, Nq, 1.4142135)
+    nbr, w = ops.knn3_dense(ops.to_pos4(s.to(cuda_device)), q4, B, Ms, Nq, ops.KNN_GRID, qsorted4=qsorted)
+    assert torch.equal(nbr.cpu().to(torch.int64), want_idx) and torch.equal(w.cpu(), want_w)
 
 
 def test_knn3_grid_hard_cases(cuda_device):
