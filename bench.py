@@ -580,7 +580,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic_cfg2.json")
     if opts.config == 2 and os.path.exists(tpath):
         tj = json.load(open(tpath))
-        traffic = {"fps1": tj.get("fps_bucket_kernel<8, 32, 0>"), "fps2": tj.get("fps_kernel<512, 8, 1>"),
+        traffic = {"fps1": tj.get("fps_bucket_kernel<8, 32, 0, 1, 1>"), "fps2": tj.get("fps_kernel<512, 8, 1>"),
                    "fp1_head": tj.get("fp1_head_kernel")}.get(dom)
     roof = None
     if dom in alg_bytes:
