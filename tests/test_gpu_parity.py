@@ -569,3 +569,26 @@ def test_cuda_path_reproduces_golden_vectors(cuda_device, path):
         r = project_to_2d_rasters(data["cloud"][b], cov_b[b], args)
         assert np.array_equal(np.isnan(r), np.isnan(z["rasters"][b]))
         np.testing.assert_allclose(np.nan_to_num(r), np.nan_to_num(z["rasters"][b]), rtol=RTOL, atol=ATOL)
+
+
+def test_error_behaviour(cuda_device):
+    """Bad requests raise RuntimeError (the C ABI's negative codes), they never fall back or corrupt memory."""
+    from sn2 import ops
+
+    d = cuda_device
+    with pytest.raises(RuntimeError):  # more points per plot than the FPS kernels support
+        ops.fps(torch.zeros(70000, 3, device=d), None, ratio=0.25)
+    with pytest.raises(RuntimeError):  # ragged batch vector
+        ops.fps(torch.zeros(10, 3, device=d), torch.tensor([0, 0, 0, 0, 0, 0, 1, 1, 1, 1], device=d), ratio=0.5)
+    with pytest.raises(RuntimeError):  # fewer than 3 sources for a 3-NN
+        ops.knn(torch.zeros(2, 3, device=d), torch.zeros(5, 3, device=d), 3)
+    with pytest.raises(RuntimeError):  # k other than 3
+        ops.knn(torch.zeros(8, 3, device=d), torch.zeros(5, 3, device=d), 2)
+    with pytest.raises(RuntimeError):  # CPU tensors: no CPU path
+        ops.radius(torch.zeros(8, 3), torch.zeros(2, 3), 1.0)
+    args, net, _ = _make_models(512, d)
+    with pytest.raises(RuntimeError):  # wrong number of points per plot (reference contract: subsample_size)
+        net({"xyz": torch.zeros(1, 3, 400), "cloud": torch.zeros(1, 10, 400)})
+    net.train()
+    with torch.no_grad(), pytest.raises(RuntimeError):  # train-mode statistics need the autograd path
+        net(_plots(1, 1, 512))
