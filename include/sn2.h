@@ -147,6 +147,10 @@ int sn2_fp2_fwd(const float *f3, const int *nbr, const float *w, const float *x1
  * cov, proba: [Q,4] row-major. */
 int sn2_fp1_head_fwd(const float *f2, const int *nbr, const float *w, const float *feat, int Q,
                      const float *w_host, int nw, float *cov, float *proba, void *stream);
+/* Same contract on the tensor cores: 128-point tiles, MLP[42,34] as tcgen05.mma kind::tf32 with a 3xTF32 hi/lo
+ * operand split (fp32-accurate, same 1e-3 bound), accumulators in TMEM, head in the epilogue. */
+int sn2_fp1_head_fwd_tc(const float *f2, const int *nbr, const float *w, const float *feat, int Q,
+                        const float *w_host, int nw, float *cov, float *proba, void *stream);
 
 /* ---- a12: plot-wise coverages.  Replaces project_to_plotwise_coverages (model/project_to_2d.py:7-55).
  * cloud (B,F,N) device (rows 0,1 = normalised x,y), pred [B*N,4].
@@ -198,6 +202,29 @@ int sn2_project_plotwise_bwd(const float *dout, const int *parg, int B, int D, f
 int sn2_linear_wgrad_supported(int Co, int Ci);
 int sn2_linear_wgrad(const float *dy, const float *x, long long E, int Co, int Ci, float *partial, int nblk,
                      float *dW, float *db, void *stream);
+
+/* ---- train-mode MLP block Linear -> ReLU -> BatchNorm1d (batch statistics), csrc/train_mlp.cu ----------------
+ * Replaces, for one block of the reference's MLP() (model/point_net2.py:45-53) applied to R rows, the torch
+ * sequence addmm / relu / batch_norm forward and their three backward nodes.  Supported (Ci, Co): (11,16) (16,16)
+ * (19,32) (80,34) (42,34).  All pointers are device pointers.
+ *   sn2_lrb_fwd        y [R,Co] = relu(x W^T + b); stats [2*Co+1] fp64 = {sum y, sum y^2, R} (zeroed here).
+ *                      For SyncBatchNorm the caller all-reduces stats across ranks before sn2_bn_finalize.
+ *   sn2_bn_finalize    stats -> ss [4*Co] = {scale, shift, mean, invstd} (biased variance, eps); running_mean /
+ *                      running_var (nullable) updated with `momentum` and the unbiased variance like torch.
+ *   sn2_bn_apply       z = y * scale + shift.
+ *   sn2_lrb_bwd_reduce sums [2*Co] fp64 = {sum dz, sum dz*y} (zeroed here; all-reduced by the caller for SyncBN).
+ *   sn2_lrb_bwd        dx [R,Ci] (nullable) = dy W with dy = relu'(y) * BN'(dz); dW [Co,Ci] = dy^T x; db [Co];
+ *                      partial: scratch [nblk, Co*(Ci+1)], fixed-order two-stage reduction. */
+int sn2_lrb_supported(int Co, int Ci);
+int sn2_lrb_fwd(const float *x, const float *W, const float *b, long long R, int Co, int Ci, float *y,
+                double *stats, void *stream);
+int sn2_bn_finalize(const double *stats, const float *gamma, const float *beta, float eps, float momentum,
+                    float *running_mean, float *running_var, float *ss, int Co, void *stream);
+int sn2_bn_apply(const float *y, const float *ss, long long R, int Co, float *z, void *stream);
+int sn2_lrb_bwd_reduce(const float *dz, const float *y, long long R, int Co, double *sums, void *stream);
+int sn2_lrb_bwd(const float *dz, const float *y, const float *x, const float *W, const float *ss,
+                const double *sums, const double *stats, long long R, int Co, int Ci, float *dx, float *partial,
+                int nblk, float *dW, float *db, void *stream);
 
 /* ================= local-map fusion (BASELINE config 4), csrc/fusion.cu =============
  * Weighted-average mosaic of per-plot rasters into the parcel grid; replaces add_weights_band_to_rasters +

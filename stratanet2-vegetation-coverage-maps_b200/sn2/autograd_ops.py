@@ -181,13 +181,100 @@ class TallLinear(torch.autograd.Function):
         return dx, dW, db
 
 
+class LinReluBN(torch.autograd.Function):
+    """One train-mode block of the reference MLP() -- Linear -> ReLU -> BatchNorm1d with batch statistics
+    (model/point_net2.py:45-53) -- in five kernels of csrc/train_mlp.cu instead of torch's nine.  Running statistics,
+    `num_batches_tracked` and SyncBatchNorm (statistics all-reduced as raw fp64 sums + counts, forward and backward)
+    behave as torch's modules do; `bn` is the block's own BatchNorm1d / SyncBatchNorm module."""
+
+    NBLK = 148 * 2
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, bn):
+        lib = _lib.load()
+        x = _c(x)
+        R, (Co, Ci) = x.shape[0], weight.shape
+        dev = x.device
+        y = torch.empty((R, Co), dtype=torch.float32, device=dev)
+        stats = torch.empty(2 * Co + 1, dtype=torch.float64, device=dev)
+        check(lib.sn2_lrb_fwd(dptr(x, torch.float32), dptr(_c(weight), torch.float32), dptr(_c(bias), torch.float32), R, Co, Ci,
+                              dptr(y), dptr(stats), stream_ptr()), "sn2_lrb_fwd")
+        group = _sync_group(bn)
+        if group is not None:
+            torch.distributed.all_reduce(stats, group=group)
+        ss = torch.empty(4 * Co, dtype=torch.float32, device=dev)
+        track = bn.track_running_stats and bn.running_mean is not None
+        check(lib.sn2_bn_finalize(dptr(stats), dptr(_c(gamma), torch.float32), dptr(_c(beta), torch.float32), float(bn.eps),
+                                  float(bn.momentum), dptr(bn.running_mean) if track else None,
+                                  dptr(bn.running_var) if track else None, dptr(ss), Co, stream_ptr()), "sn2_bn_finalize")
+        if track and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        z = torch.empty_like(y)
+        check(lib.sn2_bn_apply(dptr(y), dptr(ss), R, Co, dptr(z), stream_ptr()), "sn2_bn_apply")
+        ops._count(5)
+        ctx.save_for_backward(x, y, weight, ss, stats)
+        ctx.group = group
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        lib = _lib.load()
+        x, y, weight, ss, stats = ctx.saved_tensors
+        dz = _c(dz)
+        R, (Co, Ci) = x.shape[0], weight.shape
+        dev = x.device
+        sums = torch.empty(2 * Co, dtype=torch.float64, device=dev)
+        check(lib.sn2_lrb_bwd_reduce(dptr(dz, torch.float32), dptr(y), R, Co, dptr(sums), stream_ptr()), "sn2_lrb_bwd_reduce")
+        # BatchNorm affine gradients from this rank's sums: dbeta = sum dz, dgamma = sum dz * yhat
+        mean, inv = ss[2 * Co:3 * Co].double(), ss[3 * Co:].double()
+        dbeta = sums[:Co].float()
+        dgamma = (inv * (sums[Co:] - mean * sums[:Co])).float()
+        if ctx.group is not None:
+            torch.distributed.all_reduce(sums, group=ctx.group)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dW = torch.empty_like(weight)
+        db = torch.empty(Co, dtype=torch.float32, device=dev)
+        partial = torch.empty((LinReluBN.NBLK, Co * (Ci + 1)), dtype=torch.float32, device=dev)
+        check(lib.sn2_lrb_bwd(dptr(dz), dptr(y), dptr(x), dptr(_c(weight), torch.float32), dptr(ss), dptr(sums), dptr(stats), R,
+                              Co, Ci, dptr(dx), dptr(partial), LinReluBN.NBLK, dptr(dW), dptr(db), stream_ptr()), "sn2_lrb_bwd")
+        ops._count(4)
+        return dx, dW, db, dgamma, dbeta, None
+
+
+def _sync_group(bn):
+    """Process group over which a SyncBatchNorm shares its statistics (None for plain BatchNorm1d / single process)."""
+    if not isinstance(bn, torch.nn.SyncBatchNorm):
+        return None
+    if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        return None
+    group = bn.process_group if bn.process_group is not None else torch.distributed.group.WORLD
+    return group if torch.distributed.get_world_size(group) > 1 else None
+
+
+def _fusable_block(lib, block, x) -> bool:
+    layers = list(block)
+    if len(layers) != 3 or not isinstance(layers[0], torch.nn.Linear) or not isinstance(layers[1], torch.nn.ReLU):
+        return False
+    lin, bn = layers[0], layers[2]
+    if not isinstance(bn, (torch.nn.BatchNorm1d, torch.nn.SyncBatchNorm)):
+        return False
+    return (bn.training and bn.affine and bn.momentum is not None and lin.bias is not None and x.dtype == torch.float32
+            and bool(lib.sn2_lrb_supported(lin.out_features, lin.in_features)))
+
+
 def run_mlp(seq, x):
-    """Apply a reference MLP (Sequential of (Linear, ReLU, BatchNorm1d) blocks) with TallLinear where it pays."""
+    """Apply a reference MLP (Sequential of (Linear, ReLU, BatchNorm1d) blocks).  Blocks that see >= 65 536 rows in
+    training run as the fused LinReluBN (SN2_FUSED_MLP=0 -> the torch modules, with TallLinear where it pays)."""
     lib = _lib.load()
     import os
+    fused = os.environ.get("SN2_FUSED_MLP", "1") == "1"
     tall = os.environ.get("SN2_TALL_LINEAR", "1") == "1"
     for block in seq:
         lin = block[0]
+        if fused and x.shape[0] >= 65536 and _fusable_block(lib, block, x):
+            bn = block[2]
+            x = LinReluBN.apply(x, lin.weight, lin.bias, bn.weight, bn.bias, bn)
+            continue
         if tall and x.shape[0] >= 65536 and (x.requires_grad or lin.weight.requires_grad) and lib.sn2_linear_wgrad_supported(
                 lin.out_features, lin.in_features):
             x = TallLinear.apply(x, lin.weight, lin.bias)

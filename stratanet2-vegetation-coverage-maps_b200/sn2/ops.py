@@ -213,14 +213,14 @@ def fp2_fwd(f3, nbr, w, x1, w_host):
     return out
 
 
-def fp1_head_fwd(f2, nbr, w, feat, w_host):
+def fp1_head_fwd(f2, nbr, w, feat, w_host, tensor_core: bool = False):
     lib = _lib.load()
+    fn, name = (lib.sn2_fp1_head_fwd_tc, "sn2_fp1_head_fwd_tc") if tensor_core else (lib.sn2_fp1_head_fwd, "sn2_fp1_head_fwd")
     Q = feat.shape[0]
     cov = torch.empty((Q, 4), dtype=torch.float32, device=feat.device)
     proba = torch.empty((Q, 4), dtype=torch.float32, device=feat.device)
-    check(lib.sn2_fp1_head_fwd(dptr(f2, torch.float32), dptr(nbr, torch.int32), dptr(w, torch.float32),
-                               dptr(feat, torch.float32), Q, hptr(w_host), w_host.numel(), dptr(cov), dptr(proba),
-                               stream_ptr()), "sn2_fp1_head_fwd")
+    check(fn(dptr(f2, torch.float32), dptr(nbr, torch.int32), dptr(w, torch.float32), dptr(feat, torch.float32), Q,
+             hptr(w_host), w_host.numel(), dptr(cov), dptr(proba), stream_ptr()), name)
     _count(1)
     return cov, proba
 

@@ -67,6 +67,7 @@ class ForwardTrace:
 
 # SA1's second layer on tcgen05 (3xTF32, fp32-accurate) instead of SIMT FFMA; PointNet2.sn2_tensor_core overrides
 TENSOR_CORE_DEFAULT = int(os.environ.get("SN2_TENSOR_CORE", "0"))  # 0 SIMT fp32, 1 tcgen05 3xTF32, 2 tcgen05 TF32
+FP_TENSOR_CORE_DEFAULT = int(os.environ.get("SN2_FP_TENSOR_CORE", "0"))  # FP1 + head: 0 SIMT fp32, 1 tcgen05 3xTF32
 _SIDE = {}
 
 
@@ -155,7 +156,8 @@ def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_
         f2 = ops.fp2_fwd(f3, nbr2, w2, x1, W["fp2"])
     join(side_b, nbr1, w1)
     with T.stage("fp1_head"):
-        cov, proba = ops.fp1_head_fwd(f2, nbr1, w1, feat0, W["fp1"])
+        cov, proba = ops.fp1_head_fwd(f2, nbr1, w1, feat0, W["fp1"],
+                                      tensor_core=bool(getattr(model, "sn2_fp_tensor_core", FP_TENSOR_CORE_DEFAULT)))
 
     if trace is not None:
         trace.tensors.update(
@@ -209,7 +211,7 @@ def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num
     x2, _ = SegmentMax.apply(run_mlp(sa2.conv.local_nn, EdgeMsg.apply(x1, pos1, pos2, rowptr2, col2)), rowptr2)
     g, _ = SegmentMax.apply(model.sa3_module.nn(torch.cat([x2, pos2[:, :3]], dim=1)), plot_ptr)
     f3 = model.fp3_module.nn(torch.cat([InterpPlot.apply(g, pos2, M2), x2], dim=1))
-    f2 = model.fp2_module.nn(torch.cat([Interp3.apply(f3, nbr2, w2), x1], dim=1))
+    f2 = run_mlp(model.fp2_module.nn, torch.cat([Interp3.apply(f3, nbr2, w2), x1], dim=1))
     f1 = run_mlp(model.fp1_module.nn, torch.cat([Interp3.apply(f2, nbr1, w1), feat0], dim=1))
     h = F.relu(model.lin1(f1))
     h = F.dropout(h, p=model.drop, training=True)

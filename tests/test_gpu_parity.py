@@ -209,6 +209,26 @@ def test_forward_parity(cuda_device, B, N, variant, K):
     assert cov.shape == (B * N, 4) and cov.is_cuda
 
 
+@pytest.mark.parametrize("B,N", [(1, 10000), (3, 4096), (1, 400)])
+def test_fp1_head_tensor_core_parity(cuda_device, B, N):
+    """FP1 + head on tcgen05 (3xTF32 split operands, TMEM accumulators) against the oracle within the fp32 bound
+    and against the SIMT kernel; N = 400 / 3*4096 exercise a partial last tile and exact multiples of 128."""
+    from sn2.pipeline import ForwardTrace
+
+    args, net, port = _make_models(N, cuda_device)
+    data = _plots(1, B, N, "plain")
+    with torch.no_grad():
+        cov_o, proba_o = port(data, max_num_neighbors=2000, trace=True)
+        tr = ForwardTrace()
+        cov_s, proba_s = net(data, trace=tr)
+        net.sn2_fp_tensor_core = 1
+        cov_t, proba_t = net(data)
+    for name, got, want in (("cov", cov_t, cov_o), ("proba", proba_t, proba_o)):
+        torch.testing.assert_close(got.cpu(), want, rtol=RTOL, atol=ATOL, msg=lambda m, n=name: f"{n}: {m}")
+    torch.testing.assert_close(cov_t, cov_s, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(proba_t, proba_s, rtol=1e-4, atol=1e-6)
+
+
 @pytest.mark.parametrize("B,N", [(1, 10000), (4, 4096)])
 def test_projections_parity(cuda_device, B, N):
     from model.project_to_2d import project_to_2d_rasters, project_to_plotwise_coverages, project_to_2d_rasters_batched
@@ -524,6 +544,43 @@ def test_tall_linear_weight_gradient(cuda_device, Co, Ci):
     torch.testing.assert_close(w.grad.double(), dy64.t() @ x64, rtol=1e-4, atol=2e-2)
     torch.testing.assert_close(b.grad.double(), dy64.sum(0), rtol=1e-4, atol=2e-2)
     torch.testing.assert_close(x.grad.double(), dy64 @ w64, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("Ci,Co,R", [(11, 16, 300001), (16, 16, 131072), (19, 32, 99999), (80, 34, 70001), (42, 34, 65537)])
+def test_fused_lin_relu_bn_block(cuda_device, Ci, Co, R):
+    """LinReluBN (csrc/train_mlp.cu) against the torch modules of one reference MLP() block in float64:
+    output, all five gradients, running statistics and num_batches_tracked."""
+    from sn2.autograd_ops import LinReluBN
+
+    g = torch.Generator().manual_seed(Ci * 100 + Co)
+    x = torch.randn(R, Ci, generator=g).to(cuda_device)
+    block = torch.nn.Sequential(torch.nn.Linear(Ci, Co), torch.nn.ReLU(), torch.nn.BatchNorm1d(Co)).to(cuda_device)
+    with torch.no_grad():
+        block[2].weight.copy_(torch.randn(Co, generator=g) * 0.5 + 1.0)   # some gammas may be negative
+        block[2].bias.copy_(torch.randn(Co, generator=g) * 0.2)
+        block[2].running_mean.copy_(torch.randn(Co, generator=g))
+        block[2].running_var.copy_(torch.rand(Co, generator=g) + 0.5)
+    ref = torch.nn.Sequential(torch.nn.Linear(Ci, Co), torch.nn.ReLU(), torch.nn.BatchNorm1d(Co)).to(cuda_device).double()
+    ref.load_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in block.state_dict().items()})
+    dz = torch.randn(R, Co, generator=g).to(cuda_device)
+
+    x1 = x.clone().requires_grad_(True)
+    lin, bn = block[0], block[2]
+    z = LinReluBN.apply(x1, lin.weight, lin.bias, bn.weight, bn.bias, bn)
+    z.backward(dz)
+    x2 = x.double().requires_grad_(True)
+    z_ref = ref(x2)
+    z_ref.backward(dz.double())
+
+    torch.testing.assert_close(z.detach().double(), z_ref.detach(), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(x1.grad.double(), x2.grad, rtol=1e-3, atol=1e-4)
+    scale = float(R) ** 0.5
+    for name, got, want in (("dW", lin.weight.grad, ref[0].weight.grad), ("db", lin.bias.grad, ref[0].bias.grad),
+                            ("dgamma", bn.weight.grad, ref[2].weight.grad), ("dbeta", bn.bias.grad, ref[2].bias.grad)):
+        torch.testing.assert_close(got.double(), want, rtol=1e-3, atol=2e-4 * scale, msg=lambda m, n=name: f"{n}: {m}")
+    torch.testing.assert_close(bn.running_mean.double(), ref[2].running_mean, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(bn.running_var.double(), ref[2].running_var, rtol=1e-5, atol=1e-6)
+    assert int(bn.num_batches_tracked) == int(ref[2].num_batches_tracked) == 1
 
 
 def _golden_paths():
