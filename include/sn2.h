@@ -198,7 +198,7 @@ int sn2_project_plotwise_bwd(const float *dout, const int *parg, int B, int D, f
 
 /* Weight / bias gradient of a Linear applied to E rows (E ~ millions, Co, Ci <= 64): dW [Co,Ci] = dy^T x,
  * db [Co] = column sums of dy.  partial: scratch [nblk, Co*(Ci+1)]; deterministic two-stage reduction.
- * Supported Ci: 11, 16, 19, 35, 42 (the edge / point MLP input widths), Co <= 64. */
+ * Supported Ci: 11, 16, 19, 34, 35, 42 (the edge / point MLP and head input widths), Co <= 64. */
 int sn2_linear_wgrad_supported(int Co, int Ci);
 int sn2_linear_wgrad(const float *dy, const float *x, long long E, int Co, int Ci, float *partial, int nblk,
                      float *dW, float *db, void *stream);
@@ -210,7 +210,8 @@ int sn2_linear_wgrad(const float *dy, const float *x, long long E, int Co, int C
  *   sn2_lrb_fwd        y [R,Co] = relu(x W^T + b); stats [2*Co+1] fp64 = {sum y, sum y^2, R} (zeroed here).
  *                      For SyncBatchNorm the caller all-reduces stats across ranks before sn2_bn_finalize.
  *   sn2_bn_finalize    stats -> ss [4*Co] = {scale, shift, mean, invstd} (biased variance, eps); running_mean /
- *                      running_var (nullable) updated with `momentum` and the unbiased variance like torch.
+ *                      running_var (nullable) updated with `momentum` and the unbiased variance like torch;
+ *                      *num_batches_tracked (nullable, int64) += 1.
  *   sn2_bn_apply       z = y * scale + shift.
  *   sn2_lrb_bwd_reduce sums [2*Co] fp64 = {sum dz, sum dz*y} (zeroed here; all-reduced by the caller for SyncBN).
  *   sn2_lrb_bwd        dx [R,Ci] (nullable) = dy W with dy = relu'(y) * BN'(dz); dW [Co,Ci] = dy^T x; db [Co];
@@ -219,12 +220,25 @@ int sn2_lrb_supported(int Co, int Ci);
 int sn2_lrb_fwd(const float *x, const float *W, const float *b, long long R, int Co, int Ci, float *y,
                 double *stats, void *stream);
 int sn2_bn_finalize(const double *stats, const float *gamma, const float *beta, float eps, float momentum,
-                    float *running_mean, float *running_var, float *ss, int Co, void *stream);
+                    float *running_mean, float *running_var, long long *num_batches_tracked, float *ss, int Co,
+                    void *stream);
 int sn2_bn_apply(const float *y, const float *ss, long long R, int Co, float *z, void *stream);
 int sn2_lrb_bwd_reduce(const float *dz, const float *y, long long R, int Co, double *sums, void *stream);
+/* BatchNorm affine gradients of THIS rank from its own (not all-reduced) sums: dbeta = sum dz, dgamma = sum dz*yhat. */
+int sn2_bn_param_grad(const double *sums, const float *ss, int Co, float *dgamma, float *dbeta, void *stream);
 int sn2_lrb_bwd(const float *dz, const float *y, const float *x, const float *W, const float *ss,
                 const double *sums, const double *stats, long long R, int Co, int Ci, float *dx, float *partial,
                 int nblk, float *dW, float *db, void *stream);
+/* The same block in one call each way when no all-reduce sits between the kernels (plain BatchNorm1d):
+ * fwd = sn2_lrb_fwd + sn2_bn_finalize (num_batches_tracked += 1 when given) + sn2_bn_apply;
+ * bwd = sn2_lrb_bwd_reduce + sn2_bn_param_grad + sn2_lrb_bwd. */
+int sn2_lrb_block_fwd(const float *x, const float *W, const float *b, const float *gamma, const float *beta,
+                      float eps, float momentum, float *running_mean, float *running_var,
+                      long long *num_batches_tracked, long long R, int Co, int Ci, float *y, double *stats,
+                      float *ss, float *z, void *stream);
+int sn2_lrb_block_bwd(const float *dz, const float *y, const float *x, const float *W, const float *ss,
+                      const double *stats, long long R, int Co, int Ci, double *sums, float *dgamma,
+                      float *dbeta, float *dx, float *partial, int nblk, float *dW, float *db, void *stream);
 
 /* ================= local-map fusion (BASELINE config 4), csrc/fusion.cu =============
  * Weighted-average mosaic of per-plot rasters into the parcel grid; replaces add_weights_band_to_rasters +

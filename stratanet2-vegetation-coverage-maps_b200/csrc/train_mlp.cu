@@ -78,11 +78,15 @@ __device__ __forceinline__ void cta_channel_sums(const float (&a)[CO], const flo
 // ---------------------------------------------------------------------------------------------------------------
 template <int CI, int CO>
 struct LrbFwd {
+    static constexpr int WARPS = LRB_T / 32;
     static constexpr int COP = (CO + 3) & ~3;
     static constexpr int XS = (CI & 1) ? CI : CI + 1;  // odd row stride: conflict-free row-per-thread reads
     static constexpr size_t SMEM = sizeof(double) * 2 * CO + sizeof(float) * ((size_t)CI * COP + COP + (size_t)LRB_T * XS);
 };
 
+// Every warp owns 32-row tiles: it copies the tile's 32 * CI contiguous floats into its private shared-memory slab
+// (coalesced), then each lane runs the layer on its row.  No CTA barrier inside the loop, so the warps of an SM
+// drift apart and the loads of some overlap the FMAs of others.
 template <int CI, int CO>
 __global__ void __launch_bounds__(LRB_T, (CO > 16 ? 1 : 2))
 lrb_fwd_kernel(const float *__restrict__ x, const float *__restrict__ W, const float *__restrict__ b, long long R,
@@ -94,35 +98,40 @@ lrb_fwd_kernel(const float *__restrict__ x, const float *__restrict__ W, const f
     double *red = reinterpret_cast<double *>(lrb_smem);
     float *Wt = reinterpret_cast<float *>(red + 2 * CO);  // [CI][COP]: Wt[k][o] = W[o][k]
     float *bS = Wt + CI * COP;
-    float *xS = bS + COP;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *xS = bS + COP + warp * (32 * XS);              // this warp's [32][XS] slab
     for (int e = tid; e < CI * COP; e += LRB_T) {
         const int k = e / COP, o = e - k * COP;
         Wt[e] = o < CO ? __ldg(W + o * CI + k) : 0.f;
     }
     for (int o = tid; o < COP; o += LRB_T) bS[o] = o < CO ? __ldg(b + o) : 0.f;
     for (int o = tid; o < 2 * CO; o += LRB_T) red[o] = 0.0;
+    __syncthreads();
     float s1[CO], s2[CO];
 #pragma unroll
     for (int o = 0; o < CO; ++o) s1[o] = s2[o] = 0.f;
-    const long long ntiles = (R + LRB_T - 1) / LRB_T;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        __syncthreads();
-        const long long base = tile * LRB_T;
-        const int rows = (int)min((long long)LRB_T, R - base);
+    const long long ntiles = (R + 31) / 32;
+    for (long long tile = (long long)blockIdx.x * L::WARPS + warp; tile < ntiles; tile += (long long)gridDim.x * L::WARPS) {
+        const long long base = tile * 32;
+        const int rows = (int)min(32LL, R - base);
         const float *xt = x + base * CI;
-        for (int e = tid; e < rows * CI; e += LRB_T) {
-            const int r = e / CI, k = e - r * CI;
-            xS[r * XS + k] = __ldg(xt + e);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < CI; ++j) {
+            const int e = j * 32 + lane;  // element e of the tile = (row e / CI, column e % CI)
+            if (e < rows * CI) {
+                const int r = e / CI, k = e - r * CI;
+                xS[r * XS + k] = __ldg(xt + e);
+            }
         }
-        __syncthreads();
-        if (tid < rows) {
+        __syncwarp();
+        if (lane < rows) {
             float acc[COP];
 #pragma unroll
             for (int o = 0; o < COP; ++o) acc[o] = bS[o];
 #pragma unroll
             for (int k = 0; k < CI; ++k) {
-                const float xk = xS[tid * XS + k];
+                const float xk = xS[lane * XS + k];
 #pragma unroll
                 for (int o4 = 0; o4 < COP / 4; ++o4) {
                     const float4 w = *reinterpret_cast<const float4 *>(Wt + k * COP + 4 * o4);
@@ -139,20 +148,21 @@ lrb_fwd_kernel(const float *__restrict__ x, const float *__restrict__ W, const f
                 s1[o] += out[o];
                 s2[o] = fmaf(out[o], out[o], s2[o]);
             }
-            store_row<CO>(y + (base + tid) * CO, out);
+            store_row<CO>(y + (base + lane) * CO, out);
         }
     }
-    __syncthreads();
+    __syncwarp();
     cta_channel_sums<CO>(s1, s2, red, stats);
 }
 
 // statistics (+ count at stats[2*Co]) -> ss = [scale, shift, mean, invstd]; running statistics as torch BatchNorm.
 __global__ void bn_finalize_kernel(const double *__restrict__ stats, const float *__restrict__ gamma,
                                    const float *__restrict__ beta, float eps, float momentum, float *running_mean,
-                                   float *running_var, float *__restrict__ ss, int Co)
+                                   float *running_var, long long *num_batches_tracked, float *__restrict__ ss, int Co)
 {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= Co) return;
+    if (o == 0 && num_batches_tracked) *num_batches_tracked += 1;
     const double n = stats[2 * Co];
     const double mean = stats[o] / n;
     const double var = fmax(stats[Co + o] / n - mean * mean, 0.0);
@@ -167,6 +177,17 @@ __global__ void bn_finalize_kernel(const double *__restrict__ stats, const float
 }
 
 __global__ void set_count_kernel(double *stats, int Co, double n) { stats[2 * Co] = n; }
+
+// BatchNorm affine gradients from one rank's raw sums: dbeta = sum dz, dgamma = sum dz * yhat = invstd * (S2 - mean * S1)
+__global__ void bn_param_grad_kernel(const double *__restrict__ sums, const float *__restrict__ ss, int Co,
+                                     float *__restrict__ dgamma, float *__restrict__ dbeta)
+{
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= Co) return;
+    const double S1 = sums[o], S2 = sums[Co + o];
+    dbeta[o] = (float)S1;
+    dgamma[o] = (float)((double)ss[3 * Co + o] * (S2 - (double)ss[2 * Co + o] * S1));
+}
 
 // z = y * scale[c] + shift[c]; two channels per thread (every supported Co is even).
 __global__ void __launch_bounds__(256)
@@ -358,8 +379,8 @@ static int launch_lrb_fwd(const float *x, const float *W, const float *b, long l
     SN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM), "lrb_fwd attr");
     SN2_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * CO, st), "lrb_fwd memset");
     set_count_kernel<<<1, 1, 0, st>>>(stats, CO, (double)R);
-    const long long ntiles = (R + LRB_T - 1) / LRB_T;
-    const int grid = (int)min(ntiles, (long long)148 * 2);
+    const long long nblocks = ((R + 31) / 32 + L::WARPS - 1) / L::WARPS;
+    const int grid = (int)min(nblocks, (long long)148 * 2);
     kern<<<grid, LRB_T, L::SMEM, st>>>(x, W, b, R, y, stats);
     SN2_LAUNCH_CHECK("lrb_fwd_kernel");
     return SN2_OK;
@@ -415,11 +436,12 @@ extern "C" int sn2_lrb_fwd(const float *x, const float *W, const float *b, long 
 }
 
 extern "C" int sn2_bn_finalize(const double *stats, const float *gamma, const float *beta, float eps, float momentum,
-                               float *running_mean, float *running_var, float *ss, int Co, void *stream)
+                               float *running_mean, float *running_var, long long *num_batches_tracked, float *ss, int Co,
+                               void *stream)
 {
     if (!stats || !gamma || !beta || !ss || Co <= 0) return SN2_EINVAL;
     sn2::bn_finalize_kernel<<<(Co + 63) / 64, 64, 0, (cudaStream_t)stream>>>(stats, gamma, beta, eps, momentum, running_mean,
-                                                                           running_var, ss, Co);
+                                                                           running_var, num_batches_tracked, ss, Co);
     SN2_LAUNCH_CHECK("bn_finalize_kernel");
     return SN2_OK;
 }
@@ -446,6 +468,14 @@ extern "C" int sn2_lrb_bwd_reduce(const float *dz, const float *y, long long R, 
     }
 }
 
+extern "C" int sn2_bn_param_grad(const double *sums, const float *ss, int Co, float *dgamma, float *dbeta, void *stream)
+{
+    if (!sums || !ss || !dgamma || !dbeta || Co <= 0) return SN2_EINVAL;
+    sn2::bn_param_grad_kernel<<<(Co + 63) / 64, 64, 0, (cudaStream_t)stream>>>(sums, ss, Co, dgamma, dbeta);
+    SN2_LAUNCH_CHECK("bn_param_grad_kernel");
+    return SN2_OK;
+}
+
 extern "C" int sn2_lrb_bwd(const float *dz, const float *y, const float *x, const float *W, const float *ss,
                            const double *sums, const double *stats, long long R, int Co, int Ci, float *dx, float *partial,
                            int nblk, float *dW, float *db, void *stream)
@@ -457,4 +487,26 @@ extern "C" int sn2_lrb_bwd(const float *dz, const float *y, const float *x, cons
     SN2_LRB_SHAPES(X)
 #undef X
     return SN2_EUNSUPPORTED;
+}
+
+// Single-process block in one call each way (no all-reduce between the kernels): what LinReluBN uses when the
+// block's BatchNorm is not a SyncBatchNorm.
+extern "C" int sn2_lrb_block_fwd(const float *x, const float *W, const float *b, const float *gamma, const float *beta,
+                                 float eps, float momentum, float *running_mean, float *running_var,
+                                 long long *num_batches_tracked, long long R, int Co, int Ci, float *y, double *stats,
+                                 float *ss, float *z, void *stream)
+{
+    if (int rc = sn2_lrb_fwd(x, W, b, R, Co, Ci, y, stats, stream)) return rc;
+    if (int rc = sn2_bn_finalize(stats, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked, ss, Co, stream))
+        return rc;
+    return sn2_bn_apply(y, ss, R, Co, z, stream);
+}
+
+extern "C" int sn2_lrb_block_bwd(const float *dz, const float *y, const float *x, const float *W, const float *ss,
+                                 const double *stats, long long R, int Co, int Ci, double *sums, float *dgamma,
+                                 float *dbeta, float *dx, float *partial, int nblk, float *dW, float *db, void *stream)
+{
+    if (int rc = sn2_lrb_bwd_reduce(dz, y, R, Co, sums, stream)) return rc;
+    if (int rc = sn2_bn_param_grad(sums, ss, Co, dgamma, dbeta, stream)) return rc;
+    return sn2_lrb_bwd(dz, y, x, W, ss, sums, stats, R, Co, Ci, dx, partial, nblk, dW, db, stream);
 }

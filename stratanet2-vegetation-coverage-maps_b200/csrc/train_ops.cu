@@ -372,7 +372,7 @@ static int launch_wgrad(const float *dy, const float *x, long long E, int Co, fl
 
 extern "C" int sn2_linear_wgrad_supported(int Co, int Ci)
 {
-    return (Co >= 1 && Co <= 64) && (Ci == 11 || Ci == 16 || Ci == 19 || Ci == 35 || Ci == 42);
+    return (Co >= 1 && Co <= 64) && (Ci == 11 || Ci == 16 || Ci == 19 || Ci == 34 || Ci == 35 || Ci == 42);
 }
 
 extern "C" int sn2_linear_wgrad(const float *dy, const float *x, long long E, int Co, int Ci, float *partial, int nblk,
@@ -385,6 +385,7 @@ extern "C" int sn2_linear_wgrad(const float *dy, const float *x, long long E, in
     case 11: return sn2::launch_wgrad<11>(dy, x, E, Co, partial, nblk, dW, db, st);
     case 16: return sn2::launch_wgrad<16>(dy, x, E, Co, partial, nblk, dW, db, st);
     case 19: return sn2::launch_wgrad<19>(dy, x, E, Co, partial, nblk, dW, db, st);
+    case 34: return sn2::launch_wgrad<34>(dy, x, E, Co, partial, nblk, dW, db, st);
     case 35: return sn2::launch_wgrad<35>(dy, x, E, Co, partial, nblk, dW, db, st);
     default: return sn2::launch_wgrad<42>(dy, x, E, Co, partial, nblk, dW, db, st);
     }

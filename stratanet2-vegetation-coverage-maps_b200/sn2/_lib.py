@@ -52,7 +52,10 @@ SIGNATURES = {
     "sn2_linear_wgrad": [_vp, _vp, _ll, _i, _i, _vp, _i, _vp, _vp, _vp],
     "sn2_lrb_supported": [_i, _i],
     "sn2_lrb_fwd": [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp],
-    "sn2_bn_finalize": [_vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _i, _vp],
+    "sn2_bn_finalize": [_vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp],
+    "sn2_bn_param_grad": [_vp, _vp, _i, _vp, _vp, _vp],
+    "sn2_lrb_block_fwd": [_vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "sn2_lrb_block_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
     "sn2_bn_apply": [_vp, _vp, _ll, _i, _vp, _vp],
     "sn2_lrb_bwd_reduce": [_vp, _vp, _ll, _i, _vp, _vp],
     "sn2_lrb_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i, _vp, _vp, _vp],

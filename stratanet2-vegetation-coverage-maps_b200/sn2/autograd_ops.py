@@ -6,6 +6,8 @@ gradient; positions are inputs and get none either (as in the reference, where t
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib, ops
@@ -196,21 +198,25 @@ class LinReluBN(torch.autograd.Function):
         R, (Co, Ci) = x.shape[0], weight.shape
         dev = x.device
         y = torch.empty((R, Co), dtype=torch.float32, device=dev)
+        z = torch.empty((R, Co), dtype=torch.float32, device=dev)
         stats = torch.empty(2 * Co + 1, dtype=torch.float64, device=dev)
-        check(lib.sn2_lrb_fwd(dptr(x, torch.float32), dptr(_c(weight), torch.float32), dptr(_c(bias), torch.float32), R, Co, Ci,
-                              dptr(y), dptr(stats), stream_ptr()), "sn2_lrb_fwd")
-        group = _sync_group(bn)
-        if group is not None:
-            torch.distributed.all_reduce(stats, group=group)
         ss = torch.empty(4 * Co, dtype=torch.float32, device=dev)
         track = bn.track_running_stats and bn.running_mean is not None
-        check(lib.sn2_bn_finalize(dptr(stats), dptr(_c(gamma), torch.float32), dptr(_c(beta), torch.float32), float(bn.eps),
-                                  float(bn.momentum), dptr(bn.running_mean) if track else None,
-                                  dptr(bn.running_var) if track else None, dptr(ss), Co, stream_ptr()), "sn2_bn_finalize")
-        if track and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
-        z = torch.empty_like(y)
-        check(lib.sn2_bn_apply(dptr(y), dptr(ss), R, Co, dptr(z), stream_ptr()), "sn2_bn_apply")
+        rm, rv = (dptr(bn.running_mean), dptr(bn.running_var)) if track else (None, None)
+        nbt = dptr(bn.num_batches_tracked, torch.int64) if track and bn.num_batches_tracked is not None else None
+        wp, bp = dptr(_c(weight), torch.float32), dptr(_c(bias), torch.float32)
+        gp, btp = dptr(_c(gamma), torch.float32), dptr(_c(beta), torch.float32)
+        st = stream_ptr()
+        group = _sync_group(bn)
+        if group is None:
+            check(lib.sn2_lrb_block_fwd(dptr(x, torch.float32), wp, bp, gp, btp, float(bn.eps), float(bn.momentum), rm, rv, nbt,
+                                        R, Co, Ci, dptr(y), dptr(stats), dptr(ss), dptr(z), st), "sn2_lrb_block_fwd")
+        else:
+            check(lib.sn2_lrb_fwd(dptr(x, torch.float32), wp, bp, R, Co, Ci, dptr(y), dptr(stats), st), "sn2_lrb_fwd")
+            torch.distributed.all_reduce(stats, group=group)
+            check(lib.sn2_bn_finalize(dptr(stats), gp, btp, float(bn.eps), float(bn.momentum), rm, rv, nbt, dptr(ss), Co, st),
+                  "sn2_bn_finalize")
+            check(lib.sn2_bn_apply(dptr(y), dptr(ss), R, Co, dptr(z), st), "sn2_bn_apply")
         ops._count(5)
         ctx.save_for_backward(x, y, weight, ss, stats)
         ctx.group = group
@@ -224,21 +230,25 @@ class LinReluBN(torch.autograd.Function):
         R, (Co, Ci) = x.shape[0], weight.shape
         dev = x.device
         sums = torch.empty(2 * Co, dtype=torch.float64, device=dev)
-        check(lib.sn2_lrb_bwd_reduce(dptr(dz, torch.float32), dptr(y), R, Co, dptr(sums), stream_ptr()), "sn2_lrb_bwd_reduce")
-        # BatchNorm affine gradients from this rank's sums: dbeta = sum dz, dgamma = sum dz * yhat
-        mean, inv = ss[2 * Co:3 * Co].double(), ss[3 * Co:].double()
-        dbeta = sums[:Co].float()
-        dgamma = (inv * (sums[Co:] - mean * sums[:Co])).float()
-        if ctx.group is not None:
-            torch.distributed.all_reduce(sums, group=ctx.group)
+        dgb = torch.empty((2, Co), dtype=torch.float32, device=dev)
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         dW = torch.empty_like(weight)
         db = torch.empty(Co, dtype=torch.float32, device=dev)
         partial = torch.empty((LinReluBN.NBLK, Co * (Ci + 1)), dtype=torch.float32, device=dev)
-        check(lib.sn2_lrb_bwd(dptr(dz), dptr(y), dptr(x), dptr(_c(weight), torch.float32), dptr(ss), dptr(sums), dptr(stats), R,
-                              Co, Ci, dptr(dx), dptr(partial), LinReluBN.NBLK, dptr(dW), dptr(db), stream_ptr()), "sn2_lrb_bwd")
-        ops._count(4)
-        return dx, dW, db, dgamma, dbeta, None
+        wp, st = dptr(_c(weight), torch.float32), stream_ptr()
+        dgp, dbp = ctypes.c_void_p(dgb.data_ptr()), ctypes.c_void_p(dgb.data_ptr() + 4 * Co)
+        if ctx.group is None:
+            check(lib.sn2_lrb_block_bwd(dptr(dz, torch.float32), dptr(y), dptr(x), wp, dptr(ss), dptr(stats), R, Co, Ci, dptr(sums),
+                                        dgp, dbp, dptr(dx), dptr(partial), LinReluBN.NBLK, dptr(dW), dptr(db), st),
+                  "sn2_lrb_block_bwd")
+        else:
+            check(lib.sn2_lrb_bwd_reduce(dptr(dz, torch.float32), dptr(y), R, Co, dptr(sums), st), "sn2_lrb_bwd_reduce")
+            check(lib.sn2_bn_param_grad(dptr(sums), dptr(ss), Co, dgp, dbp, st), "sn2_bn_param_grad")  # this rank's sums
+            torch.distributed.all_reduce(sums, group=ctx.group)
+            check(lib.sn2_lrb_bwd(dptr(dz), dptr(y), dptr(x), wp, dptr(ss), dptr(sums), dptr(stats), R, Co, Ci, dptr(dx),
+                                  dptr(partial), LinReluBN.NBLK, dptr(dW), dptr(db), st), "sn2_lrb_bwd")
+        ops._count(5)
+        return dx, dW, db, dgb[0], dgb[1], None
 
 
 def _sync_group(bn):
@@ -260,6 +270,15 @@ def _fusable_block(lib, block, x) -> bool:
         return False
     return (bn.training and bn.affine and bn.momentum is not None and lin.bias is not None and x.dtype == torch.float32
             and bool(lib.sn2_lrb_supported(lin.out_features, lin.in_features)))
+
+
+def tall_linear(lin, x):
+    """lin(x) with the streaming weight-gradient kernel when x is tall (the head's lin1 / lin2 over every point)."""
+    lib = _lib.load()
+    if (x.shape[0] >= 65536 and lin.bias is not None and (x.requires_grad or lin.weight.requires_grad)
+            and lib.sn2_linear_wgrad_supported(lin.out_features, lin.in_features)):
+        return TallLinear.apply(x, lin.weight, lin.bias)
+    return lin(x)
 
 
 def run_mlp(seq, x):

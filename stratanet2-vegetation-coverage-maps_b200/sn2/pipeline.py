@@ -180,7 +180,7 @@ def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num
     interpolation -- runs in libsn2_b200.so (forward and backward)."""
     import torch.nn.functional as F
 
-    from .autograd_ops import EdgeMsg, Interp3, InterpPlot, SegmentMax, run_mlp
+    from .autograd_ops import EdgeMsg, Interp3, InterpPlot, SegmentMax, run_mlp, tall_linear
 
     B, Fc, N = cloud.shape
     if N != model.subsample_size:
@@ -213,9 +213,9 @@ def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num
     f3 = model.fp3_module.nn(torch.cat([InterpPlot.apply(g, pos2, M2), x2], dim=1))
     f2 = run_mlp(model.fp2_module.nn, torch.cat([Interp3.apply(f3, nbr2, w2), x1], dim=1))
     f1 = run_mlp(model.fp1_module.nn, torch.cat([Interp3.apply(f2, nbr1, w1), feat0], dim=1))
-    h = F.relu(model.lin1(f1))
+    h = F.relu(tall_linear(model.lin1, f1))
     h = F.dropout(h, p=model.drop, training=True)
-    scores = model.lin2(h)
+    scores = tall_linear(model.lin2, h)
     proba = torch.softmax(scores[:, :4], dim=1)
     cov = proba * torch.sigmoid(scores[:, 4:5])
     if trace is not None:
