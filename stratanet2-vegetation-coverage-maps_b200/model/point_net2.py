@@ -141,7 +141,8 @@ class PointNet2(nn.Module):
         with torch.cuda.device(device):
             if self.training and torch.is_grad_enabled():
                 cov, proba, g, cloud_dev = _pipeline.forward_train(
-                    self, cloud_data["xyz"], cloud_data["cloud"], device, self.sa1_module.max_num_neighbors, trace, timer)
+                    self, cloud_data["xyz"], cloud_data["cloud"], device, self.sa1_module.max_num_neighbors, trace, timer,
+                    structure=cloud_data.get("sn2_structure"))
             elif self.training:
                 raise RuntimeError("sn2 PointNet2: training mode under no_grad is not supported (BatchNorm batch "
                                    "statistics are only implemented on the autograd path); call model.eval()")

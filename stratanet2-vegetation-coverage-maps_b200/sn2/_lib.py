@@ -116,4 +116,6 @@ def hptr(t: torch.Tensor):
 
 
 def stream_ptr():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """Raw handle of torch's current stream on the current device (the private getter skips ~15 us of Python
+    per call in torch.cuda.current_stream(); the training step makes ~45 such calls)."""
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))

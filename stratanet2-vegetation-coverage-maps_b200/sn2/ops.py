@@ -79,8 +79,23 @@ def fps_dense(pos4: torch.Tensor, B: int, N: int, M: int, start: torch.Tensor | 
     return idx, out
 
 
-def ball_query_dense(pos4: torch.Tensor, qpos4: torch.Tensor, B: int, N: int, M: int, r: float, K: int):
-    """-> rowptr int32 [B*M+1], col int32 [E] (global point rows, ascending inside each query)."""
+_PINNED_RING = None
+_PINNED_NEXT = 0
+
+
+def _pinned_slot() -> torch.Tensor:
+    """One int32 of page-locked host memory from a ring allocated once (a fresh pinned allocation per call can
+    cost a cudaHostAlloc, which synchronises the device)."""
+    global _PINNED_RING, _PINNED_NEXT
+    if _PINNED_RING is None:
+        _PINNED_RING = torch.empty(1024, dtype=torch.int32, pin_memory=True)
+    _PINNED_NEXT = (_PINNED_NEXT + 1) % 1024
+    return _PINNED_RING[_PINNED_NEXT:_PINNED_NEXT + 1]
+
+
+def ball_query_begin(pos4: torch.Tensor, qpos4: torch.Tensor, B: int, N: int, M: int, r: float, K: int) -> dict:
+    """First half of the CSR ball query: grid, per-query counts, row pointers, and an asynchronous copy of the edge
+    total to pinned host memory.  Nothing here waits for the GPU; `ball_query_finish` does (on the recorded event)."""
     lib = _lib.load()
     dev = pos4.device
     hdr = torch.empty(B * GRID_HDR, dtype=torch.float32, device=dev)
@@ -99,12 +114,32 @@ def ball_query_dense(pos4: torch.Tensor, qpos4: torch.Tensor, B: int, N: int, M:
     scratch = torch.empty(B, dtype=torch.int32, device=dev)
     check(lib.sn2_rowptr_scan(dptr(cnt), B, M, dptr(rowptr), dptr(scratch), st), "sn2_rowptr_scan")
     _count(2)
-    E = int(rowptr[-1].item())  # the one host sync of the level: sizes the edge list
-    col = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
-    check(lib.sn2_ball_fill(dptr(hdr), dptr(cell_start), dptr(sorted4), dptr(qpos4), B, N, M, r2, int(K), dptr(rowptr),
-                            dptr(col), st), "sn2_ball_fill")
+    total = _pinned_slot()
+    total.copy_(rowptr[-1:], non_blocking=True)
+    ready = torch.cuda.Event()
+    ready.record()
+    return dict(hdr=hdr, cell_start=cell_start, sorted4=sorted4, qpos4=qpos4, rowptr=rowptr, total=total, ready=ready,
+                shape=(B, N, M, r2, int(K)))
+
+
+def ball_query_finish(state: dict):
+    """Second half: wait for the edge total (the one host sync of the level, sizes the edge list) and fill `col`.
+    Runs on the current stream, which must be the stream of `ball_query_begin` or ordered after it."""
+    lib = _lib.load()
+    state["ready"].synchronize()
+    E = int(state["total"][0])
+    B, N, M, r2, K = state["shape"]
+    rowptr = state["rowptr"]
+    col = torch.empty(max(E, 1), dtype=torch.int32, device=rowptr.device)
+    check(lib.sn2_ball_fill(dptr(state["hdr"]), dptr(state["cell_start"]), dptr(state["sorted4"]), dptr(state["qpos4"]), B, N, M,
+                            r2, K, dptr(rowptr), dptr(col), stream_ptr()), "sn2_ball_fill")
     _count(1)
     return rowptr, col[:E]
+
+
+def ball_query_dense(pos4: torch.Tensor, qpos4: torch.Tensor, B: int, N: int, M: int, r: float, K: int):
+    """-> rowptr int32 [B*M+1], col int32 [E] (global point rows, ascending inside each query)."""
+    return ball_query_finish(ball_query_begin(pos4, qpos4, B, N, M, r, K))
 
 
 def pointconv_fwd(level: int, pos4, feat, qpos4, rowptr, col, w_host: torch.Tensor):

@@ -168,44 +168,162 @@ def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_
     return cov, proba, g, cloud_d
 
 
+class TrainStructure:
+    """The no-grad structural stage of one training batch -- ingest, FPS x2, ball query x2 (CSR), kNN x2 -- split so
+    that it can run on a side stream one batch ahead of the differentiable part (StructurePrefetcher):
+    `begin` only enqueues work (and an async copy of the two edge totals); `finish` waits for those totals, sizes
+    and fills the edge lists, and records `done`.  forward_train(structure=...) makes its stream wait for `done`."""
+
+    def __init__(self, model, xyz, cloud, device, max_num_neighbors: int = 2000, timer=None):
+        B, Fc, N = cloud.shape
+        if N != model.subsample_size:
+            raise RuntimeError(f"PointNet2.forward: every plot must have subsample_size={model.subsample_size} points, got {N}")
+        self.B, self.N = B, N
+        self.stream = torch.cuda.current_stream(device)
+        sa1, sa2 = model.sa1_module, model.sa2_module
+        T = timer if timer is not None else _NOTIMER
+        self._T = T
+        with torch.no_grad():
+            self.xyz_d = xyz.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+            self.cloud_d = cloud.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+            with T.stage("ingest"):
+                self.pos0, self.feat0 = ops.ingest(self.xyz_d, self.cloud_d)
+            self.M1 = M1 = ops.m_of(N, sa1.ratio)
+            self.M2 = M2 = ops.m_of(M1, sa2.ratio)
+            with T.stage("fps1"):
+                self.idx1, self.pos1 = ops.fps_dense(self.pos0, B, N, M1)
+            with T.stage("fps2"):
+                self.idx2, self.pos2 = ops.fps_dense(self.pos1, B, M1, M2)
+            with T.stage("ball1"):
+                self._bq1 = ops.ball_query_begin(self.pos0, self.pos1, B, N, M1, sa1.r, max_num_neighbors)
+            with T.stage("ball2"):
+                self._bq2 = ops.ball_query_begin(self.pos1, self.pos2, B, M1, M2, sa2.r, max_num_neighbors)
+            with T.stage("knn"):
+                self.nbr2, self.w2 = ops.knn3_dense(self.pos2, self.pos1, B, M2, M1)
+                self.nbr1, self.w1 = ops.knn3_dense(self.pos1, self.pos0, B, M1, N)
+            self.plot_ptr = torch.arange(B + 1, dtype=torch.int32, device=device) * M2
+        self.done = None
+        self.managed = False
+
+    def finish(self):
+        """Must run with the stream of __init__ current (the edge lists are filled on it)."""
+        if self.done is None:
+            with torch.no_grad():
+                with self._T.stage("ball1"):
+                    self.rowptr1, self.col1 = ops.ball_query_finish(self._bq1)
+                with self._T.stage("ball2"):
+                    self.rowptr2, self.col2 = ops.ball_query_finish(self._bq2)
+            self._bq1 = self._bq2 = None
+            self.done = torch.cuda.Event()
+            self.done.record()
+        return self
+
+    def use_on(self, stream):
+        """Order `stream` after the structural stage.  Unless a StructurePrefetcher manages this object's lifetime
+        (it keeps it alive until `stream` has finished the step), mark the tensors as used on `stream` so that the
+        caching allocator does not hand their memory back to the producing stream too early."""
+        self.finish()
+        if stream != self.stream:
+            stream.wait_event(self.done)
+            if not self.managed:
+                for v in vars(self).values():
+                    if torch.is_tensor(v) and v.is_cuda:
+                        v.record_stream(stream)
+        return self
+
+
+class StructurePrefetcher:
+    """Iterate over training batches with the structural stage of batch i+1 running on a side stream under the
+    differentiable part of batch i (FPS is a serial chain on one SM per plot: 32 of 148 SMs at config 3).
+
+        for batch in StructurePrefetcher(model, loader):
+            cov, proba = model(batch)          # picks up batch["sn2_structure"]
+            ...loss.backward(); optimizer.step()
+
+    Each yielded batch is the loader's own dict plus the key "sn2_structure".  Results are identical to the plain
+    loop (same kernels on the same inputs); only the stream they run on changes.
+
+    Memory: the structural tensors are allocated on the side stream and read on the consumer's stream.  Instead of
+    Tensor.record_stream (whose deferred frees make the side stream's pool grow by cudaMalloc at unpredictable
+    moments -- a 100-200 ms stall per event once NCCL has enabled peer access), the prefetcher keeps each
+    structure alive until an event recorded on the consumer's stream after the step has completed, at most
+    `RETIRE_DEPTH` steps later; then the memory returns to the side stream's pool and is reused as is."""
+
+    RETIRE_DEPTH = 2
+
+    def __init__(self, model, batches, device=None, max_num_neighbors=None):
+        self.model, self.batches = model, batches
+        self.device = device if device is not None else next(model.parameters()).device
+        self.K = max_num_neighbors
+        self.side = torch.cuda.Stream(self.device)
+        self._retired = []
+
+    def _begin(self, batch):
+        K = self.K if self.K is not None else getattr(self.model.sa1_module, "max_num_neighbors", 2000)
+        with torch.cuda.stream(self.side):
+            return TrainStructure(self.model, batch["xyz"], batch["cloud"], self.device, K)
+
+    def _finish(self, st):
+        with torch.cuda.stream(self.side):
+            st.finish()
+        st.managed = True
+        return st
+
+    def _retire(self, st):
+        """Call right after the consumer enqueued its step on the current stream."""
+        ev = torch.cuda.Event()
+        ev.record()
+        self._retired.append((st, ev))
+        while len(self._retired) > self.RETIRE_DEPTH:
+            _, old = self._retired.pop(0)
+            old.synchronize()  # finished long ago unless the GPU is RETIRE_DEPTH steps behind (then: back-pressure)
+
+    def drain(self):
+        for _, ev in self._retired:
+            ev.synchronize()
+        self._retired.clear()
+
+    def __iter__(self):
+        it = iter(self.batches)
+        try:
+            cur = next(it)
+        except StopIteration:
+            return
+        cur_s = self._finish(self._begin(cur))
+        try:
+            for nxt in it:
+                nxt_s = self._begin(nxt)                 # enqueued on the side stream, no host wait
+                yield {**cur, "sn2_structure": cur_s}    # the consumer enqueues step i on its own stream
+                self._retire(cur_s)
+                cur, cur_s = nxt, self._finish(nxt_s)    # edge totals arrived long ago: sizes + fills the edge lists
+            yield {**cur, "sn2_structure": cur_s}
+            self._retire(cur_s)
+        finally:
+            self.drain()
+
+
 def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_neighbors: int = 2000,
-                  trace: ForwardTrace | None = None, timer=None):
+                  trace: ForwardTrace | None = None, timer=None, structure: TrainStructure | None = None):
     """Training-mode forward with autograd (reference :106-153 under ``model.train()``).
 
     BatchNorm needs batch statistics over every edge message / point of the batch, so the
-    message matrices are materialised like the reference does and the Linear -> ReLU -> BatchNorm blocks are
-    the model's own torch modules (cuBLAS GEMMs, running-stat updates and SyncBatchNorm all behave exactly
-    as in the reference).  Everything the reference delegates to torch_cluster / torch_scatter /
-    torch_geometric -- FPS, ball query, kNN, message gather, max aggregation with arg-routed gradient,
-    interpolation -- runs in libsn2_b200.so (forward and backward)."""
+    message matrices are materialised like the reference does; blocks Linear -> ReLU -> BatchNorm that see
+    >= 65 536 rows run as the fused LinReluBN kernels (csrc/train_mlp.cu), the small ones as the model's own torch
+    modules; running statistics and SyncBatchNorm behave as in the reference either way.  Everything the
+    reference delegates to torch_cluster / torch_scatter / torch_geometric -- FPS, ball query, kNN, message
+    gather, max aggregation with arg-routed gradient, interpolation -- runs in libsn2_b200.so (forward and
+    backward).  `structure`: a TrainStructure prepared ahead of time (StructurePrefetcher)."""
     import torch.nn.functional as F
 
     from .autograd_ops import EdgeMsg, Interp3, InterpPlot, SegmentMax, run_mlp, tall_linear
 
-    B, Fc, N = cloud.shape
-    if N != model.subsample_size:
-        raise RuntimeError(f"PointNet2.forward: every plot must have subsample_size={model.subsample_size} points, got {N}")
-    xyz_d = xyz.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
-    cloud_d = cloud.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+    S = structure if structure is not None else TrainStructure(model, xyz, cloud, device, max_num_neighbors, timer)
+    S.use_on(torch.cuda.current_stream(device))
+    B, N, M1, M2 = S.B, S.N, S.M1, S.M2
     sa1, sa2 = model.sa1_module, model.sa2_module
-    T = timer if timer is not None else _NOTIMER
-    with torch.no_grad():
-        with T.stage("ingest"):
-            pos0, feat0 = ops.ingest(xyz_d, cloud_d)
-        M1 = ops.m_of(N, sa1.ratio)
-        M2 = ops.m_of(M1, sa2.ratio)
-        with T.stage("fps1"):
-            idx1, pos1 = ops.fps_dense(pos0, B, N, M1)
-        with T.stage("fps2"):
-            idx2, pos2 = ops.fps_dense(pos1, B, M1, M2)
-        with T.stage("ball1"):
-            rowptr1, col1 = ops.ball_query_dense(pos0, pos1, B, N, M1, sa1.r, max_num_neighbors)
-        with T.stage("ball2"):
-            rowptr2, col2 = ops.ball_query_dense(pos1, pos2, B, M1, M2, sa2.r, max_num_neighbors)
-        with T.stage("knn"):
-            nbr2, w2 = ops.knn3_dense(pos2, pos1, B, M2, M1)
-            nbr1, w1 = ops.knn3_dense(pos1, pos0, B, M1, N)
-        plot_ptr = torch.arange(B + 1, dtype=torch.int32, device=device) * M2
+    cloud_d, pos0, feat0, idx1, pos1, idx2, pos2 = S.cloud_d, S.pos0, S.feat0, S.idx1, S.pos1, S.idx2, S.pos2
+    rowptr1, col1, rowptr2, col2 = S.rowptr1, S.col1, S.rowptr2, S.col2
+    nbr1, w1, nbr2, w2, plot_ptr = S.nbr1, S.w1, S.nbr2, S.w2, S.plot_ptr
 
     x1, _ = SegmentMax.apply(run_mlp(sa1.conv.local_nn, EdgeMsg.apply(feat0, pos0, pos1, rowptr1, col1)), rowptr1)
     x2, _ = SegmentMax.apply(run_mlp(sa2.conv.local_nn, EdgeMsg.apply(x1, pos1, pos2, rowptr2, col2)), rowptr2)

@@ -583,6 +583,41 @@ def test_fused_lin_relu_bn_block(cuda_device, Ci, Co, R):
     assert int(bn.num_batches_tracked) == int(ref[2].num_batches_tracked) == 1
 
 
+def test_structure_prefetcher_matches_plain_loop(cuda_device):
+    """StructurePrefetcher (structural stage of batch i+1 on a side stream) yields the same forward results and
+    gradients as the plain loop, batch by batch."""
+    import copy
+
+    from sn2.pipeline import ForwardTrace, StructurePrefetcher
+
+    N = 4096
+    args, net, _ = _make_models(N, cuda_device)
+    net.train()
+    net2 = copy.deepcopy(net)
+    batches = [_plots(3, 3, N, v) for v in ("plain", "cm", "plain", "dup")]
+    plain = []
+    for b in batches:
+        net.zero_grad()
+        cov, proba = net(b)
+        (cov.sum() + (proba ** 2).sum()).backward()
+        plain.append((cov.detach().clone(), net.lin2.weight.grad.clone(), net.sa1_module.conv.local_nn[0][0].weight.grad.clone()))
+    got = []
+    for b in StructurePrefetcher(net2, batches):
+        assert "sn2_structure" in b and "xyz" in b
+        net2.zero_grad()
+        tr = ForwardTrace()
+        cov, proba = net2(b, trace=tr)
+        (cov.sum() + (proba ** 2).sum()).backward()
+        got.append((cov.detach().clone(), net2.lin2.weight.grad.clone(), net2.sa1_module.conv.local_nn[0][0].weight.grad.clone()))
+    assert len(got) == len(plain) == 4
+    for (c0, g0, h0), (c1, g1, h1) in zip(plain, got):
+        torch.testing.assert_close(c1, c0, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(g1, g0, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(h1, h0, rtol=1e-3, atol=1e-4)
+    for (k, v), (_, v2) in zip(net.state_dict().items(), net2.state_dict().items()):
+        torch.testing.assert_close(v2, v, rtol=1e-5, atol=1e-6, msg=lambda m, k=k: f"{k}: {m}")
+
+
 def _golden_paths():
     import glob
     import os

@@ -33,3 +33,20 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3): step()
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=60))
+
+if "--cprofile" in sys.argv:
+    # host-side cost of a step (the step is launch bound once the kernels are fused): Python profile of 20 steps
+    import cProfile, pstats, time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20): step()
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"host enqueue time {1e3 * (t1 - t0) / 20:.2f} ms/step, drained after {1e3 * (t2 - t1):.2f} ms more")
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(20): step()
+    pr.disable()
+    torch.cuda.synchronize()
+    pstats.Stats(pr).sort_stats("tottime").print_stats(45)
