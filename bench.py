@@ -216,10 +216,11 @@ def init_dist(dev):
 
 def train_loss(proba, pw, gt, pdf):
     """Reference training loss (learning/train.py:52-66, learning/loss_functions.py:9-57), synthetic pdf."""
-    mae = torch.sqrt((pw[:, [0, 2, 3]] - gt[:, [0, 2, 3]]) ** 2 + 1e-4).mean()
-    # columns 0, 2, 3 of proba as slices (an index list would put a sort + index_put over every point into backward)
-    p023 = torch.cat([proba[:, :1], proba[:, 2:]], dim=1)
-    nll = -torch.log((p023.double() * pdf).sum(1) + 1e-6).mean().float()
+    # columns 0, 2, 3 as slices: an index list would put a sort + index_put over every point into backward and a
+    # host->device copy of the indices into the step (not capturable in a CUDA graph)
+    sel = lambda t: torch.cat([t[:, :1], t[:, 2:]], dim=1)  # noqa: E731
+    mae = torch.sqrt((sel(pw) - sel(gt)) ** 2 + 1e-4).mean()
+    nll = -torch.log((sel(proba).double() * pdf).sum(1) + 1e-6).mean().float()
     p = proba[:, 2:]
     ent = -(p * torch.log(p + 1e-6)).sum(1).mean()
     return mae + 0.10 * nll + 0.04 * ent
@@ -230,7 +231,7 @@ def run_train(opts, cfg):
     import torch.distributed as dist
     from model.project_to_2d import project_to_plotwise_coverages
     from sn2 import ops, parallel
-    from sn2.pipeline import StageTimer, StructurePrefetcher
+    from sn2.pipeline import GraphedTrainStep, StageTimer, StructurePrefetcher
     from sn2.synth import synth_batch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -247,7 +248,8 @@ def run_train(opts, cfg):
     if world > 1:
         net = parallel.convert_sync_batchnorm(net)  # reference-exact BatchNorm over the GLOBAL batch
     bucket = parallel.GradBucket(net)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-3)  # learning/train.py:180-185
+    use_graph = world == 1 and not opts.no_graph  # SyncBatchNorm / NCCL stay outside graphs: multi-GPU uses the prefetch loop
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-3, capturable=use_graph)  # learning/train.py:180-185
     full = synth_batch(opts.config, Bg, N)
     g = torch.Generator().manual_seed(9)
     full["gt"] = torch.rand(Bg, 4, generator=g)
@@ -273,6 +275,19 @@ def run_train(opts, cfg):
         opt.step()
         if read_loss:
             loss_host.copy_(loss.detach(), non_blocking=True)
+
+    def graph_step(batch):
+        """The same step as a graph-safe closure (no host synchronisation inside): returns the loss tensor."""
+        bucket.zero()
+        cov, proba = net(batch)
+        pw = project_to_plotwise_coverages(cov, net.last_cloud_device, args)
+        loss = train_loss(proba, pw, batch["gt"], pdf_of(batch["xyz"]))
+        loss.backward()
+        bucket.allreduce(Bl, Bg)
+        opt.step()
+        return loss.detach()
+
+    gstep = GraphedTrainStep(net, graph_step, optimizer=opt, device=dev) if use_graph else None
 
     def barrier():
         if world > 1:
@@ -301,7 +316,12 @@ def run_train(opts, cfg):
         a.record()
         for batch in StructurePrefetcher(net, (src for _ in range(steps)), dev):
             flush.fill_(1)
-            step(batch, None, read_loss)
+            if gstep is not None:  # whole step = input copies into the static buffers + one graph launch
+                loss = gstep(batch)
+                if read_loss:
+                    loss_host.copy_(loss, non_blocking=True)
+            else:
+                step(batch, None, read_loss)
         b.record()
         barrier()
         return a.elapsed_time(b)
@@ -315,9 +335,11 @@ def run_train(opts, cfg):
     timer = StageTimer()
     ms_serial = timed(lambda: step(dev_in, timer), opts.steps)
     ms_serial_e2e = timed(lambda: step(host, None, True), opts.steps)
-    l0 = ops.LAUNCHES
+    l0, r0 = ops.LAUNCHES, (gstep.replays if gstep is not None else 0)
     ms_res = timed_prefetch(dev_in, opts.steps, False)
-    launches = ops.LAUNCHES - l0
+    launches = ops.LAUNCHES - l0  # structural stage (launched live) ...
+    if gstep is not None:        # ... + our kernels inside each graph replay (counted at capture)
+        launches += (gstep.replays - r0) * gstep.launches_per_replay
     ms_e2e = timed_prefetch(host, opts.steps, True)
     clocks = sampler.stop()
     t = torch.tensor([ms_res, ms_e2e, ms_serial, ms_serial_e2e], dtype=torch.float64, device=dev)
@@ -337,6 +359,8 @@ def run_train(opts, cfg):
                    "batchnorm": "SyncBatchNorm over the global batch" if world > 1 else "single process",
                    "l2": "flushed between timed steps (256 MiB write, inside the timed region)",
                    "overlap": "StructurePrefetcher: FPS / ball query / kNN of batch i+1 on a side stream under step i",
+                   "cuda_graph": ("GraphedTrainStep: fwd + loss + bwd + Adam replayed as one CUDA graph (edge lists at fixed "
+                                  "capacity, live counts on the device)") if use_graph else "off (multi-GPU: SyncBatchNorm + NCCL run eagerly)",
                    "parallelism": f"dp{world} by plot"},
         "points_per_s": value * N,
         "serial": {"value": Bg * opts.steps / (ms_serial / 1e3), "ms_per_step": ms_serial / opts.steps,
@@ -344,8 +368,8 @@ def run_train(opts, cfg):
                    "note": "plain loop, no prefetch; per-step event pairs, L2 flush outside them"},
         "e2e": {"value": Bg * opts.steps / (ms_e2e / 1e3), "unit": "plots/s", "ms_per_step": ms_e2e / opts.steps,
                 "h2d_bytes_per_step": int(sum(v.numel() * 4 for v in host.values())), "d2h_bytes_per_step": 4,
-                "api": "StructurePrefetcher + PointNet2.forward (train) + project_to_plotwise_coverages + loss.backward + "
-                       "GradBucket.allreduce + Adam"},
+                "api": ("StructurePrefetcher + GraphedTrainStep(" if use_graph else "StructurePrefetcher + (") +
+                       "PointNet2.forward (train) + project_to_plotwise_coverages + loss.backward + GradBucket.allreduce + Adam)"},
         "gpu_launches": launches, "clocks": clocks,
         "stage_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
         "roofline": {"kernel": "fps1", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
@@ -471,6 +495,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="config 3: eager prefetch loop instead of the CUDA-graph step")
     ap.add_argument("--pipeline", type=int, default=3, help="batches in flight for value / e2e (0 = serial steps only)")
     ap.add_argument("--prewarm-s", type=float, default=1.5, help="seconds of untimed steps before anything is timed (clock / cache ramp)")
     opts = ap.parse_args()

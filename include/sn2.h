@@ -176,8 +176,12 @@ int sn2_project_rasters(const float *cloud, const float *cov, long long cov_sb, 
 /* PointConv.message (model/point_net2.py:27): msg [E, C+3] = [x[col[e]], pos[col[e]] - qpos[row(e)]]. */
 int sn2_edge_msg_fwd(const float *x, const float *pos4, const float *qpos4, const int *rowptr,
                      const int *col, int Q, int C, float *msg, void *stream);
-/* dx [P, C] += dmsg[e][0:C] at row col[e] (dx zero-initialised by the caller; atomics). */
-int sn2_edge_msg_bwd(const float *dmsg, const int *col, long long E, int C, float *dx, void *stream);
+/* dx [P, C] += dmsg[e][0:C] at row col[e] (dx zero-initialised by the caller; atomics).
+ * rows_dev (nullable, device int32): when given, only the first min(E, *rows_dev) edges are processed -- the edge
+ * arrays then have a fixed CAPACITY E and the live count stays on the device (CUDA-graph replay of a training step
+ * whose edge count changes from batch to batch).  Same meaning wherever `rows_dev` appears below. */
+int sn2_edge_msg_bwd(const float *dmsg, const int *col, long long E, const int *rows_dev, int C, float *dx,
+                     void *stream);
 /* scatter max over CSR rows (PointConv aggr='max', global_max_pool): out [Q,C], arg [Q,C] = first edge
  * attaining the max (-1 and value 0 for an empty row).  C in {16, 32, 64}. */
 int sn2_segment_max_fwd(const float *vals, const int *rowptr, int Q, int C, float *out, int *arg,
@@ -207,7 +211,8 @@ int sn2_linear_wgrad(const float *dy, const float *x, long long E, int Co, int C
  * Replaces, for one block of the reference's MLP() (model/point_net2.py:45-53) applied to R rows, the torch
  * sequence addmm / relu / batch_norm forward and their three backward nodes.  Supported (Ci, Co): (11,16) (16,16)
  * (19,32) (80,34) (42,34).  All pointers are device pointers.
- *   sn2_lrb_fwd        y [R,Co] = relu(x W^T + b); stats [2*Co+1] fp64 = {sum y, sum y^2, R} (zeroed here).
+ *   sn2_lrb_fwd        y [R,Co] = relu(x W^T + b); stats [2*Co+1] fp64 = {sum y, sum y^2, rows} (zeroed here);
+ *                      rows = R, or min(R, *rows_dev) when rows_dev is given.
  *                      For SyncBatchNorm the caller all-reduces stats across ranks before sn2_bn_finalize.
  *   sn2_bn_finalize    stats -> ss [4*Co] = {scale, shift, mean, invstd} (biased variance, eps); running_mean /
  *                      running_var (nullable) updated with `momentum` and the unbiased variance like torch;
@@ -217,28 +222,30 @@ int sn2_linear_wgrad(const float *dy, const float *x, long long E, int Co, int C
  *   sn2_lrb_bwd        dx [R,Ci] (nullable) = dy W with dy = relu'(y) * BN'(dz); dW [Co,Ci] = dy^T x; db [Co];
  *                      partial: scratch [nblk, Co*(Ci+1)], fixed-order two-stage reduction. */
 int sn2_lrb_supported(int Co, int Ci);
-int sn2_lrb_fwd(const float *x, const float *W, const float *b, long long R, int Co, int Ci, float *y,
-                double *stats, void *stream);
+int sn2_lrb_fwd(const float *x, const float *W, const float *b, long long R, const int *rows_dev, int Co, int Ci,
+                float *y, double *stats, void *stream);
 int sn2_bn_finalize(const double *stats, const float *gamma, const float *beta, float eps, float momentum,
                     float *running_mean, float *running_var, long long *num_batches_tracked, float *ss, int Co,
                     void *stream);
-int sn2_bn_apply(const float *y, const float *ss, long long R, int Co, float *z, void *stream);
-int sn2_lrb_bwd_reduce(const float *dz, const float *y, long long R, int Co, double *sums, void *stream);
+int sn2_bn_apply(const float *y, const float *ss, long long R, const int *rows_dev, int Co, float *z, void *stream);
+int sn2_lrb_bwd_reduce(const float *dz, const float *y, long long R, const int *rows_dev, int Co, double *sums,
+                       void *stream);
 /* BatchNorm affine gradients of THIS rank from its own (not all-reduced) sums: dbeta = sum dz, dgamma = sum dz*yhat. */
 int sn2_bn_param_grad(const double *sums, const float *ss, int Co, float *dgamma, float *dbeta, void *stream);
 int sn2_lrb_bwd(const float *dz, const float *y, const float *x, const float *W, const float *ss,
-                const double *sums, const double *stats, long long R, int Co, int Ci, float *dx, float *partial,
-                int nblk, float *dW, float *db, void *stream);
+                const double *sums, const double *stats, long long R, const int *rows_dev, int Co, int Ci, float *dx,
+                float *partial, int nblk, float *dW, float *db, void *stream);
 /* The same block in one call each way when no all-reduce sits between the kernels (plain BatchNorm1d):
  * fwd = sn2_lrb_fwd + sn2_bn_finalize (num_batches_tracked += 1 when given) + sn2_bn_apply;
  * bwd = sn2_lrb_bwd_reduce + sn2_bn_param_grad + sn2_lrb_bwd. */
 int sn2_lrb_block_fwd(const float *x, const float *W, const float *b, const float *gamma, const float *beta,
                       float eps, float momentum, float *running_mean, float *running_var,
-                      long long *num_batches_tracked, long long R, int Co, int Ci, float *y, double *stats,
-                      float *ss, float *z, void *stream);
+                      long long *num_batches_tracked, long long R, const int *rows_dev, int Co, int Ci, float *y,
+                      double *stats, float *ss, float *z, void *stream);
 int sn2_lrb_block_bwd(const float *dz, const float *y, const float *x, const float *W, const float *ss,
-                      const double *stats, long long R, int Co, int Ci, double *sums, float *dgamma,
-                      float *dbeta, float *dx, float *partial, int nblk, float *dW, float *db, void *stream);
+                      const double *stats, long long R, const int *rows_dev, int Co, int Ci, double *sums,
+                      float *dgamma, float *dbeta, float *dx, float *partial, int nblk, float *dW, float *db,
+                      void *stream);
 
 /* ================= local-map fusion (BASELINE config 4), csrc/fusion.cu =============
  * Weighted-average mosaic of per-plot rasters into the parcel grid; replaces add_weights_band_to_rasters +

@@ -90,8 +90,9 @@ struct LrbFwd {
 template <int CI, int CO>
 __global__ void __launch_bounds__(LRB_T, (CO > 16 ? 1 : 2))
 lrb_fwd_kernel(const float *__restrict__ x, const float *__restrict__ W, const float *__restrict__ b, long long R,
-               float *__restrict__ y, double *__restrict__ stats)
+               const int *__restrict__ rows_dev, float *__restrict__ y, double *__restrict__ stats)
 {
+    if (rows_dev) R = min(R, (long long)__ldg(rows_dev));
     using L = LrbFwd<CI, CO>;
     constexpr int COP = L::COP, XS = L::XS;
     extern __shared__ __align__(16) unsigned char lrb_smem[];
@@ -176,7 +177,10 @@ __global__ void bn_finalize_kernel(const double *__restrict__ stats, const float
     if (running_var) running_var[o] = (1.f - momentum) * running_var[o] + momentum * (float)(n > 1.0 ? var * n / (n - 1.0) : var);
 }
 
-__global__ void set_count_kernel(double *stats, int Co, double n) { stats[2 * Co] = n; }
+__global__ void set_count_kernel(double *stats, int Co, long long R, const int *__restrict__ rows_dev)
+{
+    stats[2 * Co] = (double)(rows_dev ? min(R, (long long)*rows_dev) : R);
+}
 
 // BatchNorm affine gradients from one rank's raw sums: dbeta = sum dz, dgamma = sum dz * yhat = invstd * (S2 - mean * S1)
 __global__ void bn_param_grad_kernel(const double *__restrict__ sums, const float *__restrict__ ss, int Co,
@@ -191,8 +195,11 @@ __global__ void bn_param_grad_kernel(const double *__restrict__ sums, const floa
 
 // z = y * scale[c] + shift[c]; two channels per thread (every supported Co is even).
 __global__ void __launch_bounds__(256)
-bn_apply_kernel(const float2 *__restrict__ y, const float *__restrict__ ss, long long n2, int Co, float2 *__restrict__ z)
+bn_apply_kernel(const float2 *__restrict__ y, const float *__restrict__ ss, long long R, const int *__restrict__ rows_dev,
+                int Co, float2 *__restrict__ z)
 {
+    if (rows_dev) R = min(R, (long long)__ldg(rows_dev));
+    const long long n2 = R * (Co >> 1);
     const int half = Co >> 1;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const int step = (int)(stride % half);
@@ -212,8 +219,10 @@ bn_apply_kernel(const float2 *__restrict__ y, const float *__restrict__ ss, long
 // ---------------------------------------------------------------------------------------------------------------
 template <int CO>
 __global__ void __launch_bounds__(LRB_T, (CO > 16 ? 1 : 2))
-lrb_bwd_reduce_kernel(const float *__restrict__ dz, const float *__restrict__ y, long long R, double *__restrict__ sums)
+lrb_bwd_reduce_kernel(const float *__restrict__ dz, const float *__restrict__ y, long long R,
+                      const int *__restrict__ rows_dev, double *__restrict__ sums)
 {
+    if (rows_dev) R = min(R, (long long)__ldg(rows_dev));
     __shared__ double red[2 * CO];
     for (int o = threadIdx.x; o < 2 * CO; o += LRB_T) red[o] = 0.0;
     float a1[CO], a2[CO];
@@ -253,8 +262,10 @@ template <int CI, int CO>
 __global__ void __launch_bounds__(LrbBwd<CI, CO>::TR, (CI > 48 ? 1 : 2))
 lrb_bwd_kernel(const float *__restrict__ dz, const float *__restrict__ y, const float *__restrict__ x,
                const float *__restrict__ W, const float *__restrict__ ss, const double *__restrict__ sums,
-               const double *__restrict__ stats, long long R, float *__restrict__ dx, float *__restrict__ partial)
+               const double *__restrict__ stats, long long R, const int *__restrict__ rows_dev, float *__restrict__ dx,
+               float *__restrict__ partial)
 {
+    if (rows_dev) R = min(R, (long long)__ldg(rows_dev));
     using L = LrbBwd<CI, CO>;
     constexpr int TR = L::TR, CIP = L::CIP, G = L::G, NP = L::NP;
     extern __shared__ __align__(16) unsigned char lrb_smem[];
@@ -357,57 +368,63 @@ lrb_bwd_kernel(const float *__restrict__ dz, const float *__restrict__ y, const 
     }
 }
 
-// fixed-order reduction of the CTA partials (same layout as linear_wgrad's: [Co][Ci + 1], last column = db)
+// fixed-order reduction of the CTA partials (layout [Co][Ci + 1], last column = db): one warp per output, lanes
+// stride over the CTAs, xor-shuffle tree (deterministic)
 __global__ void __launch_bounds__(256)
 lrb_wgrad_reduce_kernel(const float *__restrict__ partial, int nblk, int Co, int CI, float *__restrict__ dW, float *__restrict__ db)
 {
     const int n = Co * (CI + 1);
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (t >= n) return;
     float s = 0.f;
-    for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * n + t];
-    const int o = t / (CI + 1), i = t - o * (CI + 1);
-    if (i < CI) dW[o * CI + i] = s;
-    else db[o] = s;
+    for (int b = lane; b < nblk; b += 32) s += __ldg(partial + (size_t)b * n + t);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(SN2_FULL, s, d);
+    if (lane == 0) {
+        const int o = t / (CI + 1), i = t - o * (CI + 1);
+        if (i < CI) dW[o * CI + i] = s;
+        else db[o] = s;
+    }
 }
 
 template <int CI, int CO>
-static int launch_lrb_fwd(const float *x, const float *W, const float *b, long long R, float *y, double *stats, cudaStream_t st)
+static int launch_lrb_fwd(const float *x, const float *W, const float *b, long long R, const int *rows_dev, float *y,
+                          double *stats, cudaStream_t st)
 {
     using L = LrbFwd<CI, CO>;
     auto kern = lrb_fwd_kernel<CI, CO>;
     SN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM), "lrb_fwd attr");
     SN2_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * CO, st), "lrb_fwd memset");
-    set_count_kernel<<<1, 1, 0, st>>>(stats, CO, (double)R);
+    set_count_kernel<<<1, 1, 0, st>>>(stats, CO, R, rows_dev);
     const long long nblocks = ((R + 31) / 32 + L::WARPS - 1) / L::WARPS;
     const int grid = (int)min(nblocks, (long long)148 * 2);
-    kern<<<grid, LRB_T, L::SMEM, st>>>(x, W, b, R, y, stats);
+    kern<<<grid, LRB_T, L::SMEM, st>>>(x, W, b, R, rows_dev, y, stats);
     SN2_LAUNCH_CHECK("lrb_fwd_kernel");
     return SN2_OK;
 }
 
 template <int CO>
-static int launch_lrb_bwd_reduce(const float *dz, const float *y, long long R, double *sums, cudaStream_t st)
+static int launch_lrb_bwd_reduce(const float *dz, const float *y, long long R, const int *rows_dev, double *sums, cudaStream_t st)
 {
     SN2_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * CO, st), "lrb_bwd_reduce memset");
     const long long ntiles = (R + LRB_T - 1) / LRB_T;
     const int grid = (int)min(ntiles, (long long)148 * 2);
-    lrb_bwd_reduce_kernel<CO><<<grid, LRB_T, 0, st>>>(dz, y, R, sums);
+    lrb_bwd_reduce_kernel<CO><<<grid, LRB_T, 0, st>>>(dz, y, R, rows_dev, sums);
     SN2_LAUNCH_CHECK("lrb_bwd_reduce_kernel");
     return SN2_OK;
 }
 
 template <int CI, int CO>
 static int launch_lrb_bwd(const float *dz, const float *y, const float *x, const float *W, const float *ss, const double *sums,
-                          const double *stats, long long R, float *dx, float *partial, int nblk, float *dW, float *db,
-                          cudaStream_t st)
+                          const double *stats, long long R, const int *rows_dev, float *dx, float *partial, int nblk, float *dW,
+                          float *db, cudaStream_t st)
 {
     using L = LrbBwd<CI, CO>;
     auto kern = lrb_bwd_kernel<CI, CO>;
     SN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM), "lrb_bwd attr");
-    kern<<<nblk, L::TR, L::SMEM, st>>>(dz, y, x, W, ss, sums, stats, R, dx, partial);
+    kern<<<nblk, L::TR, L::SMEM, st>>>(dz, y, x, W, ss, sums, stats, R, rows_dev, dx, partial);
     SN2_LAUNCH_CHECK("lrb_bwd_kernel");
-    lrb_wgrad_reduce_kernel<<<(L::NP + 255) / 256, 256, 0, st>>>(partial, nblk, CO, CI, dW, db);
+    lrb_wgrad_reduce_kernel<<<(L::NP * 32 + 255) / 256, 256, 0, st>>>(partial, nblk, CO, CI, dW, db);
     SN2_LAUNCH_CHECK("lrb_wgrad_reduce_kernel");
     return SN2_OK;
 }
@@ -425,11 +442,11 @@ extern "C" int sn2_lrb_supported(int Co, int Ci)
     return 0;
 }
 
-extern "C" int sn2_lrb_fwd(const float *x, const float *W, const float *b, long long R, int Co, int Ci, float *y,
-                           double *stats, void *stream)
+extern "C" int sn2_lrb_fwd(const float *x, const float *W, const float *b, long long R, const int *rows_dev, int Co, int Ci,
+                           float *y, double *stats, void *stream)
 {
     if (!x || !W || !b || !y || !stats || R <= 0) return SN2_EINVAL;
-#define X(ci, co) if (Ci == ci && Co == co) return sn2::launch_lrb_fwd<ci, co>(x, W, b, R, y, stats, (cudaStream_t)stream);
+#define X(ci, co) if (Ci == ci && Co == co) return sn2::launch_lrb_fwd<ci, co>(x, W, b, R, rows_dev, y, stats, (cudaStream_t)stream);
     SN2_LRB_SHAPES(X)
 #undef X
     return SN2_EUNSUPPORTED;
@@ -446,24 +463,25 @@ extern "C" int sn2_bn_finalize(const double *stats, const float *gamma, const fl
     return SN2_OK;
 }
 
-extern "C" int sn2_bn_apply(const float *y, const float *ss, long long R, int Co, float *z, void *stream)
+extern "C" int sn2_bn_apply(const float *y, const float *ss, long long R, const int *rows_dev, int Co, float *z, void *stream)
 {
     if (!y || !ss || !z || R <= 0 || Co <= 0 || (Co & 1)) return SN2_EINVAL;
     const long long n2 = R * Co / 2;
     const int grid = (int)((n2 + 255) / 256 < 148 * 8 ? (n2 + 255) / 256 : 148 * 8);
-    sn2::bn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(y), ss, n2, Co,
+    sn2::bn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(y), ss, R, rows_dev, Co,
                                                                reinterpret_cast<float2 *>(z));
     SN2_LAUNCH_CHECK("bn_apply_kernel");
     return SN2_OK;
 }
 
-extern "C" int sn2_lrb_bwd_reduce(const float *dz, const float *y, long long R, int Co, double *sums, void *stream)
+extern "C" int sn2_lrb_bwd_reduce(const float *dz, const float *y, long long R, const int *rows_dev, int Co, double *sums,
+                                  void *stream)
 {
     if (!dz || !y || !sums || R <= 0) return SN2_EINVAL;
     switch (Co) {
-    case 16: return sn2::launch_lrb_bwd_reduce<16>(dz, y, R, sums, (cudaStream_t)stream);
-    case 32: return sn2::launch_lrb_bwd_reduce<32>(dz, y, R, sums, (cudaStream_t)stream);
-    case 34: return sn2::launch_lrb_bwd_reduce<34>(dz, y, R, sums, (cudaStream_t)stream);
+    case 16: return sn2::launch_lrb_bwd_reduce<16>(dz, y, R, rows_dev, sums, (cudaStream_t)stream);
+    case 32: return sn2::launch_lrb_bwd_reduce<32>(dz, y, R, rows_dev, sums, (cudaStream_t)stream);
+    case 34: return sn2::launch_lrb_bwd_reduce<34>(dz, y, R, rows_dev, sums, (cudaStream_t)stream);
     default: return SN2_EUNSUPPORTED;
     }
 }
@@ -477,13 +495,13 @@ extern "C" int sn2_bn_param_grad(const double *sums, const float *ss, int Co, fl
 }
 
 extern "C" int sn2_lrb_bwd(const float *dz, const float *y, const float *x, const float *W, const float *ss,
-                           const double *sums, const double *stats, long long R, int Co, int Ci, float *dx, float *partial,
-                           int nblk, float *dW, float *db, void *stream)
+                           const double *sums, const double *stats, long long R, const int *rows_dev, int Co, int Ci, float *dx,
+                           float *partial, int nblk, float *dW, float *db, void *stream)
 {
     if (!dz || !y || !x || !W || !ss || !sums || !stats || !partial || !dW || !db || R <= 0 || nblk <= 0) return SN2_EINVAL;
 #define X(ci, co)                  \
     if (Ci == ci && Co == co)      \
-        return sn2::launch_lrb_bwd<ci, co>(dz, y, x, W, ss, sums, stats, R, dx, partial, nblk, dW, db, (cudaStream_t)stream);
+        return sn2::launch_lrb_bwd<ci, co>(dz, y, x, W, ss, sums, stats, R, rows_dev, dx, partial, nblk, dW, db, (cudaStream_t)stream);
     SN2_LRB_SHAPES(X)
 #undef X
     return SN2_EUNSUPPORTED;
@@ -493,20 +511,21 @@ extern "C" int sn2_lrb_bwd(const float *dz, const float *y, const float *x, cons
 // block's BatchNorm is not a SyncBatchNorm.
 extern "C" int sn2_lrb_block_fwd(const float *x, const float *W, const float *b, const float *gamma, const float *beta,
                                  float eps, float momentum, float *running_mean, float *running_var,
-                                 long long *num_batches_tracked, long long R, int Co, int Ci, float *y, double *stats,
-                                 float *ss, float *z, void *stream)
+                                 long long *num_batches_tracked, long long R, const int *rows_dev, int Co, int Ci, float *y,
+                                 double *stats, float *ss, float *z, void *stream)
 {
-    if (int rc = sn2_lrb_fwd(x, W, b, R, Co, Ci, y, stats, stream)) return rc;
+    if (int rc = sn2_lrb_fwd(x, W, b, R, rows_dev, Co, Ci, y, stats, stream)) return rc;
     if (int rc = sn2_bn_finalize(stats, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked, ss, Co, stream))
         return rc;
-    return sn2_bn_apply(y, ss, R, Co, z, stream);
+    return sn2_bn_apply(y, ss, R, rows_dev, Co, z, stream);
 }
 
 extern "C" int sn2_lrb_block_bwd(const float *dz, const float *y, const float *x, const float *W, const float *ss,
-                                 const double *stats, long long R, int Co, int Ci, double *sums, float *dgamma,
-                                 float *dbeta, float *dx, float *partial, int nblk, float *dW, float *db, void *stream)
+                                 const double *stats, long long R, const int *rows_dev, int Co, int Ci, double *sums,
+                                 float *dgamma, float *dbeta, float *dx, float *partial, int nblk, float *dW, float *db,
+                                 void *stream)
 {
-    if (int rc = sn2_lrb_bwd_reduce(dz, y, R, Co, sums, stream)) return rc;
+    if (int rc = sn2_lrb_bwd_reduce(dz, y, R, rows_dev, Co, sums, stream)) return rc;
     if (int rc = sn2_bn_param_grad(sums, ss, Co, dgamma, dbeta, stream)) return rc;
-    return sn2_lrb_bwd(dz, y, x, W, ss, sums, stats, R, Co, Ci, dx, partial, nblk, dW, db, stream);
+    return sn2_lrb_bwd(dz, y, x, W, ss, sums, stats, R, rows_dev, Co, Ci, dx, partial, nblk, dW, db, stream);
 }

@@ -38,9 +38,10 @@ edge_msg_fwd_kernel(const float *__restrict__ x, const float4 *__restrict__ pos,
 
 // dx[col[e]] += dmsg[e][0:C]   (positions are inputs: no gradient)
 __global__ void __launch_bounds__(256)
-edge_msg_bwd_kernel(const float *__restrict__ dmsg, const int *__restrict__ col, long long E, int C,
-                    float *__restrict__ dx)
+edge_msg_bwd_kernel(const float *__restrict__ dmsg, const int *__restrict__ col, long long E,
+                    const int *__restrict__ rows_dev, int C, float *__restrict__ dx)
 {
+    if (rows_dev) E = min(E, (long long)__ldg(rows_dev));
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= E * C) return;
     const long long e = t / C;
@@ -219,11 +220,12 @@ extern "C" int sn2_edge_msg_fwd(const float *x, const float *pos4, const float *
     return SN2_OK;
 }
 
-extern "C" int sn2_edge_msg_bwd(const float *dmsg, const int *col, long long E, int C, float *dx, void *stream)
+extern "C" int sn2_edge_msg_bwd(const float *dmsg, const int *col, long long E, const int *rows_dev, int C, float *dx,
+                                void *stream)
 {
     if (!dmsg || !col || !dx || E < 0 || C <= 0) return SN2_EINVAL;
     if (E == 0) return SN2_OK;
-    edge_msg_bwd_kernel<<<blocks_for(E * C, 256), 256, 0, (cudaStream_t)stream>>>(dmsg, col, E, C, dx);
+    edge_msg_bwd_kernel<<<blocks_for(E * C, 256), 256, 0, (cudaStream_t)stream>>>(dmsg, col, E, rows_dev, C, dx);
     SN2_LAUNCH_CHECK("edge_msg_bwd_kernel");
     return SN2_OK;
 }
@@ -338,18 +340,23 @@ linear_wgrad_kernel(const float *__restrict__ dy, const float *__restrict__ x, l
     }
 }
 
+// one warp per output element, lanes stride over the CTA partials, xor-shuffle tree (fixed order)
 __global__ void __launch_bounds__(256)
 linear_wgrad_reduce_kernel(const float *__restrict__ partial, int nblk, int Co, int CI, float *__restrict__ dW,
                            float *__restrict__ db)
 {
     const int n = Co * (CI + 1);
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (t >= n) return;
     float s = 0.f;
-    for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * n + t];
-    const int o = t / (CI + 1), i = t - o * (CI + 1);
-    if (i < CI) dW[o * CI + i] = s;
-    else db[o] = s;
+    for (int b = lane; b < nblk; b += 32) s += __ldg(partial + (size_t)b * n + t);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(SN2_FULL, s, d);
+    if (lane == 0) {
+        const int o = t / (CI + 1), i = t - o * (CI + 1);
+        if (i < CI) dW[o * CI + i] = s;
+        else db[o] = s;
+    }
 }
 
 template <int CI>
@@ -363,7 +370,7 @@ static int launch_wgrad(const float *dy, const float *x, long long E, int Co, fl
     kern<<<nblk, WG_THREADS, smem, st>>>(dy, x, E, Co, partial);
     SN2_LAUNCH_CHECK("linear_wgrad_kernel");
     const int n = Co * (CI + 1);
-    linear_wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(partial, nblk, Co, CI, dW, db);
+    linear_wgrad_reduce_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(partial, nblk, Co, CI, dW, db);
     SN2_LAUNCH_CHECK("linear_wgrad_reduce_kernel");
     return SN2_OK;
 }

@@ -22,7 +22,8 @@ class EdgeMsg(torch.autograd.Function):
     """msg[e] = [x[col[e]], pos[col[e]] - qpos[row(e)]]  (PointConv.message)."""
 
     @staticmethod
-    def forward(ctx, x, pos4, qpos4, rowptr, col):
+    def forward(ctx, x, pos4, qpos4, rowptr, col, rows=None):
+        """rows: optional device int32 [1] = live edge count when `col` is a fixed-capacity buffer (graph replay)."""
         lib = _lib.load()
         x = _c(x)
         E, C = col.numel(), x.shape[1]
@@ -31,21 +32,22 @@ class EdgeMsg(torch.autograd.Function):
                                    dptr(col, torch.int32), qpos4.shape[0], C, dptr(msg), stream_ptr()), "sn2_edge_msg_fwd")
         ops._count(1)
         ctx.save_for_backward(col)
+        ctx.rows = rows
         ctx.shape = (x.shape[0], C)
         return msg
 
     @staticmethod
     def backward(ctx, dmsg):
         if not ctx.needs_input_grad[0]:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         lib = _lib.load()
         (col,) = ctx.saved_tensors
         P, C = ctx.shape
         dx = torch.zeros((P, C), dtype=torch.float32, device=dmsg.device)
-        check(lib.sn2_edge_msg_bwd(dptr(_c(dmsg), torch.float32), dptr(col), col.numel(), C, dptr(dx), stream_ptr()),
-              "sn2_edge_msg_bwd")
+        check(lib.sn2_edge_msg_bwd(dptr(_c(dmsg), torch.float32), dptr(col), col.numel(), dptr(ctx.rows), C, dptr(dx),
+                                   stream_ptr()), "sn2_edge_msg_bwd")
         ops._count(1)
-        return dx, None, None, None, None
+        return dx, None, None, None, None, None
 
 
 class SegmentMax(torch.autograd.Function):
@@ -192,9 +194,10 @@ class LinReluBN(torch.autograd.Function):
     NBLK = 148 * 2
 
     @staticmethod
-    def forward(ctx, x, weight, bias, gamma, beta, bn):
+    def forward(ctx, x, weight, bias, gamma, beta, bn, rows=None):
         lib = _lib.load()
         x = _c(x)
+        rp = dptr(rows, torch.int32)
         R, (Co, Ci) = x.shape[0], weight.shape
         dev = x.device
         y = torch.empty((R, Co), dtype=torch.float32, device=dev)
@@ -210,16 +213,16 @@ class LinReluBN(torch.autograd.Function):
         group = _sync_group(bn)
         if group is None:
             check(lib.sn2_lrb_block_fwd(dptr(x, torch.float32), wp, bp, gp, btp, float(bn.eps), float(bn.momentum), rm, rv, nbt,
-                                        R, Co, Ci, dptr(y), dptr(stats), dptr(ss), dptr(z), st), "sn2_lrb_block_fwd")
+                                        R, rp, Co, Ci, dptr(y), dptr(stats), dptr(ss), dptr(z), st), "sn2_lrb_block_fwd")
         else:
-            check(lib.sn2_lrb_fwd(dptr(x, torch.float32), wp, bp, R, Co, Ci, dptr(y), dptr(stats), st), "sn2_lrb_fwd")
+            check(lib.sn2_lrb_fwd(dptr(x, torch.float32), wp, bp, R, rp, Co, Ci, dptr(y), dptr(stats), st), "sn2_lrb_fwd")
             torch.distributed.all_reduce(stats, group=group)
             check(lib.sn2_bn_finalize(dptr(stats), gp, btp, float(bn.eps), float(bn.momentum), rm, rv, nbt, dptr(ss), Co, st),
                   "sn2_bn_finalize")
-            check(lib.sn2_bn_apply(dptr(y), dptr(ss), R, Co, dptr(z), st), "sn2_bn_apply")
+            check(lib.sn2_bn_apply(dptr(y), dptr(ss), R, rp, Co, dptr(z), st), "sn2_bn_apply")
         ops._count(5)
         ctx.save_for_backward(x, y, weight, ss, stats)
-        ctx.group = group
+        ctx.group, ctx.rows = group, rows
         return z
 
     @staticmethod
@@ -235,20 +238,20 @@ class LinReluBN(torch.autograd.Function):
         dW = torch.empty_like(weight)
         db = torch.empty(Co, dtype=torch.float32, device=dev)
         partial = torch.empty((LinReluBN.NBLK, Co * (Ci + 1)), dtype=torch.float32, device=dev)
-        wp, st = dptr(_c(weight), torch.float32), stream_ptr()
+        wp, st, rp = dptr(_c(weight), torch.float32), stream_ptr(), dptr(ctx.rows, torch.int32)
         dgp, dbp = ctypes.c_void_p(dgb.data_ptr()), ctypes.c_void_p(dgb.data_ptr() + 4 * Co)
         if ctx.group is None:
-            check(lib.sn2_lrb_block_bwd(dptr(dz, torch.float32), dptr(y), dptr(x), wp, dptr(ss), dptr(stats), R, Co, Ci, dptr(sums),
+            check(lib.sn2_lrb_block_bwd(dptr(dz, torch.float32), dptr(y), dptr(x), wp, dptr(ss), dptr(stats), R, rp, Co, Ci, dptr(sums),
                                         dgp, dbp, dptr(dx), dptr(partial), LinReluBN.NBLK, dptr(dW), dptr(db), st),
                   "sn2_lrb_block_bwd")
         else:
-            check(lib.sn2_lrb_bwd_reduce(dptr(dz, torch.float32), dptr(y), R, Co, dptr(sums), st), "sn2_lrb_bwd_reduce")
+            check(lib.sn2_lrb_bwd_reduce(dptr(dz, torch.float32), dptr(y), R, rp, Co, dptr(sums), st), "sn2_lrb_bwd_reduce")
             check(lib.sn2_bn_param_grad(dptr(sums), dptr(ss), Co, dgp, dbp, st), "sn2_bn_param_grad")  # this rank's sums
             torch.distributed.all_reduce(sums, group=ctx.group)
-            check(lib.sn2_lrb_bwd(dptr(dz), dptr(y), dptr(x), wp, dptr(ss), dptr(sums), dptr(stats), R, Co, Ci, dptr(dx),
+            check(lib.sn2_lrb_bwd(dptr(dz), dptr(y), dptr(x), wp, dptr(ss), dptr(sums), dptr(stats), R, rp, Co, Ci, dptr(dx),
                                   dptr(partial), LinReluBN.NBLK, dptr(dW), dptr(db), st), "sn2_lrb_bwd")
         ops._count(5)
-        return dx, dW, db, dgb[0], dgb[1], None
+        return dx, dW, db, dgb[0], dgb[1], None, None
 
 
 def _sync_group(bn):
@@ -281,9 +284,10 @@ def tall_linear(lin, x):
     return lin(x)
 
 
-def run_mlp(seq, x):
+def run_mlp(seq, x, rows=None):
     """Apply a reference MLP (Sequential of (Linear, ReLU, BatchNorm1d) blocks).  Blocks that see >= 65 536 rows in
-    training run as the fused LinReluBN (SN2_FUSED_MLP=0 -> the torch modules, with TallLinear where it pays)."""
+    training run as the fused LinReluBN (SN2_FUSED_MLP=0 -> the torch modules, with TallLinear where it pays).
+    rows: device int32 [1] live row count when x is a fixed-capacity buffer (graph replay); needs the fused blocks."""
     lib = _lib.load()
     import os
     fused = os.environ.get("SN2_FUSED_MLP", "1") == "1"
@@ -292,8 +296,10 @@ def run_mlp(seq, x):
         lin = block[0]
         if fused and x.shape[0] >= 65536 and _fusable_block(lib, block, x):
             bn = block[2]
-            x = LinReluBN.apply(x, lin.weight, lin.bias, bn.weight, bn.bias, bn)
+            x = LinReluBN.apply(x, lin.weight, lin.bias, bn.weight, bn.bias, bn, rows)
             continue
+        if rows is not None:
+            raise RuntimeError("sn2: a fixed-capacity edge buffer needs the fused Linear-ReLU-BatchNorm blocks")
         if tall and x.shape[0] >= 65536 and (x.requires_grad or lin.weight.requires_grad) and lib.sn2_linear_wgrad_supported(
                 lin.out_features, lin.in_features):
             x = TallLinear.apply(x, lin.weight, lin.bias)

@@ -618,6 +618,58 @@ def test_structure_prefetcher_matches_plain_loop(cuda_device):
         torch.testing.assert_close(v2, v, rtol=1e-5, atol=1e-6, msg=lambda m, k=k: f"{k}: {m}")
 
 
+def test_graphed_train_step_matches_eager_loop(cuda_device):
+    """GraphedTrainStep (whole step in one CUDA graph, edge lists at fixed capacity with device-side counts) against
+    the eager loop: same losses and same parameters after four optimizer steps on batches with different edge
+    counts, including one that overflows the capacity and forces a re-capture."""
+    import copy
+
+    from model.project_to_2d import project_to_plotwise_coverages
+    from sn2.pipeline import GraphedTrainStep, StructurePrefetcher
+
+    N = 8192
+    args, net, _ = _make_models(N, cuda_device)
+    net.train()
+    net.drop = 0.0  # dropout draws differ between the two runs; everything else is deterministic up to atomics
+    net2 = copy.deepcopy(net)
+    batches = []
+    for i, v in enumerate(("cm", "plain", "cm", "plain")):
+        b = _plots(3, 9, N, v)
+        if i == 2:  # denser cloud -> more edges than the capacity captured on batch 0
+            b["xyz"] = b["xyz"] * 0.85
+        g = torch.Generator().manual_seed(i)
+        b["gt"] = torch.rand(9, 4, generator=g)
+        batches.append(b)
+
+    def make_step(model, opt):
+        def step(batch):
+            opt.zero_grad(set_to_none=False)
+            cov, proba = model(batch)
+            pw = project_to_plotwise_coverages(cov, model.last_cloud_device, args)
+            loss = ((pw - batch["gt"].to(pw.device)) ** 2).mean() + 0.01 * (proba ** 2).mean()
+            loss.backward()
+            opt.step()
+            return loss.detach()
+        return step
+
+    def adam(model):
+        for p in model.parameters():
+            p.grad = torch.zeros_like(p)
+        return torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
+
+    step1 = make_step(net, adam(net))
+    eager = [float(step1(b)) for b in batches]
+    opt2 = adam(net2)
+    gstep = GraphedTrainStep(net2, make_step(net2, opt2), optimizer=opt2, capacity_factor=1.02)
+    graphed = [float(gstep(b)) for b in StructurePrefetcher(net2, batches)]
+    assert gstep.captures == 2, gstep.captures
+    torch.testing.assert_close(torch.tensor(graphed), torch.tensor(eager), rtol=2e-4, atol=1e-6)
+    # Adam's normalised update turns the ~1e-7 atomics noise of near-zero gradients into O(lr) differences on a
+    # handful of weights: parameters are compared at a fraction of the 4 * lr = 4e-3 they could have moved
+    for (k, v), (_, v2) in zip(net.state_dict().items(), net2.state_dict().items()):
+        torch.testing.assert_close(v2, v, rtol=2e-3, atol=4e-4, msg=lambda m, k=k: f"{k}: {m}")
+
+
 def _golden_paths():
     import glob
     import os
