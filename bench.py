@@ -64,6 +64,8 @@ class ClockSampler:
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
+        if os.environ.get("SN2_NO_CLOCK_SAMPLER") == "1":  # debugging aid: is the sampler itself perturbing the run?
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -314,7 +316,12 @@ def run_train(opts, cfg):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
+        trace = os.environ.get("SN2_BENCH_TRACE") == "1"
+        t_prev, host_ms = time.perf_counter(), []
         for batch in StructurePrefetcher(net, (src for _ in range(steps)), dev):
+            if trace:
+                host_ms.append(round((time.perf_counter() - t_prev) * 1e3, 2))
+                t_prev = time.perf_counter()
             flush.fill_(1)
             if gstep is not None:  # whole step = input copies into the static buffers + one graph launch
                 loss = gstep(batch)
@@ -324,22 +331,29 @@ def run_train(opts, cfg):
                 step(batch, None, read_loss)
         b.record()
         barrier()
+        if trace and rank == 0:
+            print(f"[trace] host ms between steps ({'host' if src is host else 'resident'} inputs): {host_ms}", file=sys.stderr)
         return a.elapsed_time(b)
 
-    for _ in range(W):
-        step(dev_in)
-        step(host, read_loss=True)
-    timed_prefetch(dev_in, W, False)
+    # W untimed steps of EACH mode right before it is timed: graph capture empties the caching allocator
+    # (torch.cuda.graph calls empty_cache), so the first eager steps after it pay their cudaMallocs again
+    timed_prefetch(dev_in, W, False)   # captures the graph (single GPU)
     sampler = ClockSampler(local)
     sampler.start()
     timer = StageTimer()
+    for _ in range(W):
+        step(dev_in)
     ms_serial = timed(lambda: step(dev_in, timer), opts.steps)
+    for _ in range(W):
+        step(host, read_loss=True)
     ms_serial_e2e = timed(lambda: step(host, None, True), opts.steps)
+    timed_prefetch(dev_in, W, False)
     l0, r0 = ops.LAUNCHES, (gstep.replays if gstep is not None else 0)
     ms_res = timed_prefetch(dev_in, opts.steps, False)
     launches = ops.LAUNCHES - l0  # structural stage (launched live) ...
     if gstep is not None:        # ... + our kernels inside each graph replay (counted at capture)
         launches += (gstep.replays - r0) * gstep.launches_per_replay
+    timed_prefetch(host, W, True)
     ms_e2e = timed_prefetch(host, opts.steps, True)
     clocks = sampler.stop()
     t = torch.tensor([ms_res, ms_e2e, ms_serial, ms_serial_e2e], dtype=torch.float64, device=dev)

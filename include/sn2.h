@@ -212,7 +212,8 @@ int sn2_linear_wgrad(const float *dy, const float *x, long long E, int Co, int C
  * sequence addmm / relu / batch_norm forward and their three backward nodes.  Supported (Ci, Co): (11,16) (16,16)
  * (19,32) (80,34) (42,34).  All pointers are device pointers.
  *   sn2_lrb_fwd        y [R,Co] = relu(x W^T + b); stats [2*Co+1] fp64 = {sum y, sum y^2, rows} (zeroed here);
- *                      rows = R, or min(R, *rows_dev) when rows_dev is given.
+ *                      rows = R, or min(R, *rows_dev) when rows_dev is given.  x must be 16-byte aligned (its row
+ *                      tiles are fetched with TMA bulk copies).
  *                      For SyncBatchNorm the caller all-reduces stats across ranks before sn2_bn_finalize.
  *   sn2_bn_finalize    stats -> ss [4*Co] = {scale, shift, mean, invstd} (biased variance, eps); running_mean /
  *                      running_var (nullable) updated with `momentum` and the unbiased variance like torch;

@@ -44,6 +44,23 @@ __device__ __forceinline__ void load_row(const float *__restrict__ p, float (&v)
     }
 }
 template <int CO>
+__device__ __forceinline__ void load_row_s(const float *p, float (&v)[CO])  // from shared memory
+{
+    if constexpr (CO % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < CO / 4; ++i) {
+            const float4 t = reinterpret_cast<const float4 *>(p)[i];
+            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < CO / 2; ++i) {
+            const float2 t = reinterpret_cast<const float2 *>(p)[i];
+            v[2 * i] = t.x; v[2 * i + 1] = t.y;
+        }
+    }
+}
+template <int CO>
 __device__ __forceinline__ void store_row(float *__restrict__ p, const float (&v)[CO])
 {
     if constexpr (CO % 4 == 0) {
@@ -76,17 +93,51 @@ __device__ __forceinline__ void cta_channel_sums(const float (&a)[CO], const flo
 // ---------------------------------------------------------------------------------------------------------------
 // forward: y = relu(x W^T + b), stats[0..CO) += sum y, stats[CO..2CO) += sum y^2
 // ---------------------------------------------------------------------------------------------------------------
+// ---- TMA bulk copy + mbarrier helpers (1-D cp.async.bulk: contiguous global bytes -> shared memory) -------------
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(count));
+}
+// one arrival that also arms the barrier phase with the bytes the following bulk copies will deliver
+__device__ __forceinline__ void mbar_expect(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+// bulk copy global -> shared; its bytes count towards the phase of `bar`
+__device__ __forceinline__ void tma_copy_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    mbar_expect(bar, bytes);
+    tma_copy_1d(dst, src, bytes, bar);
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+
 template <int CI, int CO>
 struct LrbFwd {
     static constexpr int WARPS = LRB_T / 32;
     static constexpr int COP = (CO + 3) & ~3;
-    static constexpr int XS = (CI & 1) ? CI : CI + 1;  // odd row stride: conflict-free row-per-thread reads
-    static constexpr size_t SMEM = sizeof(double) * 2 * CO + sizeof(float) * ((size_t)CI * COP + COP + (size_t)LRB_T * XS);
+    static constexpr int STAGES = CI > 48 ? 2 : 3;      // 32-row slabs in flight per warp
+    static constexpr int SLAB = 32 * CI;                 // floats; 128 * CI bytes: a multiple of 16 for any CI
+    static constexpr size_t SMEM = sizeof(double) * 2 * CO + sizeof(float) * ((size_t)CI * COP + COP + (size_t)WARPS * STAGES * SLAB) +
+                                   sizeof(unsigned long long) * WARPS * STAGES;
 };
 
-// Every warp owns 32-row tiles: it copies the tile's 32 * CI contiguous floats into its private shared-memory slab
-// (coalesced), then each lane runs the layer on its row.  No CTA barrier inside the loop, so the warps of an SM
-// drift apart and the loads of some overlap the FMAs of others.
+// Every warp owns 32-row tiles.  A tile's 32 * CI floats are contiguous in global memory: lane 0 fetches them with
+// one TMA bulk copy into a slab of the warp's private ring, STAGES tiles ahead of the one being computed, and an
+// mbarrier per slab tells the warp when the bytes have landed.  No CTA barrier inside the loop and no register
+// staging: the loads of the next tiles are in flight while each lane runs the layer on its row.
 template <int CI, int CO>
 __global__ void __launch_bounds__(LRB_T, (CO > 16 ? 1 : 2))
 lrb_fwd_kernel(const float *__restrict__ x, const float *__restrict__ W, const float *__restrict__ b, long long R,
@@ -94,52 +145,83 @@ lrb_fwd_kernel(const float *__restrict__ x, const float *__restrict__ W, const f
 {
     if (rows_dev) R = min(R, (long long)__ldg(rows_dev));
     using L = LrbFwd<CI, CO>;
-    constexpr int COP = L::COP, XS = L::XS;
+    constexpr int COP = L::COP, STAGES = L::STAGES, SLAB = L::SLAB;
     extern __shared__ __align__(16) unsigned char lrb_smem[];
     double *red = reinterpret_cast<double *>(lrb_smem);
     float *Wt = reinterpret_cast<float *>(red + 2 * CO);  // [CI][COP]: Wt[k][o] = W[o][k]
     float *bS = Wt + CI * COP;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float *xS = bS + COP + warp * (32 * XS);              // this warp's [32][XS] slab
+    float *ring = bS + COP + warp * (STAGES * SLAB);      // this warp's STAGES slabs of [32][CI]
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(bS + COP + L::WARPS * STAGES * SLAB) + warp * STAGES;
     for (int e = tid; e < CI * COP; e += LRB_T) {
         const int k = e / COP, o = e - k * COP;
         Wt[e] = o < CO ? __ldg(W + o * CI + k) : 0.f;
     }
     for (int o = tid; o < COP; o += LRB_T) bS[o] = o < CO ? __ldg(b + o) : 0.f;
     for (int o = tid; o < 2 * CO; o += LRB_T) red[o] = 0.0;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(bars + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
     __syncthreads();
     float s1[CO], s2[CO];
 #pragma unroll
     for (int o = 0; o < CO; ++o) s1[o] = s2[o] = 0.f;
-    const long long ntiles = (R + 31) / 32;
-    for (long long tile = (long long)blockIdx.x * L::WARPS + warp; tile < ntiles; tile += (long long)gridDim.x * L::WARPS) {
-        const long long base = tile * 32;
-        const int rows = (int)min(32LL, R - base);
-        const float *xt = x + base * CI;
-        __syncwarp();
+    const long long ntiles = (R + 31) / 32, nfull = R / 32;
+    const long long tile0 = (long long)blockIdx.x * L::WARPS + warp, stride = (long long)gridDim.x * L::WARPS;
+    if (lane == 0) {
 #pragma unroll
-        for (int j = 0; j < CI; ++j) {
-            const int e = j * 32 + lane;  // element e of the tile = (row e / CI, column e % CI)
-            if (e < rows * CI) {
-                const int r = e / CI, k = e - r * CI;
-                xS[r * XS + k] = __ldg(xt + e);
-            }
+        for (int s = 0; s < STAGES; ++s) {
+            const long long t = tile0 + s * stride;
+            if (t < nfull) tma_load_1d(ring + s * SLAB, x + t * SLAB, SLAB * 4, bars + s);
         }
-        __syncwarp();
+    }
+    int stage = 0;
+    unsigned parity = 0;
+    for (long long tile = tile0; tile < ntiles; tile += stride) {
+        const long long base = tile * 32;
+        const float *xS = ring + stage * SLAB;
+        int rows = 32;
+        if (tile < nfull) {
+            mbar_wait(bars + stage, parity);
+        } else {  // the ragged last tile of the array: its byte count need not be a multiple of 16 -> plain loads
+            rows = (int)(R - base);
+            float *dst = ring + stage * SLAB;
+            for (int e = lane; e < rows * CI; e += 32) dst[e] = __ldg(x + base * CI + e);
+            __syncwarp();
+        }
         if (lane < rows) {
             float acc[COP];
 #pragma unroll
             for (int o = 0; o < COP; ++o) acc[o] = bS[o];
+            // dense [32][CI] slab: rows of even width are read as float4 / float2 (a scalar read at stride CI = 16
+            // would be a 16-way bank conflict), odd widths are conflict-free as they are
+            constexpr int V = (CI % 4 == 0) ? 4 : ((CI % 2 == 0) ? 2 : 1);
 #pragma unroll
-            for (int k = 0; k < CI; ++k) {
-                const float xk = xS[lane * XS + k];
+            for (int kv = 0; kv < CI / V; ++kv) {
+                float xv[V];
+                if constexpr (V == 4) {
+                    const float4 t = *reinterpret_cast<const float4 *>(xS + lane * CI + 4 * kv);
+                    xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+                } else if constexpr (V == 2) {
+                    const float2 t = *reinterpret_cast<const float2 *>(xS + lane * CI + 2 * kv);
+                    xv[0] = t.x; xv[1] = t.y;
+                } else {
+                    xv[0] = xS[lane * CI + kv];
+                }
 #pragma unroll
-                for (int o4 = 0; o4 < COP / 4; ++o4) {
-                    const float4 w = *reinterpret_cast<const float4 *>(Wt + k * COP + 4 * o4);
-                    acc[4 * o4] = fmaf(xk, w.x, acc[4 * o4]);
-                    acc[4 * o4 + 1] = fmaf(xk, w.y, acc[4 * o4 + 1]);
-                    acc[4 * o4 + 2] = fmaf(xk, w.z, acc[4 * o4 + 2]);
-                    acc[4 * o4 + 3] = fmaf(xk, w.w, acc[4 * o4 + 3]);
+                for (int j = 0; j < V; ++j) {
+                    const float xk = xv[j];
+                    const int k = kv * V + j;
+#pragma unroll
+                    for (int o4 = 0; o4 < COP / 4; ++o4) {
+                        const float4 w = *reinterpret_cast<const float4 *>(Wt + k * COP + 4 * o4);
+                        acc[4 * o4] = fmaf(xk, w.x, acc[4 * o4]);
+                        acc[4 * o4 + 1] = fmaf(xk, w.y, acc[4 * o4 + 1]);
+                        acc[4 * o4 + 2] = fmaf(xk, w.z, acc[4 * o4 + 2]);
+                        acc[4 * o4 + 3] = fmaf(xk, w.w, acc[4 * o4 + 3]);
+                    }
                 }
             }
             float out[CO];
@@ -150,6 +232,13 @@ lrb_fwd_kernel(const float *__restrict__ x, const float *__restrict__ W, const f
                 s2[o] = fmaf(out[o], out[o], s2[o]);
             }
             store_row<CO>(y + (base + lane) * CO, out);
+        }
+        __syncwarp();  // every lane has read its row: the slab can be refilled
+        const long long nt = tile + STAGES * stride;
+        if (lane == 0 && nt < nfull) tma_load_1d(ring + stage * SLAB, x + nt * SLAB, SLAB * 4, bars + stage);
+        if (++stage == STAGES) {
+            stage = 0;
+            parity ^= 1u;
         }
     }
     __syncwarp();
@@ -247,19 +336,30 @@ lrb_bwd_reduce_kernel(const float *__restrict__ dz, const float *__restrict__ y,
 //   dy = [y > 0] * gamma * invstd * (dz - mean(dz) - yhat * mean(dz * yhat))      (BatchNorm, then ReLU)
 //   dx = dy W;   dW[o][:] += dy[o] * x;   db[o] += dy[o]
 // sums are the (all-reduced) raw sums of pass 1, count the (global) row count in stats[2*CO].
+//
+// 128-row tiles.  The three input tiles (x, dz, y: contiguous row blocks) arrive by TMA bulk copies into a two-stage
+// ring, one tile ahead of the compute; dx leaves through shared memory with a TMA bulk store.  Phase 1: thread =
+// row (dy to shared memory, dx).  Phase 2: thread = (row group g, input column i): dW[:, i] += dy[r][:] * x[r][i]
+// over the rows r = g, g + G, ... of the tile, with column i = CI standing for the bias (x = 1); x is read dense
+// (consecutive i: conflict-free), dy rows as broadcast float4.
 // ---------------------------------------------------------------------------------------------------------------
 template <int CI, int CO>
 struct LrbBwd {
-    static constexpr int TR = CI > 48 ? 128 : 256;  // rows per tile = threads per CTA
+    static constexpr int TR = 128;                  // rows per tile = threads per CTA
+    static constexpr int COP = (CO + 3) & ~3;
+    static constexpr int DYS = COP + 4;             // dy row stride: float4 rows, conflict-free for a quarter warp
     static constexpr int CIP = (CI + 3) & ~3;
-    static constexpr int G = TR / CO;               // row groups of the weight-gradient phase
+    static constexpr int G = TR / (CI + 1);         // row groups of the weight-gradient phase
     static constexpr int NP = CO * (CI + 1);        // floats of one partial [dW | db]
-    static constexpr int XS_FLOATS = (TR * CIP > G * NP) ? TR * CIP : G * NP;
-    static constexpr size_t SMEM = sizeof(float) * ((size_t)CO * CIP + 4 * CO + XS_FLOATS + (size_t)TR * CO + (size_t)TR * CI);
+    static constexpr int STAGE = TR * (CI + 2 * CO); // floats of one stage: x | dz | y tiles
+    static constexpr int RED = (G * NP > TR * CI) ? G * NP : TR * CI;  // dx tile, reused for the group partials at the end
+    static constexpr int MINB = (2 * STAGE + TR * DYS + RED + CO * CIP) * 4 <= 72 * 1024 ? 3 : ((2 * STAGE + TR * DYS + RED + CO * CIP) * 4 <= 110 * 1024 ? 2 : 1);
+    static constexpr size_t SMEM = sizeof(float) * ((size_t)2 * STAGE + (size_t)TR * DYS + RED + (size_t)CO * CIP + 4 * CO) + 2 * sizeof(unsigned long long);
+    static_assert(RED % 4 == 0 && SMEM <= 227 * 1024, "shared-memory layout");
 };
 
 template <int CI, int CO>
-__global__ void __launch_bounds__(LrbBwd<CI, CO>::TR, (CI > 48 ? 1 : 2))
+__global__ void __launch_bounds__(LrbBwd<CI, CO>::TR, LrbBwd<CI, CO>::MINB)
 lrb_bwd_kernel(const float *__restrict__ dz, const float *__restrict__ y, const float *__restrict__ x,
                const float *__restrict__ W, const float *__restrict__ ss, const double *__restrict__ sums,
                const double *__restrict__ stats, long long R, const int *__restrict__ rows_dev, float *__restrict__ dx,
@@ -267,21 +367,21 @@ lrb_bwd_kernel(const float *__restrict__ dz, const float *__restrict__ y, const 
 {
     if (rows_dev) R = min(R, (long long)__ldg(rows_dev));
     using L = LrbBwd<CI, CO>;
-    constexpr int TR = L::TR, CIP = L::CIP, G = L::G, NP = L::NP;
+    constexpr int TR = L::TR, COP = L::COP, DYS = L::DYS, CIP = L::CIP, G = L::G, NP = L::NP, STAGE = L::STAGE;
     extern __shared__ __align__(16) unsigned char lrb_smem[];
-    float *Ws = reinterpret_cast<float *>(lrb_smem);  // [CO][CIP] = W[o][k], zero padded
-    float *cA = Ws + CO * CIP;                        // dy = mask * (cA*dz + cB*y + cC)
+    float *ring = reinterpret_cast<float *>(lrb_smem);  // 2 x { x [TR][CI] | dz [TR][CO] | y [TR][CO] }
+    float *dyS = ring + 2 * STAGE;                        // [TR][DYS]
+    float *dxS = dyS + TR * DYS;                          // [TR][CI]  (group partials at the very end)
+    float *Ws = dxS + L::RED;                             // [CO][CIP] = W[o][k], zero padded
+    float *cA = Ws + CO * CIP;                            // dy = mask * (cA*dz + cB*y + cC)
     float *cB = cA + CO;
     float *cC = cB + CO;
-    float *xS = cC + 2 * CO;                          // [TR][CIP] (later: group partials)
-    float *dyS = xS + L::XS_FLOATS;                   // [TR][CO]
-    float *dxS = dyS + TR * CO;                       // [TR][CI]
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(cC + 2 * CO);
     const int tid = threadIdx.x;
     for (int e = tid; e < CO * CIP; e += TR) {
         const int o = e / CIP, k = e - o * CIP;
         Ws[e] = k < CI ? __ldg(W + o * CI + k) : 0.f;
     }
-    for (int e = tid; e < TR * CIP; e += TR) xS[e] = 0.f;
     if (tid < CO) {
         // dz - m1 - (y - mean) * inv * m2, m1 = S1/n, m2 = mean(dz * yhat) = inv * (S2 - mean * S1) / n, times gamma * inv
         const double n = stats[2 * CO];
@@ -294,27 +394,58 @@ lrb_bwd_kernel(const float *__restrict__ dz, const float *__restrict__ y, const 
         cB[tid] = sc * kb;
         cC[tid] = sc * (-m1 - mean * kb);
     }
-    float acc[CI + 1];
+    if (tid == 0) {
+        mbar_init(bars, 1);
+        mbar_init(bars + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const long long ntiles = (R + TR - 1) / TR, nfull = R / TR;
+    // one barrier phase per tile: three bulk copies, their byte counts add up on the same mbarrier
+    auto fetch = [&](long long tile, int st) {
+        float *dst = ring + st * STAGE;
+        mbar_expect(bars + st, STAGE * 4);
+        tma_copy_1d(dst, x + tile * TR * CI, TR * CI * 4, bars + st);
+        tma_copy_1d(dst + TR * CI, dz + tile * TR * CO, TR * CO * 4, bars + st);
+        tma_copy_1d(dst + TR * (CI + CO), y + tile * TR * CO, TR * CO * 4, bars + st);
+    };
+    if (tid == 0 && blockIdx.x < nfull) fetch(blockIdx.x, 0);
+    float acc[CO];
 #pragma unroll
-    for (int i = 0; i <= CI; ++i) acc[i] = 0.f;
-    const int g = tid / CO, o_w = tid - g * CO;
-    const long long ntiles = (R + TR - 1) / TR;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        __syncthreads();
+    for (int o = 0; o < CO; ++o) acc[o] = 0.f;
+    const int g = tid / (CI + 1), i_w = tid - g * (CI + 1);
+    int stage = 0;
+    unsigned it = 0;  // stages alternate strictly, so the phase parity of a stage is bit 1 of the iteration count
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const long long base = tile * TR;
-        const int rows = (int)min((long long)TR, R - base);
-        const float *xt = x + base * CI;
-        for (int e = tid; e < rows * CI; e += TR) {
-            const int r = e / CI, k = e - r * CI;
-            xS[r * CIP + k] = __ldg(xt + e);
+        float *xS = ring + stage * STAGE, *dzS = xS + TR * CI, *yS = dzS + TR * CO;
+        const long long nxt = tile + gridDim.x;
+        if (tid == 0 && nxt < nfull) fetch(nxt, stage ^ 1);  // its previous readers finished before the last barrier
+        int rows = TR;
+        if (tile < nfull) {
+            mbar_wait(bars + stage, (it >> 1) & 1u);
+        } else {  // ragged last tile: byte counts need not be multiples of 16 -> plain loads
+            rows = (int)(R - base);
+            for (int e = tid; e < rows * CI; e += TR) xS[e] = __ldg(x + base * CI + e);
+            for (int e = tid; e < rows * CO; e += TR) {
+                dzS[e] = __ldg(dz + base * CO + e);
+                yS[e] = __ldg(y + base * CO + e);
+            }
+            __syncthreads();
         }
+        if (tid == 0 && dx) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // previous dx tile has left dxS
+        __syncthreads();
         if (tid < rows) {
             float d[CO], v[CO];
-            load_row<CO>(dz + (base + tid) * CO, d);
-            load_row<CO>(y + (base + tid) * CO, v);
+            load_row_s<CO>(dzS + tid * CO, d);
+            load_row_s<CO>(yS + tid * CO, v);
 #pragma unroll
             for (int o = 0; o < CO; ++o) d[o] = v[o] > 0.f ? fmaf(cA[o], d[o], fmaf(cB[o], v[o], cC[o])) : 0.f;
-            store_row<CO>(dyS + tid * CO, d);
+#pragma unroll
+            for (int o4 = 0; o4 < COP / 4; ++o4)
+                *reinterpret_cast<float4 *>(dyS + tid * DYS + 4 * o4) =
+                    make_float4(d[4 * o4], 4 * o4 + 1 < CO ? d[4 * o4 + 1] : 0.f, 4 * o4 + 2 < CO ? d[4 * o4 + 2] : 0.f,
+                                4 * o4 + 3 < CO ? d[4 * o4 + 3] : 0.f);
             if (dx) {
                 float dxr[CIP];
 #pragma unroll
@@ -330,40 +461,60 @@ lrb_bwd_kernel(const float *__restrict__ dz, const float *__restrict__ y, const 
                         dxr[4 * k4 + 3] = fmaf(d[o], w.w, dxr[4 * k4 + 3]);
                     }
                 }
+                if constexpr (CI % 4 == 0) {
 #pragma unroll
-                for (int k = 0; k < CI; ++k) dxS[tid * CI + k] = dxr[k];
+                    for (int k4 = 0; k4 < CI / 4; ++k4)
+                        *reinterpret_cast<float4 *>(dxS + tid * CI + 4 * k4) = make_float4(dxr[4 * k4], dxr[4 * k4 + 1], dxr[4 * k4 + 2], dxr[4 * k4 + 3]);
+                } else if constexpr (CI % 2 == 0) {
+#pragma unroll
+                    for (int k2 = 0; k2 < CI / 2; ++k2)
+                        *reinterpret_cast<float2 *>(dxS + tid * CI + 2 * k2) = make_float2(dxr[2 * k2], dxr[2 * k2 + 1]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < CI; ++k) dxS[tid * CI + k] = dxr[k];
+                }
             }
         }
+        if (dx) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // dxS writes -> visible to the TMA store
         __syncthreads();
         if (dx) {
-            float *dxt = dx + base * CI;
-            for (int e = tid; e < rows * CI; e += TR) dxt[e] = dxS[e];
-        }
-        if (g < G) {
-            // rows r = g, g + G, ...: dyS address (r * CO + o) = (G * it) * CO + tid -> contiguous over the CTA
-            for (int r = g; r < rows; r += G) {
-                const float dv = dyS[r * CO + o_w];
-#pragma unroll
-                for (int k4 = 0; k4 < CIP / 4; ++k4) {
-                    const float4 xv = *reinterpret_cast<const float4 *>(xS + r * CIP + 4 * k4);
-                    if (4 * k4 < CI) acc[4 * k4] = fmaf(dv, xv.x, acc[4 * k4]);
-                    if (4 * k4 + 1 < CI) acc[4 * k4 + 1] = fmaf(dv, xv.y, acc[4 * k4 + 1]);
-                    if (4 * k4 + 2 < CI) acc[4 * k4 + 2] = fmaf(dv, xv.z, acc[4 * k4 + 2]);
-                    if (4 * k4 + 3 < CI) acc[4 * k4 + 3] = fmaf(dv, xv.w, acc[4 * k4 + 3]);
+            if (rows == TR) {
+                if (tid == 0) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dx + base * CI),
+                                 "r"(smem_addr(dxS)), "r"(TR * CI * 4)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
                 }
-                acc[CI] += dv;
+            } else {
+                for (int e = tid; e < rows * CI; e += TR) dx[base * CI + e] = dxS[e];
             }
         }
+        if (g < G) {
+            for (int r = g; r < rows; r += G) {
+                const float xv = i_w < CI ? xS[r * CI + i_w] : 1.f;
+#pragma unroll
+                for (int o4 = 0; o4 < COP / 4; ++o4) {
+                    const float4 dv = *reinterpret_cast<const float4 *>(dyS + r * DYS + 4 * o4);
+                    if (4 * o4 < CO) acc[4 * o4] = fmaf(dv.x, xv, acc[4 * o4]);
+                    if (4 * o4 + 1 < CO) acc[4 * o4 + 1] = fmaf(dv.y, xv, acc[4 * o4 + 1]);
+                    if (4 * o4 + 2 < CO) acc[4 * o4 + 2] = fmaf(dv.z, xv, acc[4 * o4 + 2]);
+                    if (4 * o4 + 3 < CO) acc[4 * o4 + 3] = fmaf(dv.w, xv, acc[4 * o4 + 3]);
+                }
+            }
+        }
+        __syncthreads();  // xS / dzS / yS of this stage and dyS are free again
+        stage ^= 1;
     }
+    if (tid == 0 && dx) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
     __syncthreads();
     if (g < G) {
 #pragma unroll
-        for (int i = 0; i <= CI; ++i) xS[(g * CO + o_w) * (CI + 1) + i] = acc[i];
+        for (int o = 0; o < CO; ++o) dxS[g * NP + o * (CI + 1) + i_w] = acc[o];
     }
     __syncthreads();
     for (int t = tid; t < NP; t += TR) {
         float s = 0.f;
-        for (int gg = 0; gg < G; ++gg) s += xS[gg * NP + t];
+        for (int gg = 0; gg < G; ++gg) s += dxS[gg * NP + t];
         partial[(size_t)blockIdx.x * NP + t] = s;
     }
 }
@@ -446,6 +597,7 @@ extern "C" int sn2_lrb_fwd(const float *x, const float *W, const float *b, long 
                            float *y, double *stats, void *stream)
 {
     if (!x || !W || !b || !y || !stats || R <= 0) return SN2_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return SN2_EINVAL;  // TMA bulk copies read 16-byte aligned tiles
 #define X(ci, co) if (Ci == ci && Co == co) return sn2::launch_lrb_fwd<ci, co>(x, W, b, R, rows_dev, y, stats, (cudaStream_t)stream);
     SN2_LRB_SHAPES(X)
 #undef X
@@ -499,6 +651,9 @@ extern "C" int sn2_lrb_bwd(const float *dz, const float *y, const float *x, cons
                            float *partial, int nblk, float *dW, float *db, void *stream)
 {
     if (!dz || !y || !x || !W || !ss || !sums || !stats || !partial || !dW || !db || R <= 0 || nblk <= 0) return SN2_EINVAL;
+    if (((reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x) |
+          reinterpret_cast<uintptr_t>(dx)) & 15) != 0)
+        return SN2_EINVAL;  // TMA bulk copies move 16-byte aligned tiles
 #define X(ci, co)                  \
     if (Ci == ci && Co == co)      \
         return sn2::launch_lrb_bwd<ci, co>(dz, y, x, W, ss, sums, stats, R, rows_dev, dx, partial, nblk, dW, db, (cudaStream_t)stream);

@@ -191,12 +191,14 @@ class LinReluBN(torch.autograd.Function):
     `num_batches_tracked` and SyncBatchNorm (statistics all-reduced as raw fp64 sums + counts, forward and backward)
     behave as torch's modules do; `bn` is the block's own BatchNorm1d / SyncBatchNorm module."""
 
-    NBLK = 148 * 2
+    NBLK = 148 * 3
 
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, bn, rows=None):
         lib = _lib.load()
         x = _c(x)
+        if x.data_ptr() % 16:
+            x = x.clone()
         rp = dptr(rows, torch.int32)
         R, (Co, Ci) = x.shape[0], weight.shape
         dev = x.device
@@ -230,6 +232,8 @@ class LinReluBN(torch.autograd.Function):
         lib = _lib.load()
         x, y, weight, ss, stats = ctx.saved_tensors
         dz = _c(dz)
+        if dz.data_ptr() % 16:  # a view into a larger gradient buffer: the kernels fetch 16-byte aligned tiles
+            dz = dz.clone()
         R, (Co, Ci) = x.shape[0], weight.shape
         dev = x.device
         sums = torch.empty(2 * Co, dtype=torch.float64, device=dev)

@@ -232,6 +232,20 @@ class TrainStructure:
         return self
 
 
+_PREFETCH_STREAMS: dict = {}
+
+
+def _prefetch_stream(device) -> "torch.cuda.Stream":
+    """ONE side stream per device, shared by every StructurePrefetcher: the caching allocator keeps a pool per
+    stream, so a fresh stream per epoch would re-cudaMalloc the structural buffers each time (measured: the first
+    three steps of a loop took 100-250 ms each).  High priority, so that the FPS CTAs (a whole SM each) do not queue
+    behind every wave of the step's wide kernels."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _PREFETCH_STREAMS:
+        _PREFETCH_STREAMS[key] = torch.cuda.Stream(torch.device("cuda", key), priority=-1)
+    return _PREFETCH_STREAMS[key]
+
+
 class StructurePrefetcher:
     """Iterate over training batches with the structural stage of batch i+1 running on a side stream under the
     differentiable part of batch i (FPS is a serial chain on one SM per plot: 32 of 148 SMs at config 3).
@@ -255,9 +269,7 @@ class StructurePrefetcher:
         self.model, self.batches = model, batches
         self.device = device if device is not None else next(model.parameters()).device
         self.K = max_num_neighbors
-        # high priority: the FPS CTAs need a whole SM each and would otherwise queue behind every wave of the step's
-        # wide kernels (measured: the structural stage then finishes 5.8 ms after it was enqueued instead of ~2 ms)
-        self.side = torch.cuda.Stream(self.device, priority=-1)
+        self.side = _prefetch_stream(self.device)
         self._retired = []
 
     def _begin(self, batch):
