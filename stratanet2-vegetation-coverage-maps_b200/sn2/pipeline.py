@@ -88,8 +88,13 @@ def _packed(model) -> dict:
 
 
 def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_neighbors: int = 2000,
-                 trace: ForwardTrace | None = None, timer=None, side_streams=None):
-    """xyz (B,3,N), cloud (B,10,N) fp32 (host or device) -> coverages (B*N,4), proba (B*N,4) on device."""
+                 trace: ForwardTrace | None = None, timer=None, side_streams=None, head_stream=None, keep: list | None = None):
+    """xyz (B,3,N), cloud (B,10,N) fp32 (host or device) -> coverages (B*N,4), proba (B*N,4) on device.
+    head_stream: optional (high-priority) stream for the head of the dependency chain -- input copies, ingest, the
+    raw-point grid and FPS level 1 -- when several batches are in flight (InferencePipeline).
+    keep: when given, tensors that cross streams are appended to it and the CALLER keeps them alive until the batch
+    has finished, instead of Tensor.record_stream (whose deferred frees make the allocator's behaviour timing
+    dependent)."""
     if cloud.dim() != 3 or xyz.dim() != 3 or xyz.shape[1] != 3 or cloud.shape[0] != xyz.shape[0] \
             or cloud.shape[2] != xyz.shape[2]:
         raise RuntimeError("PointNet2.forward: expected xyz (B,3,N) and cloud (B,F,N)")
@@ -97,13 +102,12 @@ def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_
     if N != model.subsample_size:
         raise RuntimeError(f"PointNet2.forward: every plot must have subsample_size={model.subsample_size} points, got {N}")
     W = _packed(model)
-    xyz_d = xyz.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
-    cloud_d = cloud.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
     sa1, sa2 = model.sa1_module, model.sa2_module
 
     T = timer if timer is not None else _NOTIMER
     main = torch.cuda.current_stream(device)
     side_a, side_b = side_streams if side_streams is not None else _side_streams(device)
+    head = head_stream if head_stream is not None else main
 
     def fork(stream):
         ev = torch.cuda.Event()
@@ -114,16 +118,26 @@ def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_
         ev = torch.cuda.Event()
         ev.record(stream)
         main.wait_event(ev)
-        for t in tensors:
-            t.record_stream(main)
+        if keep is not None:
+            keep.extend(tensors)
+        else:
+            for t in tensors:
+                t.record_stream(main)
 
-    with T.stage("ingest"):
-        pos0, feat0 = ops.ingest(xyz_d, cloud_d)
     M1 = ops.m_of(N, sa1.ratio)
     M2 = ops.m_of(M1, sa2.ratio)
-    grid0 = ops.build_grid(pos0, B, N, sa1.r)  # cell order of the raw points: SA1's search grid AND knn1's query order
-    with T.stage("fps1"):
-        idx1, pos1 = ops.fps_dense(pos0, B, N, M1)
+    if head is not main:
+        fork(head)
+    with torch.cuda.stream(head):
+        xyz_d = xyz.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+        cloud_d = cloud.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+        with T.stage("ingest"):
+            pos0, feat0 = ops.ingest(xyz_d, cloud_d)
+        grid0 = ops.build_grid(pos0, B, N, sa1.r)  # cell order of the raw points: SA1's search grid AND knn1's query order
+        with T.stage("fps1"):
+            idx1, pos1 = ops.fps_dense(pos0, B, N, M1)
+    if head is not main:
+        join(head, xyz_d, cloud_d, pos0, feat0, idx1, pos1, *grid0)
     # The plot-level dependency graph (reference :131-139) has three independent branches after fps1:
     # sa1 (needs all SMs), fps2 -> knn2 (a 64-CTA latency chain, then a small search) and knn1.
     # They run on separate streams so the serial FPS chain of level 2 hides under the SA1 kernel.
@@ -520,8 +534,13 @@ class InferencePipeline:
         self.device = torch.device("cuda", model.cuda_device)
         mk = lambda: torch.cuda.Stream(device=self.device)  # noqa: E731
         self.sets = [(mk(), mk(), mk()) for _ in range(depth)]
+        # the head of each batch's chain (copies, ingest, FPS level 1: one SM per plot for ~40 % of the latency) on a
+        # high-priority stream, so that its CTAs do not queue behind the wide kernels of the batches ahead of it
+        self.heads = [torch.cuda.Stream(device=self.device, priority=-1) if os.environ.get("SN2_FPS_PRIORITY", "1") == "1" else None
+                      for _ in range(depth)]
         self.done = [None] * depth
         self.out = [None] * depth
+        self.keep = [[] for _ in range(depth)]  # per slot: tensors alive until the slot's batch has finished
         self.k = 0
 
     def submit(self, cloud_data: dict, keep_on_device: bool = False) -> int:
@@ -531,13 +550,15 @@ class InferencePipeline:
         self.k += 1
         if self.done[slot] is not None:
             self.done[slot].synchronize()  # the slot's previous batch (and its pinned buffers) must be finished
+        keep = self.keep[slot] = []
         main, a, b = self.sets[slot]
         D = int(self.args.diam_pix)
         launch = torch.cuda.current_stream(self.device)
         main.wait_stream(launch)
         with torch.cuda.stream(main), torch.no_grad():
             cov, proba, g, cloud_d = forward_eval(self.model, cloud_data["xyz"], cloud_data["cloud"], self.device,
-                                                  2000, None, None, side_streams=(a, b))
+                                                  2000, None, None, side_streams=(a, b), head_stream=self.heads[slot], keep=keep)
+            keep.extend((cov, proba, g, cloud_d))
             pw = _ops.project_plotwise(cloud_d, cov, D)
             rs = _ops.project_rasters(cloud_d, cov, "point_major", D, int(self.args.diam_meters))
             if keep_on_device:
