@@ -50,42 +50,69 @@ edge_msg_bwd_kernel(const float *__restrict__ dmsg, const int *__restrict__ col,
 }
 
 // ---- segment max with first-edge arg-max -------------------------------------------------------
-// one warp per row; lane l scans edges s+l, s+l+32, ... (ascending), strict '>' keeps the first
-template <int C>
-__global__ void __launch_bounds__(256)
+// Lane = (edge slot, channel quad): C/4 lanes cover one edge row with float4 loads (coalesced: a warp reads 32/(C/4)
+// consecutive rows = 512 contiguous bytes per instruction); every lane keeps the best (value, edge) of its four
+// channels over the edges of its slot, visited in ascending order with strict '>' (first edge wins inside a lane);
+// slots are merged with xor shuffles on (value, edge): larger value, then lower edge index.  WARPS = 1: one warp per
+// row (set-abstraction neighbourhoods, tens of edges); WARPS = 8: one CTA per row (global_max_pool: 32 rows of
+// hundreds of points), warps merged through shared memory.
+__device__ __forceinline__ void argmax_merge(float &v, int &e, float ov, int oe)
+{
+    if (ov > v || (ov == v && oe < e)) { v = ov; e = oe; }
+}
+
+template <int C, int WARPS>
+__global__ void __launch_bounds__(WARPS == 1 ? 256 : 32 * WARPS)
 segment_max_fwd_kernel(const float *__restrict__ vals, const int *__restrict__ rowptr, int Q,
                        float *__restrict__ out, int *__restrict__ arg)
 {
-    const int lane = threadIdx.x & 31;
-    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    constexpr int CQ = C / 4, SLOTS = 32 / CQ;  // lanes per edge row, edge rows per warp and step
+    static_assert(C % 4 == 0 && 32 % CQ == 0, "C must be 16, 32, 64 or 128");
+    __shared__ float sv[WARPS > 1 ? WARPS * C : 1];
+    __shared__ int se[WARPS > 1 ? WARPS * C : 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long q = WARPS == 1 ? (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) : (long long)blockIdx.x;
     if (q >= Q) return;
     const int s = __ldg(rowptr + q), e = __ldg(rowptr + q + 1);
-    constexpr int PER = (C + 31) / 32;  // channels handled per lane in the reduce phase
-    // phase 1: each lane keeps (best, edge) for every channel over its strided edges
-    float bv[C];
-    int be[C];
+    const int slot = lane / CQ, cq = lane - slot * CQ;
+    float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int be[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+    const int first = s + (WARPS == 1 ? 0 : warp * SLOTS) + slot, step = SLOTS * WARPS;
+    for (int j = first; j < e; j += step) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(vals + (size_t)j * C) + cq);
+        if (t.x > bv[0]) { bv[0] = t.x; be[0] = j; }
+        if (t.y > bv[1]) { bv[1] = t.y; be[1] = j; }
+        if (t.z > bv[2]) { bv[2] = t.z; be[2] = j; }
+        if (t.w > bv[3]) { bv[3] = t.w; be[3] = j; }
+    }
 #pragma unroll
-    for (int c = 0; c < C; ++c) { bv[c] = -INFINITY; be[c] = 0x7fffffff; }
-    for (int j = s + lane; j < e; j += 32) {
-        const float *v = vals + (size_t)j * C;
+    for (int d = CQ; d < 32; d <<= 1) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const float t = __ldg(v + c);
-            if (t > bv[c]) { bv[c] = t; be[c] = j; }
+        for (int c = 0; c < 4; ++c) {
+            const float ov = __shfl_xor_sync(SN2_FULL, bv[c], d);
+            const int oe = __shfl_xor_sync(SN2_FULL, be[c], d);
+            argmax_merge(bv[c], be[c], ov, oe);
         }
     }
-    (void)PER;
-    // phase 2: warp arg-max per channel: max value, then lowest edge index among the ties
+    if constexpr (WARPS > 1) {
+        if (slot == 0) {
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-        const unsigned key = fkey(bv[c]);
-        const unsigned m = __reduce_max_sync(SN2_FULL, key);
-        const unsigned me = __reduce_min_sync(SN2_FULL, (key == m && be[c] != 0x7fffffff) ? (unsigned)be[c] : 0xffffffffu);
-        if (lane == (c & 31)) {
-            // torch_scatter: empty row -> value 0, arg = number of edges (we store -1)
-            out[(size_t)q * C + c] = e > s ? fkey_inv(m) : 0.f;
-            arg[(size_t)q * C + c] = e > s ? (int)me : -1;
+            for (int c = 0; c < 4; ++c) { sv[warp * C + 4 * cq + c] = bv[c]; se[warp * C + 4 * cq + c] = be[c]; }
         }
+        __syncthreads();
+        if (threadIdx.x < C) {
+            float v = sv[threadIdx.x];
+            int ee = se[threadIdx.x];
+            for (int w = 1; w < WARPS; ++w) argmax_merge(v, ee, sv[w * C + threadIdx.x], se[w * C + threadIdx.x]);
+            // torch_scatter: empty row -> value 0, arg = number of edges (we store -1)
+            out[(size_t)q * C + threadIdx.x] = e > s ? v : 0.f;
+            arg[(size_t)q * C + threadIdx.x] = e > s ? ee : -1;
+        }
+    } else if (slot == 0) {
+        const bool any = e > s;
+        *reinterpret_cast<float4 *>(out + (size_t)q * C + 4 * cq) =
+            any ? make_float4(bv[0], bv[1], bv[2], bv[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<int4 *>(arg + (size_t)q * C + 4 * cq) = any ? make_int4(be[0], be[1], be[2], be[3]) : make_int4(-1, -1, -1, -1);
     }
 }
 
@@ -234,12 +261,24 @@ extern "C" int sn2_segment_max_fwd(const float *vals, const int *rowptr, int Q, 
                                    void *stream)
 {
     if (!vals || !rowptr || !out || !arg || Q <= 0) return SN2_EINVAL;
-    const unsigned blocks = blocks_for((long long)Q * 32, 256);
     cudaStream_t st = (cudaStream_t)stream;
+    if ((reinterpret_cast<uintptr_t>(vals) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(arg)) & 15) return SN2_EINVAL;
+    // few long rows (global_max_pool: one row per plot) -> one CTA per row; many short rows -> one warp per row
+    const bool cta_rows = (long long)Q * 32 < 148LL * 256 * 2;
+    const unsigned blocks = blocks_for((long long)Q * 32, 256);
     switch (C) {
-    case 16: segment_max_fwd_kernel<16><<<blocks, 256, 0, st>>>(vals, rowptr, Q, out, arg); break;
-    case 32: segment_max_fwd_kernel<32><<<blocks, 256, 0, st>>>(vals, rowptr, Q, out, arg); break;
-    case 64: segment_max_fwd_kernel<64><<<blocks, 256, 0, st>>>(vals, rowptr, Q, out, arg); break;
+    case 16:
+        if (cta_rows) segment_max_fwd_kernel<16, 8><<<Q, 256, 0, st>>>(vals, rowptr, Q, out, arg);
+        else segment_max_fwd_kernel<16, 1><<<blocks, 256, 0, st>>>(vals, rowptr, Q, out, arg);
+        break;
+    case 32:
+        if (cta_rows) segment_max_fwd_kernel<32, 8><<<Q, 256, 0, st>>>(vals, rowptr, Q, out, arg);
+        else segment_max_fwd_kernel<32, 1><<<blocks, 256, 0, st>>>(vals, rowptr, Q, out, arg);
+        break;
+    case 64:
+        if (cta_rows) segment_max_fwd_kernel<64, 8><<<Q, 256, 0, st>>>(vals, rowptr, Q, out, arg);
+        else segment_max_fwd_kernel<64, 1><<<blocks, 256, 0, st>>>(vals, rowptr, Q, out, arg);
+        break;
     default: return SN2_EUNSUPPORTED;
     }
     SN2_LAUNCH_CHECK("segment_max_fwd_kernel");

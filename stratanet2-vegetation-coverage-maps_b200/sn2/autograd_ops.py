@@ -57,6 +57,8 @@ class SegmentMax(torch.autograd.Function):
     def forward(ctx, vals, rowptr):
         lib = _lib.load()
         vals = _c(vals)
+        if vals.data_ptr() % 16:  # the kernel reads float4 channel quads
+            vals = vals.clone()
         Q, C = rowptr.numel() - 1, vals.shape[1]
         out = torch.empty((Q, C), dtype=torch.float32, device=vals.device)
         arg = torch.empty((Q, C), dtype=torch.int32, device=vals.device)
