@@ -14,9 +14,40 @@
 namespace sn2 {
 
 // ---- edge messages ---------------------------------------------------------------------------
+// One warp per query row; the lanes walk the row's message block msg[s*(C+3) .. e*(C+3)) element by element, so
+// every store instruction writes 128 contiguous bytes (a lane-per-edge mapping writes 32 rows 4 bytes at a time).
+// Element (edge j, column c): c < C -> x[col[j]][c], else pos[col[j]] - qpos[q] component c - C.
+template <int C>
 __global__ void __launch_bounds__(256)
 edge_msg_fwd_kernel(const float *__restrict__ x, const float4 *__restrict__ pos, const float4 *__restrict__ qpos,
-                    const int *__restrict__ rowptr, const int *__restrict__ col, int Q, int C, float *__restrict__ msg)
+                    const int *__restrict__ rowptr, const int *__restrict__ col, int Q, float *__restrict__ msg)
+{
+    constexpr int LD = C + 3;
+    const int lane = threadIdx.x & 31;
+    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= Q) return;
+    const int s = __ldg(rowptr + q), e = __ldg(rowptr + q + 1);
+    const float4 qp = __ldg(qpos + q);
+    const int n = (e - s) * LD;
+    float *m = msg + (size_t)s * LD;
+    for (int t = lane; t < n; t += 32) {
+        const int jl = t / LD, c = t - jl * LD;
+        const int p = __ldg(col + s + jl);
+        float v;
+        if (c < C) {
+            v = __ldg(x + (size_t)p * C + c);
+        } else {
+            const float4 pp = __ldg(pos + p);
+            v = c == C ? pp.x - qp.x : (c == C + 1 ? pp.y - qp.y : pp.z - qp.z);
+        }
+        m[t] = v;
+    }
+}
+
+// any other width: lane per edge
+__global__ void __launch_bounds__(256)
+edge_msg_fwd_generic_kernel(const float *__restrict__ x, const float4 *__restrict__ pos, const float4 *__restrict__ qpos,
+                            const int *__restrict__ rowptr, const int *__restrict__ col, int Q, int C, float *__restrict__ msg)
 {
     const int lane = threadIdx.x & 31;
     const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -241,8 +272,12 @@ extern "C" int sn2_edge_msg_fwd(const float *x, const float *pos4, const float *
                                 const int *col, int Q, int C, float *msg, void *stream)
 {
     if (!x || !pos4 || !qpos4 || !rowptr || !col || !msg || Q <= 0 || C <= 0) return SN2_EINVAL;
-    edge_msg_fwd_kernel<<<blocks_for((long long)Q * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-        x, reinterpret_cast<const float4 *>(pos4), reinterpret_cast<const float4 *>(qpos4), rowptr, col, Q, C, msg);
+    const unsigned blocks = blocks_for((long long)Q * 32, 256);
+    const float4 *p4 = reinterpret_cast<const float4 *>(pos4), *q4 = reinterpret_cast<const float4 *>(qpos4);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 8) edge_msg_fwd_kernel<8><<<blocks, 256, 0, st>>>(x, p4, q4, rowptr, col, Q, msg);
+    else if (C == 16) edge_msg_fwd_kernel<16><<<blocks, 256, 0, st>>>(x, p4, q4, rowptr, col, Q, msg);
+    else edge_msg_fwd_generic_kernel<<<blocks, 256, 0, st>>>(x, p4, q4, rowptr, col, Q, C, msg);
     SN2_LAUNCH_CHECK("edge_msg_fwd_kernel");
     return SN2_OK;
 }

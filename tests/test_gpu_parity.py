@@ -546,7 +546,8 @@ def test_tall_linear_weight_gradient(cuda_device, Co, Ci):
     torch.testing.assert_close(x.grad.double(), dy64 @ w64, rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("Ci,Co,R", [(11, 16, 300001), (16, 16, 131072), (19, 32, 99999), (80, 34, 70001), (42, 34, 65537)])
+@pytest.mark.parametrize("Ci,Co,R", [(11, 16, 300001), (16, 16, 131072), (19, 32, 99999), (80, 34, 70001), (42, 34, 65537),
+                                     (16, 16, 37), (42, 34, 129)])
 def test_fused_lin_relu_bn_block(cuda_device, Ci, Co, R):
     """LinReluBN (csrc/train_mlp.cu) against the torch modules of one reference MLP() block in float64:
     output, all five gradients, running statistics and num_batches_tracked."""
