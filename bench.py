@@ -619,11 +619,20 @@ def main():
     rot_host = [{k: v.pin_memory() for k, v in d.items()} for d in rot]
     rot_dev = [{k: v.to(dev) for k, v in d.items()} for d in rot]
 
+    # small batches (config 1: single plots) are launch bound on the host: more slots, one CUDA graph per slot
+    small = B * N <= (1 << 18)
+    depth = opts.pipeline if opts.pipeline else 0
+    if small and opts.pipeline == 3 and not opts.no_graph:
+        depth = 12
+    use_graph = small and not opts.no_graph
+    graph_launches = [0]
+
     def timed_pipe(batches, keep):
-        pipe = InferencePipeline(net, args, depth=opts.pipeline)
-        for i in range(W):
+        pipe = InferencePipeline(net, args, depth=depth, graph=use_graph)
+        for i in range(max(W, depth + 1)):
             pipe.submit(batches[i % nrot], keep_on_device=keep)
         pipe.drain()
+        r0 = pipe.replays
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -633,6 +642,8 @@ def main():
             torch.cuda.current_stream().wait_stream(s_[0])
         b.record()
         barrier()
+        if use_graph:  # our kernels inside the replayed graphs (counted at capture)
+            graph_launches[0] = (pipe.replays - r0) * pipe.graphs[0][3]
         return a.elapsed_time(b)
 
     ms_pipe_res = ms_pipe_e2e = None
@@ -692,7 +703,7 @@ def main():
         "n_gpus": world, "steps": opts.steps, "warmup": W, "ms_per_step": ms_res_used / opts.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["name"], "plots_per_gpu_per_step": B, "points_per_plot": N, "max_num_neighbors": 2000,
-                   "batches_in_flight": opts.pipeline or 1,
+                   "batches_in_flight": depth or 1, "cuda_graph_per_batch": bool(use_graph and opts.pipeline),
                    "l2": ("inputs larger than L2: steps rotate over 4 distinct input batches (218 MB), K steps timed as one region"
                           if opts.pipeline else "flushed between timed steps (256 MiB write outside the event pairs)"),
                    "parallelism": f"plot-sharded x{world}"},

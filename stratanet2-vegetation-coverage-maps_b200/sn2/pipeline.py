@@ -527,10 +527,20 @@ class InferencePipeline:
         for batch in loader:
             slot = pipe.submit(batch)          # returns immediately
             ... pipe.result(prev_slot) ...     # (plot-wise coverages [B,4], rasters [B,3,D,D]) on the host
+
+    graph=True: each slot's whole batch (forward on its three streams, both projections, the copies of the results
+    to pinned host memory) is captured once in a CUDA graph and replayed per submit; the inputs are copied into the
+    slot's fixed device buffers first.  The eval path has static shapes and no host synchronisation, so nothing
+    else changes.  This is for SMALL batches (single plots: ~30 launches cost the host 0.7 ms while the GPU needs
+    one SM for 1.1 ms): with 8-16 slots the throughput of a stream of single plots goes up several-fold.  The
+    packed weights are baked into the graphs: call `recapture()` after changing the model's parameters.
     """
 
-    def __init__(self, model, args, depth: int = 2):
+    def __init__(self, model, args, depth: int = 2, graph: bool = False):
         self.model, self.args, self.depth = model, args, depth
+        self.graph = graph
+        self.graphs = [None] * depth       # per slot: (CUDAGraph, static xyz, static cloud, launches inside the graph)
+        self.replays = 0
         self.device = torch.device("cuda", model.cuda_device)
         mk = lambda: torch.cuda.Stream(device=self.device)  # noqa: E731
         self.sets = [(mk(), mk(), mk()) for _ in range(depth)]
@@ -543,6 +553,50 @@ class InferencePipeline:
         self.keep = [[] for _ in range(depth)]  # per slot: tensors alive until the slot's batch has finished
         self.k = 0
 
+    def recapture(self):
+        self.drain()
+        self.graphs = [None] * self.depth
+
+    def _run(self, slot, xyz, cloud, keep, keep_on_device):
+        """One batch on the slot's streams (current stream = the slot's main stream)."""
+        from . import ops as _ops
+
+        main, a, b = self.sets[slot]
+        D = int(self.args.diam_pix)
+        cov, proba, g, cloud_d = forward_eval(self.model, xyz, cloud, self.device, 2000, None, None, side_streams=(a, b),
+                                              head_stream=self.heads[slot], keep=keep)
+        keep.extend((cov, proba, g, cloud_d))
+        pw = _ops.project_plotwise(cloud_d, cov, D)
+        rs = _ops.project_rasters(cloud_d, cov, "point_major", D, int(self.args.diam_meters))
+        if keep_on_device:
+            self.out[slot] = (pw, rs)
+        else:
+            if self.out[slot] is None or self.out[slot][0].shape != pw.shape or self.out[slot][0].is_cuda:
+                self.out[slot] = (torch.empty(pw.shape, dtype=pw.dtype).pin_memory(),
+                                  torch.empty(rs.shape, dtype=rs.dtype).pin_memory())
+            self.out[slot][0].copy_(pw, non_blocking=True)
+            self.out[slot][1].copy_(rs, non_blocking=True)
+
+    def _capture(self, slot, xyz, cloud, keep_on_device):
+        from . import ops as _ops
+
+        self.drain()
+        main = self.sets[slot][0]
+        sx = torch.empty(xyz.shape, dtype=torch.float32, device=self.device)
+        sc = torch.empty(cloud.shape, dtype=torch.float32, device=self.device)
+        with torch.cuda.stream(main), torch.no_grad():
+            sx.copy_(xyz, non_blocking=True)
+            sc.copy_(cloud, non_blocking=True)
+            self._run(slot, sx, sc, [], keep_on_device)  # eager once: output buffers, lazy initialisations
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        keep = []
+        l0 = _ops.LAUNCHES
+        with torch.no_grad(), torch.cuda.graph(graph, stream=main):
+            self._run(slot, sx, sc, keep, keep_on_device)
+        # tensors of the capture live in the graph's private pool; `keep` only had to outlive the capture
+        self.graphs[slot] = (graph, sx, sc, _ops.LAUNCHES - l0, bool(keep_on_device))
+
     def submit(self, cloud_data: dict, keep_on_device: bool = False) -> int:
         from . import ops as _ops
 
@@ -550,6 +604,24 @@ class InferencePipeline:
         self.k += 1
         if self.done[slot] is not None:
             self.done[slot].synchronize()  # the slot's previous batch (and its pinned buffers) must be finished
+        if self.graph:
+            xyz, cloud = cloud_data["xyz"], cloud_data["cloud"]
+            gs = self.graphs[slot]
+            if gs is None or gs[1].shape != xyz.shape or gs[2].shape != cloud.shape or gs[4] != bool(keep_on_device):
+                self._capture(slot, xyz, cloud, keep_on_device)
+                gs = self.graphs[slot]
+            graph, sx, sc = gs[0], gs[1], gs[2]
+            main = self.sets[slot][0]
+            main.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(main):
+                sx.copy_(xyz, non_blocking=True)
+                sc.copy_(cloud, non_blocking=True)
+                graph.replay()
+                ev = torch.cuda.Event()
+                ev.record(main)
+            self.replays += 1
+            self.done[slot] = ev
+            return slot
         keep = self.keep[slot] = []
         main, a, b = self.sets[slot]
         D = int(self.args.diam_pix)

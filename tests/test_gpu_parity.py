@@ -454,21 +454,23 @@ def test_submodule_forward_matches_reference_modules(cuda_device):
     assert xin.grad is not None and net.sa1_module.conv.local_nn[0][0].weight.grad is not None
 
 
-def test_inference_pipeline_matches_serial(cuda_device):
-    """Batches in flight on independent stream sets give exactly the serial results."""
+@pytest.mark.parametrize("graph,B,nb", [(False, 3, 5), (True, 3, 7), (True, 1, 9)])
+def test_inference_pipeline_matches_serial(cuda_device, graph, B, nb):
+    """Batches in flight on independent stream sets give exactly the serial results; graph=True replays each
+    slot's batch as one CUDA graph (more batches than slots, so every graph is replayed on new inputs)."""
     from model.project_to_2d import project_to_2d_rasters_batched, project_to_plotwise_coverages
     from sn2.pipeline import InferencePipeline
 
-    N, B = 4096, 3
+    N = 4096
     args, net, _ = _make_models(N, cuda_device)
-    batches = [_plots(30 + i, B, N) for i in range(5)]
+    batches = [_plots(30 + i, B, N) for i in range(nb)]
     want = []
     with torch.no_grad():
         for d in batches:
             cov, _ = net(d)
             want.append((project_to_plotwise_coverages(cov, d["cloud"], args).cpu(),
                          project_to_2d_rasters_batched(d["cloud"], cov, args).cpu()))
-    pipe = InferencePipeline(net, args, depth=3)
+    pipe = InferencePipeline(net, args, depth=3, graph=graph)
     slots = []
     got = [None] * len(batches)
     for i, d in enumerate(batches):
