@@ -183,8 +183,10 @@ int sn2_edge_msg_fwd(const float *x, const float *pos4, const float *qpos4, cons
 int sn2_edge_msg_bwd(const float *dmsg, const int *col, long long E, const int *rows_dev, int C, float *dx,
                      void *stream);
 /* scatter max over CSR rows (PointConv aggr='max', global_max_pool): out [Q,C], arg [Q,C] = first edge
- * attaining the max (-1 and value 0 for an empty row).  C in {16, 32, 64}. */
-int sn2_segment_max_fwd(const float *vals, const int *rowptr, int Q, int C, float *out, int *arg,
+ * attaining the max (-1 and value 0 for an empty row).  C in {16, 32, 64}.
+ * ss (nullable, device [2*C] = per-channel scale | shift): the max is taken over vals * scale + shift, i.e. the
+ * BatchNorm of the producing block applied on load instead of in a pass of its own (train-mode blocks below). */
+int sn2_segment_max_fwd(const float *vals, const float *ss, const int *rowptr, int Q, int C, float *out, int *arg,
                         void *stream);
 /* dvals [E,C] (zero-initialised) receives dout at the arg-max edges. */
 int sn2_segment_max_bwd(const float *dout, const int *arg, long long Q, int C, float *dvals, void *stream);
@@ -218,13 +220,17 @@ int sn2_linear_wgrad(const float *dy, const float *x, long long E, int Co, int C
  *   sn2_bn_finalize    stats -> ss [4*Co] = {scale, shift, mean, invstd} (biased variance, eps); running_mean /
  *                      running_var (nullable) updated with `momentum` and the unbiased variance like torch;
  *                      *num_batches_tracked (nullable, int64) += 1.
- *   sn2_bn_apply       z = y * scale + shift.
+ *   sn2_bn_apply       z = y * scale + shift.  A consumer that is itself one of these kernels can skip this pass:
+ *                      `in_ss` (nullable, device [2*Ci] = scale | shift of the PRODUCING block, i.e. the first half of
+ *                      its ss) makes sn2_lrb_fwd / sn2_lrb_bwd read x * scale + shift instead of x, and
+ *                      sn2_segment_max_fwd takes the same through its `ss`; sn2_lrb_block_fwd skips it when z is NULL.
+ *                      The gradient wrt that virtual z is what sn2_lrb_bwd returns in dx / expects in dz.
  *   sn2_lrb_bwd_reduce sums [2*Co] fp64 = {sum dz, sum dz*y} (zeroed here; all-reduced by the caller for SyncBN).
  *   sn2_lrb_bwd        dx [R,Ci] (nullable) = dy W with dy = relu'(y) * BN'(dz); dW [Co,Ci] = dy^T x; db [Co];
  *                      partial: scratch [nblk, Co*(Ci+1)], fixed-order two-stage reduction. */
 int sn2_lrb_supported(int Co, int Ci);
-int sn2_lrb_fwd(const float *x, const float *W, const float *b, long long R, const int *rows_dev, int Co, int Ci,
-                float *y, double *stats, void *stream);
+int sn2_lrb_fwd(const float *x, const float *in_ss, const float *W, const float *b, long long R, const int *rows_dev,
+                int Co, int Ci, float *y, double *stats, void *stream);
 int sn2_bn_finalize(const double *stats, const float *gamma, const float *beta, float eps, float momentum,
                     float *running_mean, float *running_var, long long *num_batches_tracked, float *ss, int Co,
                     void *stream);
@@ -233,17 +239,17 @@ int sn2_lrb_bwd_reduce(const float *dz, const float *y, long long R, const int *
                        void *stream);
 /* BatchNorm affine gradients of THIS rank from its own (not all-reduced) sums: dbeta = sum dz, dgamma = sum dz*yhat. */
 int sn2_bn_param_grad(const double *sums, const float *ss, int Co, float *dgamma, float *dbeta, void *stream);
-int sn2_lrb_bwd(const float *dz, const float *y, const float *x, const float *W, const float *ss,
+int sn2_lrb_bwd(const float *dz, const float *y, const float *x, const float *in_ss, const float *W, const float *ss,
                 const double *sums, const double *stats, long long R, const int *rows_dev, int Co, int Ci, float *dx,
                 float *partial, int nblk, float *dW, float *db, void *stream);
 /* The same block in one call each way when no all-reduce sits between the kernels (plain BatchNorm1d):
  * fwd = sn2_lrb_fwd + sn2_bn_finalize (num_batches_tracked += 1 when given) + sn2_bn_apply;
  * bwd = sn2_lrb_bwd_reduce + sn2_bn_param_grad + sn2_lrb_bwd. */
-int sn2_lrb_block_fwd(const float *x, const float *W, const float *b, const float *gamma, const float *beta,
+int sn2_lrb_block_fwd(const float *x, const float *in_ss, const float *W, const float *b, const float *gamma, const float *beta,
                       float eps, float momentum, float *running_mean, float *running_var,
                       long long *num_batches_tracked, long long R, const int *rows_dev, int Co, int Ci, float *y,
                       double *stats, float *ss, float *z, void *stream);
-int sn2_lrb_block_bwd(const float *dz, const float *y, const float *x, const float *W, const float *ss,
+int sn2_lrb_block_bwd(const float *dz, const float *y, const float *x, const float *in_ss, const float *W, const float *ss,
                       const double *stats, long long R, const int *rows_dev, int Co, int Ci, double *sums,
                       float *dgamma, float *dbeta, float *dx, float *partial, int nblk, float *dW, float *db,
                       void *stream);

@@ -130,7 +130,8 @@ struct LrbFwd {
     static constexpr int COP = (CO + 3) & ~3;
     static constexpr int STAGES = CI > 48 ? 2 : 3;      // 32-row slabs in flight per warp
     static constexpr int SLAB = 32 * CI;                 // floats; 128 * CI bytes: a multiple of 16 for any CI
-    static constexpr size_t SMEM = sizeof(double) * 2 * CO + sizeof(float) * ((size_t)CI * COP + COP + (size_t)WARPS * STAGES * SLAB) +
+    static constexpr int CIP = (CI + 3) & ~3;
+    static constexpr size_t SMEM = sizeof(double) * 2 * CO + sizeof(float) * ((size_t)CI * COP + COP + 2 * CIP + (size_t)WARPS * STAGES * SLAB) +
                                    sizeof(unsigned long long) * WARPS * STAGES;
 };
 
@@ -140,19 +141,25 @@ struct LrbFwd {
 // staging: the loads of the next tiles are in flight while each lane runs the layer on its row.
 template <int CI, int CO>
 __global__ void __launch_bounds__(LRB_T, (CO > 16 ? 1 : 2))
-lrb_fwd_kernel(const float *__restrict__ x, const float *__restrict__ W, const float *__restrict__ b, long long R,
-               const int *__restrict__ rows_dev, float *__restrict__ y, double *__restrict__ stats)
+lrb_fwd_kernel(const float *__restrict__ x, const float *__restrict__ in_ss, const float *__restrict__ W,
+               const float *__restrict__ b, long long R, const int *__restrict__ rows_dev, float *__restrict__ y,
+               double *__restrict__ stats)
 {
     if (rows_dev) R = min(R, (long long)__ldg(rows_dev));
     using L = LrbFwd<CI, CO>;
-    constexpr int COP = L::COP, STAGES = L::STAGES, SLAB = L::SLAB;
+    constexpr int COP = L::COP, STAGES = L::STAGES, SLAB = L::SLAB, CIP = L::CIP;
     extern __shared__ __align__(16) unsigned char lrb_smem[];
     double *red = reinterpret_cast<double *>(lrb_smem);
     float *Wt = reinterpret_cast<float *>(red + 2 * CO);  // [CI][COP]: Wt[k][o] = W[o][k]
     float *bS = Wt + CI * COP;
+    float *inS = bS + COP;                                // input affine: scale [CIP] | shift [CIP] (identity if none)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float *ring = bS + COP + warp * (STAGES * SLAB);      // this warp's STAGES slabs of [32][CI]
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(bS + COP + L::WARPS * STAGES * SLAB) + warp * STAGES;
+    float *ring = inS + 2 * CIP + warp * (STAGES * SLAB); // this warp's STAGES slabs of [32][CI]
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(inS + 2 * CIP + L::WARPS * STAGES * SLAB) + warp * STAGES;
+    for (int k = tid; k < CI; k += LRB_T) {
+        inS[k] = in_ss ? __ldg(in_ss + k) : 1.f;
+        inS[CIP + k] = in_ss ? __ldg(in_ss + CI + k) : 0.f;
+    }
     for (int e = tid; e < CI * COP; e += LRB_T) {
         const int k = e / COP, o = e - k * COP;
         Wt[e] = o < CO ? __ldg(W + o * CI + k) : 0.f;
@@ -212,8 +219,8 @@ lrb_fwd_kernel(const float *__restrict__ x, const float *__restrict__ W, const f
                 }
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
-                    const float xk = xv[j];
                     const int k = kv * V + j;
+                    const float xk = fmaf(xv[j], inS[k], inS[CIP + k]);  // the producer block's BatchNorm, applied on load
 #pragma unroll
                     for (int o4 = 0; o4 < COP / 4; ++o4) {
                         const float4 w = *reinterpret_cast<const float4 *>(Wt + k * COP + 4 * o4);
@@ -361,7 +368,7 @@ struct LrbBwd {
 template <int CI, int CO>
 __global__ void __launch_bounds__(LrbBwd<CI, CO>::TR, LrbBwd<CI, CO>::MINB)
 lrb_bwd_kernel(const float *__restrict__ dz, const float *__restrict__ y, const float *__restrict__ x,
-               const float *__restrict__ W, const float *__restrict__ ss, const double *__restrict__ sums,
+               const float *__restrict__ in_ss, const float *__restrict__ W, const float *__restrict__ ss, const double *__restrict__ sums,
                const double *__restrict__ stats, long long R, const int *__restrict__ rows_dev, float *__restrict__ dx,
                float *__restrict__ partial)
 {
@@ -414,6 +421,8 @@ lrb_bwd_kernel(const float *__restrict__ dz, const float *__restrict__ y, const 
 #pragma unroll
     for (int o = 0; o < CO; ++o) acc[o] = 0.f;
     const int g = tid / (CI + 1), i_w = tid - g * (CI + 1);
+    // x as the forward saw it: the producer block's BatchNorm (scale, shift of column i_w) applied on load
+    const float xs = (in_ss && i_w < CI) ? __ldg(in_ss + i_w) : 1.f, xt = (in_ss && i_w < CI) ? __ldg(in_ss + CI + i_w) : 0.f;
     int stage = 0;
     unsigned it = 0;  // stages alternate strictly, so the phase parity of a stage is bit 1 of the iteration count
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -491,7 +500,7 @@ lrb_bwd_kernel(const float *__restrict__ dz, const float *__restrict__ y, const 
         }
         if (g < G) {
             for (int r = g; r < rows; r += G) {
-                const float xv = i_w < CI ? xS[r * CI + i_w] : 1.f;
+                const float xv = i_w < CI ? fmaf(xS[r * CI + i_w], xs, xt) : 1.f;
 #pragma unroll
                 for (int o4 = 0; o4 < COP / 4; ++o4) {
                     const float4 dv = *reinterpret_cast<const float4 *>(dyS + r * DYS + 4 * o4);
@@ -539,8 +548,8 @@ lrb_wgrad_reduce_kernel(const float *__restrict__ partial, int nblk, int Co, int
 }
 
 template <int CI, int CO>
-static int launch_lrb_fwd(const float *x, const float *W, const float *b, long long R, const int *rows_dev, float *y,
-                          double *stats, cudaStream_t st)
+static int launch_lrb_fwd(const float *x, const float *in_ss, const float *W, const float *b, long long R, const int *rows_dev,
+                          float *y, double *stats, cudaStream_t st)
 {
     using L = LrbFwd<CI, CO>;
     auto kern = lrb_fwd_kernel<CI, CO>;
@@ -549,7 +558,7 @@ static int launch_lrb_fwd(const float *x, const float *W, const float *b, long l
     set_count_kernel<<<1, 1, 0, st>>>(stats, CO, R, rows_dev);
     const long long nblocks = ((R + 31) / 32 + L::WARPS - 1) / L::WARPS;
     const int grid = (int)min(nblocks, (long long)148 * 2);
-    kern<<<grid, LRB_T, L::SMEM, st>>>(x, W, b, R, rows_dev, y, stats);
+    kern<<<grid, LRB_T, L::SMEM, st>>>(x, in_ss, W, b, R, rows_dev, y, stats);
     SN2_LAUNCH_CHECK("lrb_fwd_kernel");
     return SN2_OK;
 }
@@ -566,14 +575,15 @@ static int launch_lrb_bwd_reduce(const float *dz, const float *y, long long R, c
 }
 
 template <int CI, int CO>
-static int launch_lrb_bwd(const float *dz, const float *y, const float *x, const float *W, const float *ss, const double *sums,
+static int launch_lrb_bwd(const float *dz, const float *y, const float *x, const float *in_ss, const float *W, const float *ss,
+                          const double *sums,
                           const double *stats, long long R, const int *rows_dev, float *dx, float *partial, int nblk, float *dW,
                           float *db, cudaStream_t st)
 {
     using L = LrbBwd<CI, CO>;
     auto kern = lrb_bwd_kernel<CI, CO>;
     SN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM), "lrb_bwd attr");
-    kern<<<nblk, L::TR, L::SMEM, st>>>(dz, y, x, W, ss, sums, stats, R, rows_dev, dx, partial);
+    kern<<<nblk, L::TR, L::SMEM, st>>>(dz, y, x, in_ss, W, ss, sums, stats, R, rows_dev, dx, partial);
     SN2_LAUNCH_CHECK("lrb_bwd_kernel");
     lrb_wgrad_reduce_kernel<<<(L::NP * 32 + 255) / 256, 256, 0, st>>>(partial, nblk, CO, CI, dW, db);
     SN2_LAUNCH_CHECK("lrb_wgrad_reduce_kernel");
@@ -593,12 +603,12 @@ extern "C" int sn2_lrb_supported(int Co, int Ci)
     return 0;
 }
 
-extern "C" int sn2_lrb_fwd(const float *x, const float *W, const float *b, long long R, const int *rows_dev, int Co, int Ci,
-                           float *y, double *stats, void *stream)
+extern "C" int sn2_lrb_fwd(const float *x, const float *in_ss, const float *W, const float *b, long long R, const int *rows_dev,
+                           int Co, int Ci, float *y, double *stats, void *stream)
 {
     if (!x || !W || !b || !y || !stats || R <= 0) return SN2_EINVAL;
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return SN2_EINVAL;  // TMA bulk copies read 16-byte aligned tiles
-#define X(ci, co) if (Ci == ci && Co == co) return sn2::launch_lrb_fwd<ci, co>(x, W, b, R, rows_dev, y, stats, (cudaStream_t)stream);
+#define X(ci, co) if (Ci == ci && Co == co) return sn2::launch_lrb_fwd<ci, co>(x, in_ss, W, b, R, rows_dev, y, stats, (cudaStream_t)stream);
     SN2_LRB_SHAPES(X)
 #undef X
     return SN2_EUNSUPPORTED;
@@ -646,7 +656,7 @@ extern "C" int sn2_bn_param_grad(const double *sums, const float *ss, int Co, fl
     return SN2_OK;
 }
 
-extern "C" int sn2_lrb_bwd(const float *dz, const float *y, const float *x, const float *W, const float *ss,
+extern "C" int sn2_lrb_bwd(const float *dz, const float *y, const float *x, const float *in_ss, const float *W, const float *ss,
                            const double *sums, const double *stats, long long R, const int *rows_dev, int Co, int Ci, float *dx,
                            float *partial, int nblk, float *dW, float *db, void *stream)
 {
@@ -656,7 +666,7 @@ extern "C" int sn2_lrb_bwd(const float *dz, const float *y, const float *x, cons
         return SN2_EINVAL;  // TMA bulk copies move 16-byte aligned tiles
 #define X(ci, co)                  \
     if (Ci == ci && Co == co)      \
-        return sn2::launch_lrb_bwd<ci, co>(dz, y, x, W, ss, sums, stats, R, rows_dev, dx, partial, nblk, dW, db, (cudaStream_t)stream);
+        return sn2::launch_lrb_bwd<ci, co>(dz, y, x, in_ss, W, ss, sums, stats, R, rows_dev, dx, partial, nblk, dW, db, (cudaStream_t)stream);
     SN2_LRB_SHAPES(X)
 #undef X
     return SN2_EUNSUPPORTED;
@@ -664,23 +674,23 @@ extern "C" int sn2_lrb_bwd(const float *dz, const float *y, const float *x, cons
 
 // Single-process block in one call each way (no all-reduce between the kernels): what LinReluBN uses when the
 // block's BatchNorm is not a SyncBatchNorm.
-extern "C" int sn2_lrb_block_fwd(const float *x, const float *W, const float *b, const float *gamma, const float *beta,
+extern "C" int sn2_lrb_block_fwd(const float *x, const float *in_ss, const float *W, const float *b, const float *gamma, const float *beta,
                                  float eps, float momentum, float *running_mean, float *running_var,
                                  long long *num_batches_tracked, long long R, const int *rows_dev, int Co, int Ci, float *y,
                                  double *stats, float *ss, float *z, void *stream)
 {
-    if (int rc = sn2_lrb_fwd(x, W, b, R, rows_dev, Co, Ci, y, stats, stream)) return rc;
+    if (int rc = sn2_lrb_fwd(x, in_ss, W, b, R, rows_dev, Co, Ci, y, stats, stream)) return rc;
     if (int rc = sn2_bn_finalize(stats, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked, ss, Co, stream))
         return rc;
-    return sn2_bn_apply(y, ss, R, rows_dev, Co, z, stream);
+    return z ? sn2_bn_apply(y, ss, R, rows_dev, Co, z, stream) : SN2_OK;  // z == NULL: the consumer applies ss on load
 }
 
-extern "C" int sn2_lrb_block_bwd(const float *dz, const float *y, const float *x, const float *W, const float *ss,
+extern "C" int sn2_lrb_block_bwd(const float *dz, const float *y, const float *x, const float *in_ss, const float *W, const float *ss,
                                  const double *stats, long long R, const int *rows_dev, int Co, int Ci, double *sums,
                                  float *dgamma, float *dbeta, float *dx, float *partial, int nblk, float *dW, float *db,
                                  void *stream)
 {
     if (int rc = sn2_lrb_bwd_reduce(dz, y, R, rows_dev, Co, sums, stream)) return rc;
     if (int rc = sn2_bn_param_grad(sums, ss, Co, dgamma, dbeta, stream)) return rc;
-    return sn2_lrb_bwd(dz, y, x, W, ss, sums, stats, R, rows_dev, Co, Ci, dx, partial, nblk, dW, db, stream);
+    return sn2_lrb_bwd(dz, y, x, in_ss, W, ss, sums, stats, R, rows_dev, Co, Ci, dx, partial, nblk, dW, db, stream);
 }

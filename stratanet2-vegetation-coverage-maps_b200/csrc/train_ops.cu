@@ -94,7 +94,7 @@ __device__ __forceinline__ void argmax_merge(float &v, int &e, float ov, int oe)
 
 template <int C, int WARPS>
 __global__ void __launch_bounds__(WARPS == 1 ? 256 : 32 * WARPS)
-segment_max_fwd_kernel(const float *__restrict__ vals, const int *__restrict__ rowptr, int Q,
+segment_max_fwd_kernel(const float *__restrict__ vals, const float *__restrict__ ss, const int *__restrict__ rowptr, int Q,
                        float *__restrict__ out, int *__restrict__ arg)
 {
     constexpr int CQ = C / 4, SLOTS = 32 / CQ;  // lanes per edge row, edge rows per warp and step
@@ -108,9 +108,17 @@ segment_max_fwd_kernel(const float *__restrict__ vals, const int *__restrict__ r
     const int slot = lane / CQ, cq = lane - slot * CQ;
     float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     int be[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+    // optional per-channel affine (the producer block's BatchNorm scale | shift) applied on load: with a negative
+    // scale the max of the transformed values is not the transform of the max, so it cannot wait until afterwards
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ss) {
+        sc = __ldg(reinterpret_cast<const float4 *>(ss) + cq);
+        sh = __ldg(reinterpret_cast<const float4 *>(ss + C) + cq);
+    }
     const int first = s + (WARPS == 1 ? 0 : warp * SLOTS) + slot, step = SLOTS * WARPS;
     for (int j = first; j < e; j += step) {
-        const float4 t = __ldg(reinterpret_cast<const float4 *>(vals + (size_t)j * C) + cq);
+        float4 t = __ldg(reinterpret_cast<const float4 *>(vals + (size_t)j * C) + cq);
+        t = make_float4(fmaf(t.x, sc.x, sh.x), fmaf(t.y, sc.y, sh.y), fmaf(t.z, sc.z, sh.z), fmaf(t.w, sc.w, sh.w));
         if (t.x > bv[0]) { bv[0] = t.x; be[0] = j; }
         if (t.y > bv[1]) { bv[1] = t.y; be[1] = j; }
         if (t.z > bv[2]) { bv[2] = t.z; be[2] = j; }
@@ -292,10 +300,11 @@ extern "C" int sn2_edge_msg_bwd(const float *dmsg, const int *col, long long E, 
     return SN2_OK;
 }
 
-extern "C" int sn2_segment_max_fwd(const float *vals, const int *rowptr, int Q, int C, float *out, int *arg,
+extern "C" int sn2_segment_max_fwd(const float *vals, const float *ss, const int *rowptr, int Q, int C, float *out, int *arg,
                                    void *stream)
 {
     if (!vals || !rowptr || !out || !arg || Q <= 0) return SN2_EINVAL;
+    if (reinterpret_cast<uintptr_t>(ss) & 15) return SN2_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     if ((reinterpret_cast<uintptr_t>(vals) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(arg)) & 15) return SN2_EINVAL;
     // few long rows (global_max_pool: one row per plot) -> one CTA per row; many short rows -> one warp per row
@@ -303,16 +312,16 @@ extern "C" int sn2_segment_max_fwd(const float *vals, const int *rowptr, int Q, 
     const unsigned blocks = blocks_for((long long)Q * 32, 256);
     switch (C) {
     case 16:
-        if (cta_rows) segment_max_fwd_kernel<16, 8><<<Q, 256, 0, st>>>(vals, rowptr, Q, out, arg);
-        else segment_max_fwd_kernel<16, 1><<<blocks, 256, 0, st>>>(vals, rowptr, Q, out, arg);
+        if (cta_rows) segment_max_fwd_kernel<16, 8><<<Q, 256, 0, st>>>(vals, ss, rowptr, Q, out, arg);
+        else segment_max_fwd_kernel<16, 1><<<blocks, 256, 0, st>>>(vals, ss, rowptr, Q, out, arg);
         break;
     case 32:
-        if (cta_rows) segment_max_fwd_kernel<32, 8><<<Q, 256, 0, st>>>(vals, rowptr, Q, out, arg);
-        else segment_max_fwd_kernel<32, 1><<<blocks, 256, 0, st>>>(vals, rowptr, Q, out, arg);
+        if (cta_rows) segment_max_fwd_kernel<32, 8><<<Q, 256, 0, st>>>(vals, ss, rowptr, Q, out, arg);
+        else segment_max_fwd_kernel<32, 1><<<blocks, 256, 0, st>>>(vals, ss, rowptr, Q, out, arg);
         break;
     case 64:
-        if (cta_rows) segment_max_fwd_kernel<64, 8><<<Q, 256, 0, st>>>(vals, rowptr, Q, out, arg);
-        else segment_max_fwd_kernel<64, 1><<<blocks, 256, 0, st>>>(vals, rowptr, Q, out, arg);
+        if (cta_rows) segment_max_fwd_kernel<64, 8><<<Q, 256, 0, st>>>(vals, ss, rowptr, Q, out, arg);
+        else segment_max_fwd_kernel<64, 1><<<blocks, 256, 0, st>>>(vals, ss, rowptr, Q, out, arg);
         break;
     default: return SN2_EUNSUPPORTED;
     }

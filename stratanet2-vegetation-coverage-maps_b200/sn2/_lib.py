@@ -41,7 +41,7 @@ SIGNATURES = {
     "sn2_fp1_head_fwd_tc": [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp],
     "sn2_edge_msg_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp],
     "sn2_edge_msg_bwd": [_vp, _vp, _ll, _vp, _i, _vp, _vp],
-    "sn2_segment_max_fwd": [_vp, _vp, _i, _i, _vp, _vp, _vp],
+    "sn2_segment_max_fwd": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "sn2_segment_max_bwd": [_vp, _vp, _ll, _i, _vp, _vp],
     "sn2_interp3_fwd": [_vp, _i, _vp, _vp, _ll, _i, _vp, _vp],
     "sn2_interp3_bwd": [_vp, _vp, _vp, _ll, _i, _vp, _vp],
@@ -51,14 +51,14 @@ SIGNATURES = {
     "sn2_linear_wgrad_supported": [_i, _i],
     "sn2_linear_wgrad": [_vp, _vp, _ll, _i, _i, _vp, _i, _vp, _vp, _vp],
     "sn2_lrb_supported": [_i, _i],
-    "sn2_lrb_fwd": [_vp, _vp, _vp, _ll, _vp, _i, _i, _vp, _vp, _vp],
+    "sn2_lrb_fwd": [_vp, _vp, _vp, _vp, _ll, _vp, _i, _i, _vp, _vp, _vp],
     "sn2_bn_finalize": [_vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp],
     "sn2_bn_param_grad": [_vp, _vp, _i, _vp, _vp, _vp],
-    "sn2_lrb_block_fwd": [_vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _ll, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp],
-    "sn2_lrb_block_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "sn2_lrb_block_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _ll, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "sn2_lrb_block_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
     "sn2_bn_apply": [_vp, _vp, _ll, _vp, _i, _vp, _vp],
     "sn2_lrb_bwd_reduce": [_vp, _vp, _ll, _vp, _i, _vp, _vp],
-    "sn2_lrb_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp],
+    "sn2_lrb_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp],
     "sn2_fuse_accumulate": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "sn2_fuse_finalize": [_vp, _vp, _vp, _i, _i, _vp, _vp],
     "sn2_project_plotwise": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],

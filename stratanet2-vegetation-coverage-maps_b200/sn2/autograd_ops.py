@@ -54,7 +54,9 @@ class SegmentMax(torch.autograd.Function):
     """Per-row max over CSR rows with first-edge arg-max; gradient routed to the arg-max edges (A3, A4, A6)."""
 
     @staticmethod
-    def forward(ctx, vals, rowptr):
+    def forward(ctx, vals, rowptr, ss=None):
+        """ss: optional [>= 2C] scale | shift of the producing LinReluBN block (apply=False): the max is taken over
+        vals * scale + shift and the gradient returned for `vals` is the gradient with respect to that product."""
         lib = _lib.load()
         vals = _c(vals)
         if vals.data_ptr() % 16:  # the kernel reads float4 channel quads
@@ -62,8 +64,8 @@ class SegmentMax(torch.autograd.Function):
         Q, C = rowptr.numel() - 1, vals.shape[1]
         out = torch.empty((Q, C), dtype=torch.float32, device=vals.device)
         arg = torch.empty((Q, C), dtype=torch.int32, device=vals.device)
-        check(lib.sn2_segment_max_fwd(dptr(vals, torch.float32), dptr(rowptr, torch.int32), Q, C, dptr(out), dptr(arg),
-                                      stream_ptr()), "sn2_segment_max_fwd")
+        check(lib.sn2_segment_max_fwd(dptr(vals, torch.float32), dptr(ss, torch.float32), dptr(rowptr, torch.int32), Q, C,
+                                      dptr(out), dptr(arg), stream_ptr()), "sn2_segment_max_fwd")
         ops._count(1)
         ctx.save_for_backward(arg)
         ctx.E = vals.shape[0]
@@ -79,7 +81,7 @@ class SegmentMax(torch.autograd.Function):
         check(lib.sn2_segment_max_bwd(dptr(_c(dout), torch.float32), dptr(arg), Q, C, dptr(dvals), stream_ptr()),
               "sn2_segment_max_bwd")
         ops._count(1)
-        return dvals, None
+        return dvals, None, None
 
 
 class Interp3(torch.autograd.Function):
@@ -196,7 +198,11 @@ class LinReluBN(torch.autograd.Function):
     NBLK = 148 * 3
 
     @staticmethod
-    def forward(ctx, x, weight, bias, gamma, beta, bn, rows=None):
+    def forward(ctx, x, weight, bias, gamma, beta, bn, rows=None, in_ss=None, apply=True):
+        """in_ss: scale | shift of the block that produced x with apply=False (x is then that block's un-normalised
+        output and is read as x * scale + shift).  apply=False: return (y, ss) instead of z = y * scale + shift;
+        the consumer (the next LinReluBN through in_ss, or SegmentMax through ss) applies ss on load and hands the
+        gradient with respect to z back as the gradient of y."""
         lib = _lib.load()
         x = _c(x)
         if x.data_ptr() % 16:
@@ -205,7 +211,8 @@ class LinReluBN(torch.autograd.Function):
         R, (Co, Ci) = x.shape[0], weight.shape
         dev = x.device
         y = torch.empty((R, Co), dtype=torch.float32, device=dev)
-        z = torch.empty((R, Co), dtype=torch.float32, device=dev)
+        z = torch.empty((R, Co), dtype=torch.float32, device=dev) if apply else None
+        ip = dptr(in_ss, torch.float32)
         stats = torch.empty(2 * Co + 1, dtype=torch.float64, device=dev)
         ss = torch.empty(4 * Co, dtype=torch.float32, device=dev)
         track = bn.track_running_stats and bn.running_mean is not None
@@ -216,23 +223,28 @@ class LinReluBN(torch.autograd.Function):
         st = stream_ptr()
         group = _sync_group(bn)
         if group is None:
-            check(lib.sn2_lrb_block_fwd(dptr(x, torch.float32), wp, bp, gp, btp, float(bn.eps), float(bn.momentum), rm, rv, nbt,
+            check(lib.sn2_lrb_block_fwd(dptr(x, torch.float32), ip, wp, bp, gp, btp, float(bn.eps), float(bn.momentum), rm, rv, nbt,
                                         R, rp, Co, Ci, dptr(y), dptr(stats), dptr(ss), dptr(z), st), "sn2_lrb_block_fwd")
         else:
-            check(lib.sn2_lrb_fwd(dptr(x, torch.float32), wp, bp, R, rp, Co, Ci, dptr(y), dptr(stats), st), "sn2_lrb_fwd")
+            check(lib.sn2_lrb_fwd(dptr(x, torch.float32), ip, wp, bp, R, rp, Co, Ci, dptr(y), dptr(stats), st), "sn2_lrb_fwd")
             torch.distributed.all_reduce(stats, group=group)
             check(lib.sn2_bn_finalize(dptr(stats), gp, btp, float(bn.eps), float(bn.momentum), rm, rv, nbt, dptr(ss), Co, st),
                   "sn2_bn_finalize")
-            check(lib.sn2_bn_apply(dptr(y), dptr(ss), R, rp, Co, dptr(z), st), "sn2_bn_apply")
-        ops._count(5)
+            if apply:
+                check(lib.sn2_bn_apply(dptr(y), dptr(ss), R, rp, Co, dptr(z), st), "sn2_bn_apply")
+        ops._count(5 if apply else 4)
         ctx.save_for_backward(x, y, weight, ss, stats)
-        ctx.group, ctx.rows = group, rows
-        return z
+        ctx.group, ctx.rows, ctx.in_ss = group, rows, in_ss
+        if apply:
+            return z
+        ctx.mark_non_differentiable(ss)
+        return y, ss
 
     @staticmethod
-    def backward(ctx, dz):
+    def backward(ctx, dz, _dss=None):
         lib = _lib.load()
         x, y, weight, ss, stats = ctx.saved_tensors
+        ip = dptr(ctx.in_ss, torch.float32)
         dz = _c(dz)
         if dz.data_ptr() % 16:  # a view into a larger gradient buffer: the kernels fetch 16-byte aligned tiles
             dz = dz.clone()
@@ -247,17 +259,17 @@ class LinReluBN(torch.autograd.Function):
         wp, st, rp = dptr(_c(weight), torch.float32), stream_ptr(), dptr(ctx.rows, torch.int32)
         dgp, dbp = ctypes.c_void_p(dgb.data_ptr()), ctypes.c_void_p(dgb.data_ptr() + 4 * Co)
         if ctx.group is None:
-            check(lib.sn2_lrb_block_bwd(dptr(dz, torch.float32), dptr(y), dptr(x), wp, dptr(ss), dptr(stats), R, rp, Co, Ci, dptr(sums),
+            check(lib.sn2_lrb_block_bwd(dptr(dz, torch.float32), dptr(y), dptr(x), ip, wp, dptr(ss), dptr(stats), R, rp, Co, Ci, dptr(sums),
                                         dgp, dbp, dptr(dx), dptr(partial), LinReluBN.NBLK, dptr(dW), dptr(db), st),
                   "sn2_lrb_block_bwd")
         else:
             check(lib.sn2_lrb_bwd_reduce(dptr(dz, torch.float32), dptr(y), R, rp, Co, dptr(sums), st), "sn2_lrb_bwd_reduce")
             check(lib.sn2_bn_param_grad(dptr(sums), dptr(ss), Co, dgp, dbp, st), "sn2_bn_param_grad")  # this rank's sums
             torch.distributed.all_reduce(sums, group=ctx.group)
-            check(lib.sn2_lrb_bwd(dptr(dz), dptr(y), dptr(x), wp, dptr(ss), dptr(sums), dptr(stats), R, rp, Co, Ci, dptr(dx),
+            check(lib.sn2_lrb_bwd(dptr(dz), dptr(y), dptr(x), ip, wp, dptr(ss), dptr(sums), dptr(stats), R, rp, Co, Ci, dptr(dx),
                                   dptr(partial), LinReluBN.NBLK, dptr(dW), dptr(db), st), "sn2_lrb_bwd")
         ops._count(5)
-        return dx, dW, db, dgb[0], dgb[1], None, None
+        return dx, dW, db, dgb[0], dgb[1], None, None, None, None
 
 
 def _sync_group(bn):
@@ -290,19 +302,29 @@ def tall_linear(lin, x):
     return lin(x)
 
 
-def run_mlp(seq, x, rows=None):
+def run_mlp(seq, x, rows=None, defer_last: bool = False):
     """Apply a reference MLP (Sequential of (Linear, ReLU, BatchNorm1d) blocks).  Blocks that see >= 65 536 rows in
-    training run as the fused LinReluBN (SN2_FUSED_MLP=0 -> the torch modules, with TallLinear where it pays).
-    rows: device int32 [1] live row count when x is a fixed-capacity buffer (graph replay); needs the fused blocks."""
+    training run as the fused LinReluBN (SN2_FUSED_MLP=0 -> the torch modules, with TallLinear where it pays); between
+    two fused blocks the BatchNorm transform is not materialised (the consumer applies it on load).
+    rows: device int32 [1] live row count when x is a fixed-capacity buffer (graph replay); needs the fused blocks.
+    defer_last: return (y, ss) instead of z when the last block is fused -- for SegmentMax(y, rowptr, ss); ss is
+    None when the last block was not fused (then y is the finished output)."""
     lib = _lib.load()
     import os
     fused = os.environ.get("SN2_FUSED_MLP", "1") == "1"
     tall = os.environ.get("SN2_TALL_LINEAR", "1") == "1"
-    for block in seq:
+    defer_ok = os.environ.get("SN2_DEFER_BN", "1") == "1"
+    blocks = list(seq)
+    fusable = [fused and x.shape[0] >= 65536 and _fusable_block(lib, b, x) for b in blocks]
+    in_ss = None
+    for i, block in enumerate(blocks):
         lin = block[0]
-        if fused and x.shape[0] >= 65536 and _fusable_block(lib, block, x):
+        if fusable[i]:
             bn = block[2]
-            x = LinReluBN.apply(x, lin.weight, lin.bias, bn.weight, bn.bias, bn, rows)
+            last = i + 1 == len(blocks)
+            defer = defer_ok and ((not last and fusable[i + 1]) or (last and defer_last))
+            res = LinReluBN.apply(x, lin.weight, lin.bias, bn.weight, bn.bias, bn, rows, in_ss, not defer)
+            x, in_ss = res if defer else (res, None)
             continue
         if rows is not None:
             raise RuntimeError("sn2: a fixed-capacity edge buffer needs the fused Linear-ReLU-BatchNorm blocks")
@@ -313,4 +335,4 @@ def run_mlp(seq, x, rows=None):
             x = lin(x)
         for layer in list(block)[1:]:
             x = layer(x)
-    return x
+    return (x, in_ss) if defer_last else x

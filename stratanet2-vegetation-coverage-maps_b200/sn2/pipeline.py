@@ -354,8 +354,11 @@ def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num
     nbr1, w1, nbr2, w2, plot_ptr = S.nbr1, S.w1, S.nbr2, S.w2, S.plot_ptr
     rows1, rows2 = getattr(S, "rows1", None), getattr(S, "rows2", None)  # device edge counts of fixed-capacity lists
 
-    x1, _ = SegmentMax.apply(run_mlp(sa1.conv.local_nn, EdgeMsg.apply(feat0, pos0, pos1, rowptr1, col1, rows1), rows1), rowptr1)
-    x2, _ = SegmentMax.apply(run_mlp(sa2.conv.local_nn, EdgeMsg.apply(x1, pos1, pos2, rowptr2, col2, rows2), rows2), rowptr2)
+    # the last BatchNorm of each message MLP is applied inside the max aggregation (no pass of its own)
+    y1, ss1 = run_mlp(sa1.conv.local_nn, EdgeMsg.apply(feat0, pos0, pos1, rowptr1, col1, rows1), rows1, defer_last=True)
+    x1, _ = SegmentMax.apply(y1, rowptr1, ss1)
+    y2, ss2 = run_mlp(sa2.conv.local_nn, EdgeMsg.apply(x1, pos1, pos2, rowptr2, col2, rows2), rows2, defer_last=True)
+    x2, _ = SegmentMax.apply(y2, rowptr2, ss2)
     g, _ = SegmentMax.apply(model.sa3_module.nn(torch.cat([x2, pos2[:, :3]], dim=1)), plot_ptr)
     f3 = model.fp3_module.nn(torch.cat([InterpPlot.apply(g, pos2, M2), x2], dim=1))
     f2 = run_mlp(model.fp2_module.nn, torch.cat([Interp3.apply(f3, nbr2, w2), x1], dim=1))
@@ -415,7 +418,8 @@ class GraphedTrainStep:
     (`rows_dev` in include/sn2.h), so all shapes inside the graph are static.  If a batch exceeds the capacity the
     graph is re-captured with a larger one.  `step_fn` must not synchronise with the host (no .item(), no printing
     of tensors); the optimizer must be capture-safe (e.g. torch.optim.Adam(..., capturable=True)); BatchNorm must
-    not be SyncBatchNorm (single process).  The three warm-up executions that capture needs are rolled back
+    not be SyncBatchNorm (single process).  Python numbers read inside `step_fn` (learning rate, loss weights) are
+    baked in: use tensors updated in place, or `recapture()`.  The three warm-up executions that capture needs are rolled back
     (parameters, buffers and optimizer state are restored), so results match the eager loop step for step.
     Every tensor value of the batch dict (xyz, cloud, targets ...) is copied into a static buffer of the same shape;
     all batches must therefore have the same shapes."""
@@ -483,6 +487,12 @@ class GraphedTrainStep:
         self.launches_per_replay = ops.LAUNCHES - l0  # kernels of libsn2_b200 inside the graph (torch's come on top)
         self.captures += 1
 
+    def recapture(self):
+        """Drop the captured graph (call after changing optimizer hyper-parameters held as Python numbers, e.g. a
+        learning-rate scheduler step, or anything else that was baked in at capture)."""
+        torch.cuda.synchronize(self.device)
+        self.graph = None
+
     def _load_batch(self, batch, S=None):
         for k, v in batch.items():
             if k != "sn2_structure" and torch.is_tensor(v):
@@ -502,8 +512,10 @@ class GraphedTrainStep:
         if S.stream != cur:
             cur.wait_event(S.done)
         st = self.static_struct
-        if self.graph is None or S.col1.numel() > st.cap1 or S.col2.numel() > st.cap2:
-            self._capture(batch, S)
+        if (self.graph is None or S.col1.numel() > st.cap1 or S.col2.numel() > st.cap2 or (S.B, S.N) != (st.B, st.N)
+                or any(torch.is_tensor(v) and k in self.static_batch and tuple(v.shape) != tuple(self.static_batch[k].shape)
+                       for k, v in batch.items() if k != "sn2_structure")):
+            self._capture(batch, S)  # first call, edge capacity exceeded, or a batch of another shape (last of an epoch)
         else:
             st.load(S)
             self._load_batch(batch, S)

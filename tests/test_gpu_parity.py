@@ -586,6 +586,44 @@ def test_fused_lin_relu_bn_block(cuda_device, Ci, Co, R):
     assert int(bn.num_batches_tracked) == int(ref[2].num_batches_tracked) == 1
 
 
+def test_deferred_batchnorm_matches_materialised(cuda_device, monkeypatch):
+    """run_mlp(..., defer_last=True) + SegmentMax(y, rowptr, ss): the BatchNorm transforms applied on load by the next
+    block / by the max aggregation give the same outputs and gradients as the materialised z = y * scale + shift
+    (SN2_DEFER_BN=0), including negative gammas (max of the transform != transform of the max)."""
+    import copy
+
+    from model.point_net2 import MLP
+    from sn2.autograd_ops import SegmentMax, run_mlp
+
+    g = torch.Generator().manual_seed(11)
+    Q, deg = 3000, 30
+    E = Q * deg
+    rowptr = (torch.arange(Q + 1, dtype=torch.int32) * deg).to(cuda_device)
+    x = torch.randn(E, 11, generator=g).to(cuda_device)
+    dout = torch.randn(Q, 16, generator=g).to(cuda_device)
+    mlp = MLP([11, 16, 16]).to(cuda_device).train()
+    with torch.no_grad():
+        for blk in mlp:
+            blk[2].weight.copy_((torch.randn(16, generator=g) * 0.7 + 0.3).to(cuda_device))  # some negative
+            blk[2].bias.copy_((torch.randn(16, generator=g) * 0.2).to(cuda_device))
+    results = []
+    for defer in ("0", "1"):
+        monkeypatch.setenv("SN2_DEFER_BN", defer)
+        m = copy.deepcopy(mlp)
+        y, ss = run_mlp(m, x, defer_last=True)
+        assert (ss is not None) == (defer == "1")
+        out, arg = SegmentMax.apply(y, rowptr, ss)
+        out.backward(dout)
+        results.append((out.detach(), arg, [p.grad.clone() for p in m.parameters()], {k: v.clone() for k, v in m.state_dict().items()}))
+    (o0, a0, g0, s0), (o1, a1, g1, s1) = results
+    torch.testing.assert_close(o1, o0, rtol=1e-5, atol=1e-6)
+    assert (a1 != a0).float().mean() < 1e-3  # arg-max may flip between candidates that tie to the last bit
+    for p0, p1 in zip(g0, g1):
+        torch.testing.assert_close(p1, p0, rtol=2e-3, atol=2e-4)
+    for k in s0:
+        torch.testing.assert_close(s1[k], s0[k], rtol=1e-5, atol=1e-6, msg=lambda m_, k=k: f"{k}: {m_}")
+
+
 def test_structure_prefetcher_matches_plain_loop(cuda_device):
     """StructurePrefetcher (structural stage of batch i+1 on a side stream) yields the same forward results and
     gradients as the plain loop, batch by batch."""
