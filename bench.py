@@ -78,6 +78,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def wait_ready(self, timeout: float = 8.0):
+        """Block until nvidia-smi has produced its first sample.  Its start-up (NVML / driver initialisation, a few
+        hundred ms) perturbs kernel submission: a timed pass that began right after start() came out 1.3-3x slower
+        in about half of the runs.  Everything timed starts after this returns."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -340,6 +348,7 @@ def run_train(opts, cfg):
     timed_prefetch(dev_in, W, False)   # captures the graph (single GPU)
     sampler = ClockSampler(local)
     sampler.start()
+    sampler.wait_ready()
     timer = StageTimer()
     for _ in range(W):
         step(dev_in)
@@ -468,6 +477,7 @@ def run_parcel(opts, cfg):
         one_pass(pool_host, True)
         sampler = ClockSampler(local)
         sampler.start()
+        sampler.wait_ready()
         l0 = ops.LAUNCHES
         reps = max(1, opts.steps // 25)
         ms_res = timed(pool_dev, False, reps)
@@ -603,9 +613,19 @@ def main():
             step_e2e()
         sampler = ClockSampler(local)
         sampler.start()
+        sampler.wait_ready()
+        for _ in range(3):  # and a few untimed steps with the sampler running
+            step_resident()
         l0 = ops.LAUNCHES
+        nalloc = lambda: torch.cuda.memory_stats(dev).get("num_device_alloc", 0)  # noqa: E731  cudaMalloc calls so far
+        n0 = nalloc()
         ms_res, _ = timed(step_resident, opts.steps, False)
         launches = ops.LAUNCHES - l0
+        if os.environ.get("SN2_BENCH_TRACE") == "1":
+            ms_ = torch.cuda.memory_stats(dev)
+            print(f"[trace] serial resident pass: {ms_res / opts.steps:.3f} ms/step, cudaMalloc calls during the pass: {nalloc() - n0}, "
+                  f"reserved {torch.cuda.memory_reserved(dev) / 2**30:.1f} GiB, allocated {torch.cuda.memory_allocated(dev) / 2**30:.1f} GiB, "
+                  f"retries {ms_.get('num_alloc_retries')}, cudaFree calls {ms_.get('num_device_free')}", file=sys.stderr)
         ms_e2e, _ = timed(step_e2e, opts.steps, False)
         # same steps once more with per-stage events (instrumented pass: feeds stage_ms_per_step / roofline only)
         _, timer = timed(step_resident, opts.steps, True)
@@ -627,30 +647,42 @@ def main():
     use_graph = small and not opts.no_graph
     graph_launches = [0]
 
+    PIPE_REPS = 3
+
     def timed_pipe(batches, keep):
+        """K submits timed as one region, repeated PIPE_REPS times on the same pipeline; returns every pass (ms).
+        The reported value is the MEDIAN pass: a one-off allocator / driver stall (seen once in ~10 runs, a whole
+        pass 2-3x slower with clocks unchanged) then shows in `passes_ms_per_step` instead of in the headline."""
         pipe = InferencePipeline(net, args, depth=depth, graph=use_graph)
-        for i in range(max(W, depth + 1)):
+        for i in range(max(W, 20, depth + 1)):
             pipe.submit(batches[i % nrot], keep_on_device=keep)
         pipe.drain()
-        r0 = pipe.replays
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for i in range(opts.steps):
-            pipe.submit(batches[i % nrot], keep_on_device=keep)
-        for s_ in pipe.sets:
-            torch.cuda.current_stream().wait_stream(s_[0])
-        b.record()
-        barrier()
-        if use_graph:  # our kernels inside the replayed graphs (counted at capture)
-            graph_launches[0] = (pipe.replays - r0) * pipe.graphs[0][3]
-        return a.elapsed_time(b)
+        out = []
+        for _ in range(PIPE_REPS):
+            r0 = pipe.replays
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(opts.steps):
+                pipe.submit(batches[i % nrot], keep_on_device=keep)
+            for s_ in pipe.sets:
+                torch.cuda.current_stream().wait_stream(s_[0])
+            b.record()
+            barrier()
+            if use_graph:  # our kernels inside the replayed graphs (counted at capture)
+                graph_launches[0] = (pipe.replays - r0) * pipe.graphs[0][3]
+            out.append(a.elapsed_time(b))
+        return out
 
     ms_pipe_res = ms_pipe_e2e = None
+    pipe_passes = None
     if opts.pipeline:
         with torch.no_grad():
-            ms_pipe_res = timed_pipe(rot_dev, True)
-            ms_pipe_e2e = timed_pipe(rot_host, False)
+            res_passes = timed_pipe(rot_dev, True)
+            e2e_passes = timed_pipe(rot_host, False)
+        ms_pipe_res, ms_pipe_e2e = float(np.median(res_passes)), float(np.median(e2e_passes))
+        pipe_passes = {"resident": [round(v / opts.steps, 4) for v in res_passes], "e2e": [round(v / opts.steps, 4) for v in e2e_passes],
+                       "reported": "median pass"}
 
     t = torch.tensor([ms_res, ms_e2e, ms_pipe_res or 0.0, ms_pipe_e2e or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -704,6 +736,7 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["name"], "plots_per_gpu_per_step": B, "points_per_plot": N, "max_num_neighbors": 2000,
                    "batches_in_flight": depth or 1, "cuda_graph_per_batch": bool(use_graph and opts.pipeline),
+                   "passes_ms_per_step": pipe_passes,
                    "l2": ("inputs larger than L2: steps rotate over 4 distinct input batches (218 MB), K steps timed as one region"
                           if opts.pipeline else "flushed between timed steps (256 MiB write outside the event pairs)"),
                    "parallelism": f"plot-sharded x{world}"},

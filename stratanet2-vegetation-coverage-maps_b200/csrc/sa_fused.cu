@@ -209,7 +209,10 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
                 acc_init(W.l2, h2);
 #pragma unroll
                 for (int k = 0; k < SN2_C1; ++k) acc_step<0>(W.l2, h1[k], h2, k);
-                relu_bn(W.l2, h2);
+                // No ReLU / BatchNorm per edge: f(a) = fma(max(a, 0), s, t) is monotone in the pre-activation a, so
+                // max_j f(a_j) = f(max_j a_j) for s >= 0 and f(min_j a_j) for s < 0.  The launcher negates the
+                // second-layer weights and bias of the s < 0 channels (fma is odd: the accumulators come out exactly
+                // negated), so a running max serves both signs; f is applied once per centroid at the end.
 #pragma unroll
                 for (int o = 0; o < C; ++o) mx[o] = fmaxf(mx[o], h2[o]);
             }
@@ -423,6 +426,13 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
         if constexpr (LEVEL == 1) {
 #pragma unroll
             for (int o = 0; o < C; ++o) mx[o] = cnt > 0 ? warp_max(mx[o]) : 0.f;
+            if constexpr (!TC) {  // streaming / redo kernels track the (sign-adjusted) pre-activation: finish it here
+#pragma unroll
+                for (int o = 0; o < C; ++o) {
+                    const float sc = W.l2.s[o], a = sc < 0.f ? -mx[o] : mx[o];
+                    mx[o] = cnt > 0 ? fmaf(fmaxf(a, 0.f), sc, W.l2.t[o]) : 0.f;
+                }
+            }
             if (lane == 0) {
                 float4 *o4 = reinterpret_cast<float4 *>(out + row * C);
 #pragma unroll
@@ -461,6 +471,15 @@ static int launch_sa_fused(const float *grid_hdr, const int *cell_start, const f
 {
     typename SAEdge<LEVEL>::W w;
     if (int rc = load_weights(w, w_host, nw)) return rc;
+    typename SAEdge<LEVEL>::W ws = w;  // SIMT kernels of level 1: second layer negated where the BatchNorm scale is negative
+    if constexpr (LEVEL == 1) {
+        for (int o = 0; o < SN2_C1; ++o) {
+            if (ws.l2.s[o] < 0.f) {
+                ws.l2.b[o] = -ws.l2.b[o];
+                for (int k = 0; k < SN2_C1; ++k) ws.l2.w[k][o] = -ws.l2.w[k][o];
+            }
+        }
+    }
     const long long P = (long long)B * N;
     zero_int_kernel<<<1, 1, 0, st>>>(ovf);
     sa_pre_kernel<LEVEL><<<(unsigned)((P + 127) / 128), 128, 0, st>>>(reinterpret_cast<const float4 *>(pos4), feat, P, w,
@@ -488,7 +507,7 @@ static int launch_sa_fused(const float *grid_hdr, const int *cell_start, const f
     if (!(LEVEL == 1 && tc) && !exact_only) {
         auto kern = sa_fused_kernel<LEVEL, false>;
         kern<<<grid, SF_WARPS * 32, smem_ring, st>>>(grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4),
-                                                     reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, 0, w,
+                                                     reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, 0, ws,
                                                      out, cnt_out, ovf);
         SN2_LAUNCH_CHECK("sa_fused_kernel");
     }
@@ -499,7 +518,7 @@ static int launch_sa_fused(const float *grid_hdr, const int *cell_start, const f
         SN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sa_fused attr");
         kern<<<148 * 2, SF_WARPS * 32, smem, st>>>(grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4),
                                                    reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, words,
-                                                   w, out, cnt_out, ovf);
+                                                   ws, out, cnt_out, ovf);
         SN2_LAUNCH_CHECK("sa_fused_kernel<redo>");
     }
     return SN2_OK;

@@ -557,8 +557,12 @@ class InferencePipeline:
         mk = lambda: torch.cuda.Stream(device=self.device)  # noqa: E731
         self.sets = [(mk(), mk(), mk()) for _ in range(depth)]
         # the head of each batch's chain (copies, ingest, FPS level 1: one SM per plot for ~40 % of the latency) on a
-        # high-priority stream, so that its CTAs do not queue behind the wide kernels of the batches ahead of it
-        self.heads = [torch.cuda.Stream(device=self.device, priority=-1) if os.environ.get("SN2_FPS_PRIORITY", "1") == "1" else None
+        # stream of its own, so that it starts as soon as the inputs are there instead of behind the slot's main stream
+        # Measured over 12 passes each (tools/scratch): a head stream at NORMAL priority gives the best end-to-end time
+        # (3.25 ms / batch vs 3.46 without it) and a stable resident time; at high priority it is no faster and the
+        # resident pass occasionally degrades (3 slots x 64 one-SM FPS CTAs can then take every SM at once).
+        mode = os.environ.get("SN2_FPS_PRIORITY", "2")  # 1: high-priority head stream, 2: normal priority, 0: none
+        self.heads = [torch.cuda.Stream(device=self.device, priority=-1 if mode == "1" else 0) if mode in ("1", "2") else None
                       for _ in range(depth)]
         self.done = [None] * depth
         self.out = [None] * depth

@@ -31,11 +31,11 @@ for Ci, Co, R, need_dx in ((11, 16, 4_000_000, False), (16, 16, 4_000_000, True)
     dx = torch.empty_like(x) if need_dx else None
     nblk = LinReluBN.NBLK
     partial = torch.empty(nblk, Co * (Ci + 1), device=dev); dW = torch.empty_like(W); db = torch.empty(Co, device=dev)
-    fwd = lambda: lib.sn2_lrb_fwd(dptr(x), dptr(W), dptr(b), R, None, Co, Ci, dptr(y), dptr(stats), st)
+    fwd = lambda: lib.sn2_lrb_fwd(dptr(x), None, dptr(W), dptr(b), R, None, Co, Ci, dptr(y), dptr(stats), st)
     fin = lambda: lib.sn2_bn_finalize(dptr(stats), dptr(gamma), dptr(beta), 1e-5, 0.1, None, None, None, dptr(ss), Co, st)
     app = lambda: lib.sn2_bn_apply(dptr(y), dptr(ss), R, None, Co, dptr(z), st)
     red = lambda: lib.sn2_lrb_bwd_reduce(dptr(dz), dptr(y), R, None, Co, dptr(sums), st)
-    bwd = lambda: lib.sn2_lrb_bwd(dptr(dz), dptr(y), dptr(x), dptr(W), dptr(ss), dptr(sums), dptr(stats), R, None, Co, Ci, dptr(dx),
+    bwd = lambda: lib.sn2_lrb_bwd(dptr(dz), dptr(y), dptr(x), None, dptr(W), dptr(ss), dptr(sums), dptr(stats), R, None, Co, Ci, dptr(dx),
                                   dptr(partial), nblk, dptr(dW), dptr(db), st)
     assert fwd() == 0 and fin() == 0 and app() == 0 and red() == 0 and bwd() == 0
     rows = (("lrb_fwd", fwd, Ci + Co), ("bn_apply", app, 2 * Co), ("bwd_reduce", red, 2 * Co),
