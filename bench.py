@@ -589,6 +589,11 @@ def main():
         timer = StageTimer() if with_timer else None
         evs = []
         barrier()
+        import gc
+        gc_was = gc.isenabled()
+        if os.environ.get("SN2_BENCH_GC", "0") != "1":
+            gc.collect()
+            gc.disable()  # as timeit does: a full collection is a 50-200 ms host pause in the middle of a step
         for _ in range(steps):
             flush.fill_(1)  # L2 flush between timed iterations (outside the event pair)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -600,7 +605,13 @@ def main():
             b.record()
             evs.append((a, b))
         barrier()
-        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        if gc_was:
+            gc.enable()
+        per = [a.elapsed_time(b) for a, b in evs]
+        total_ms = sum(per)
+        if os.environ.get("SN2_BENCH_TRACE") == "1":
+            print(f"[trace] per-step ms: median {float(np.median(per)):.3f}, max {max(per):.3f}, "
+                  f"steps > 1.5x median: {[round(v, 2) for v in per if v > 1.5 * float(np.median(per))]}", file=sys.stderr)
         return total_ms, timer
 
     with torch.no_grad():
@@ -614,8 +625,10 @@ def main():
         sampler = ClockSampler(local)
         sampler.start()
         sampler.wait_ready()
-        for _ in range(3):  # and a few untimed steps with the sampler running
+        t_pre = time.perf_counter()
+        while time.perf_counter() - t_pre < float(os.environ.get("SN2_BENCH_SETTLE_S", "1.0")):  # untimed, sampler running
             step_resident()
+            torch.cuda.synchronize()
         l0 = ops.LAUNCHES
         nalloc = lambda: torch.cuda.memory_stats(dev).get("num_device_alloc", 0)  # noqa: E731  cudaMalloc calls so far
         n0 = nalloc()

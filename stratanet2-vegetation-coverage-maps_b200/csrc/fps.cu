@@ -668,6 +668,7 @@ extern "C" int sn2_fps_algo(const float *pos4, int B, int N, int M, const int *s
         if (algo == SN2_FPS_BRUTE) return SN2_EUNSUPPORTED;
         return launch_fps_cluster4(p, B, N, M, start, idx_out, po, st);
     }
+    if (algo == SN2_FPS_CLUSTER4) return launch_fps_cluster4(p, B, N, M, start, idx_out, po, st);
     if (algo == SN2_FPS_BUCKETED) return dispatch_fps_bucket<1>(p, B, N, M, start, idx_out, po, st);
     if (algo == SN2_FPS_BUCKETED_SPEC4) return dispatch_fps_bucket<4>(p, B, N, M, start, idx_out, po, st);
     if (algo != SN2_FPS_BRUTE) return SN2_EINVAL;

@@ -65,7 +65,7 @@ def ingest(xyz: torch.Tensor, cloud: torch.Tensor):
     return pos4, feat
 
 
-FPS_AUTO, FPS_BRUTE, FPS_BUCKETED, FPS_BUCKETED_SPEC4 = 0, 1, 2, 3
+FPS_AUTO, FPS_BRUTE, FPS_BUCKETED, FPS_BUCKETED_SPEC4, FPS_CLUSTER4 = 0, 1, 2, 3, 4
 
 
 def fps_dense(pos4: torch.Tensor, B: int, N: int, M: int, start: torch.Tensor | None = None, algo: int = FPS_AUTO):

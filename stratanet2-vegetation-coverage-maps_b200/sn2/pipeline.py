@@ -87,14 +87,18 @@ def _packed(model) -> dict:
     return cache[1]
 
 
+_PARKED: list = []  # (event, tensors) of recent forward_eval calls without a caller-managed keep list
+
+
 def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_neighbors: int = 2000,
                  trace: ForwardTrace | None = None, timer=None, side_streams=None, head_stream=None, keep: list | None = None):
     """xyz (B,3,N), cloud (B,10,N) fp32 (host or device) -> coverages (B*N,4), proba (B*N,4) on device.
     head_stream: optional (high-priority) stream for the head of the dependency chain -- input copies, ingest, the
     raw-point grid and FPS level 1 -- when several batches are in flight (InferencePipeline).
     keep: when given, tensors that cross streams are appended to it and the CALLER keeps them alive until the batch
-    has finished, instead of Tensor.record_stream (whose deferred frees make the allocator's behaviour timing
-    dependent)."""
+    has finished; otherwise they are parked in a small module-level queue until an event recorded at the end of this
+    call has completed.  Either way Tensor.record_stream is avoided: its deferred frees kept the allocator calling
+    cudaMalloc in steady state (20-80 calls per 50 forwards) and made step times bimodal."""
     if cloud.dim() != 3 or xyz.dim() != 3 or xyz.shape[1] != 3 or cloud.shape[0] != xyz.shape[0] \
             or cloud.shape[2] != xyz.shape[2]:
         raise RuntimeError("PointNet2.forward: expected xyz (B,3,N) and cloud (B,F,N)")
@@ -108,6 +112,11 @@ def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_
     main = torch.cuda.current_stream(device)
     side_a, side_b = side_streams if side_streams is not None else _side_streams(device)
     head = head_stream if head_stream is not None else main
+    parked = None
+    if keep is None:
+        keep = parked = []
+        while _PARKED and _PARKED[0][0].query():  # forwards whose GPU work has finished release their tensors
+            _PARKED.pop(0)
 
     def fork(stream):
         ev = torch.cuda.Event()
@@ -118,11 +127,7 @@ def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_
         ev = torch.cuda.Event()
         ev.record(stream)
         main.wait_event(ev)
-        if keep is not None:
-            keep.extend(tensors)
-        else:
-            for t in tensors:
-                t.record_stream(main)
+        keep.extend(tensors)
 
     M1 = ops.m_of(N, sa1.ratio)
     M2 = ops.m_of(M1, sa2.ratio)
@@ -173,6 +178,15 @@ def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_
         cov, proba = ops.fp1_head_fwd(f2, nbr1, w1, feat0, W["fp1"],
                                       tensor_core=bool(getattr(model, "sn2_fp_tensor_core", FP_TENSOR_CORE_DEFAULT)))
 
+    if parked is not None:
+        # main-stream tensors read by the side streams (pos1 by fps2 / knn2, pos0 and the grid by knn1) and the side
+        # streams' outputs stay referenced until everything queued so far on main (which has joined both) is done
+        parked.extend((pos0, pos1, *grid0))
+        done = torch.cuda.Event()
+        done.record(main)
+        _PARKED.append((done, parked))
+        if len(_PARKED) > 8:  # the host is far ahead of the GPU: wait for the oldest instead of growing
+            _PARKED.pop(0)[0].synchronize()
     if trace is not None:
         trace.tensors.update(
             cloud_dev=cloud_d, pos0=pos0, feat0=feat0, idx1=idx1, pos1=pos1, rowptr1=rowptr1, col1=col1, x1=x1,
@@ -528,6 +542,18 @@ class GraphedTrainStep:
         return self.loss
 
 
+_SLOT_STREAMS: dict = {}
+
+
+def _slot_streams(device, slot: int, mode: str):
+    key = (torch.device(device).index, slot, mode)
+    if key not in _SLOT_STREAMS:
+        mk = lambda prio=0: torch.cuda.Stream(device=device, priority=prio)  # noqa: E731
+        head = mk(-1 if mode == "1" else 0) if mode in ("1", "2") else None
+        _SLOT_STREAMS[key] = (mk(), mk(), mk(), head)
+    return _SLOT_STREAMS[key]
+
+
 class InferencePipeline:
     """Batches in flight: `depth` independent stream sets, each running H2D -> forward -> both projections ->
     D2H for one batch.  FPS is a serial chain that occupies one SM per plot (64 of 148 SMs at config 2) for
@@ -554,16 +580,20 @@ class InferencePipeline:
         self.graphs = [None] * depth       # per slot: (CUDAGraph, static xyz, static cloud, launches inside the graph)
         self.replays = 0
         self.device = torch.device("cuda", model.cuda_device)
-        mk = lambda: torch.cuda.Stream(device=self.device)  # noqa: E731
-        self.sets = [(mk(), mk(), mk()) for _ in range(depth)]
-        # the head of each batch's chain (copies, ingest, FPS level 1: one SM per plot for ~40 % of the latency) on a
-        # stream of its own, so that it starts as soon as the inputs are there instead of behind the slot's main stream
-        # Measured over 12 passes each (tools/scratch): a head stream at NORMAL priority gives the best end-to-end time
-        # (3.25 ms / batch vs 3.46 without it) and a stable resident time; at high priority it is no faster and the
-        # resident pass occasionally degrades (3 slots x 64 one-SM FPS CTAs can then take every SM at once).
+        # Streams come from a per-device cache shared by every pipeline object: the caching allocator keeps one pool
+        # per stream, so fresh streams per pipeline (e.g. one pipeline per parcel) would re-cudaMalloc every
+        # intermediate during their first batches (measured: a 6 561-plot parcel pass 0.30 s instead of 0.19 s).
+        # The head of each batch's chain (copies, ingest, FPS level 1: one SM per plot for ~40 % of the latency) runs
+        # on a stream of its own, so that it starts as soon as the inputs are there instead of behind the slot's main
+        # stream.  Measured over 12 passes each: at NORMAL priority this gives the best end-to-end time (3.25 ms /
+        # batch vs 3.46 without it) and a stable resident time; at high priority it is no faster and the resident
+        # pass occasionally degrades (3 slots x 64 one-SM FPS CTAs can then take every SM at once).
         mode = os.environ.get("SN2_FPS_PRIORITY", "2")  # 1: high-priority head stream, 2: normal priority, 0: none
-        self.heads = [torch.cuda.Stream(device=self.device, priority=-1 if mode == "1" else 0) if mode in ("1", "2") else None
-                      for _ in range(depth)]
+        self.sets, self.heads = [], []
+        for slot in range(depth):
+            main, a, b, head = _slot_streams(self.device, slot, mode)
+            self.sets.append((main, a, b))
+            self.heads.append(head)
         self.done = [None] * depth
         self.out = [None] * depth
         self.keep = [[] for _ in range(depth)]  # per slot: tensors alive until the slot's batch has finished
