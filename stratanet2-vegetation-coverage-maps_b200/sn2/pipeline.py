@@ -185,7 +185,10 @@ def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_
         done = torch.cuda.Event()
         done.record(main)
         _PARKED.append((done, parked))
-        if len(_PARKED) > 8:  # the host is far ahead of the GPU: wait for the oldest instead of growing
+        if len(_PARKED) > 3:
+            # the host is three forwards ahead of the GPU: wait for the oldest instead of running further ahead.
+            # A bounded depth keeps the allocator pools at a fixed size after the first few calls; letting them grow
+            # later costs a cudaMalloc in the middle of a forward (measured: single 100-300 ms steps).
             _PARKED.pop(0)[0].synchronize()
     if trace is not None:
         trace.tensors.update(
