@@ -591,7 +591,10 @@ class InferencePipeline:
         # stream.  Measured over 12 passes each: at NORMAL priority this gives the best end-to-end time (3.25 ms /
         # batch vs 3.46 without it) and a stable resident time; at high priority it is no faster and the resident
         # pass occasionally degrades (3 slots x 64 one-SM FPS CTAs can then take every SM at once).
-        mode = os.environ.get("SN2_FPS_PRIORITY", "2")  # 1: high-priority head stream, 2: normal priority, 0: none
+        # Small batches replayed as graphs are the opposite case: no contention for SMs, but many streams share few
+        # hardware queues and a one-CTA FPS kernel (1.1 ms) blocks whatever is queued behind it; with the heads at
+        # high priority (queues of their own) a stream of single plots runs at 7.1 k plots/s, at normal priority 3.9 k.
+        mode = os.environ.get("SN2_FPS_PRIORITY", "1" if graph else "2")  # 1: high-priority head, 2: normal priority, 0: none
         self.sets, self.heads = [], []
         for slot in range(depth):
             main, a, b, head = _slot_streams(self.device, slot, mode)
