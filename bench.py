@@ -677,7 +677,6 @@ def main():
     if small and opts.pipeline == 3 and not opts.no_graph:
         depth = 12
     use_graph = small and not opts.no_graph
-    graph_launches = [0]
 
     PIPE_REPS = 3
 
@@ -691,7 +690,6 @@ def main():
         pipe.drain()
         out = []
         for _ in range(PIPE_REPS):
-            r0 = pipe.replays
             with no_gc():  # entered (and collected once) BEFORE the region starts
                 barrier()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -702,8 +700,6 @@ def main():
                     torch.cuda.current_stream().wait_stream(s_[0])
                 b.record()
                 barrier()
-            if use_graph:  # our kernels inside the replayed graphs (counted at capture)
-                graph_launches[0] = (pipe.replays - r0) * pipe.graphs[0][3]
             out.append(a.elapsed_time(b))
         return out
 
