@@ -140,3 +140,52 @@ def test_library_exports_every_declared_symbol():
     assert loaded.sn2_abi_version() == 1
     assert b"invalid" in loaded.sn2_error_string(-1)
     assert loaded.sn2_fps_max_points() >= 16384
+
+
+def test_run_mlp_dispatch_rules(monkeypatch):
+    """Host logic of sn2.autograd_ops.run_mlp (no GPU: the library and the fused Function are stubbed): which blocks
+    run fused, where the BatchNorm transform is deferred to the consumer, and the fixed-capacity guard."""
+    import types
+
+    from model.point_net2 import MLP
+    from sn2 import autograd_ops as ao
+
+    supported = {(11, 16), (16, 16), (19, 32), (80, 34), (42, 34)}
+    fake = types.SimpleNamespace(sn2_lrb_supported=lambda co, ci: int((ci, co) in supported),
+                                 sn2_linear_wgrad_supported=lambda co, ci: 0)
+    monkeypatch.setattr(ao._lib, "load", lambda *a, **k: fake)
+    calls = []
+
+    def fake_apply(x, w, b, gamma, beta, bn, rows=None, in_ss=None, apply=True):
+        calls.append(dict(ci=w.shape[1], co=w.shape[0], rows=rows, in_ss=in_ss, apply=apply))
+        y = torch.zeros(x.shape[0], w.shape[0])
+        return y if apply else (y, torch.full((4 * w.shape[0],), float(len(calls))))
+
+    monkeypatch.setattr(ao.LinReluBN, "apply", staticmethod(fake_apply))
+    mlp = MLP([11, 16, 16]).train()
+    x = torch.zeros(65536, 11)
+
+    y, ss = ao.run_mlp(mlp, x, defer_last=True)         # both fused; BN 1 applied by block 2, BN 2 by the caller
+    assert [c["apply"] for c in calls] == [False, False] and calls[0]["in_ss"] is None
+    assert calls[1]["in_ss"] is not None and float(calls[1]["in_ss"][0]) == 1.0 and float(ss[0]) == 2.0
+    calls.clear()
+    z = ao.run_mlp(mlp, x)                               # the last transform is materialised for a torch consumer
+    assert [c["apply"] for c in calls] == [False, True] and torch.is_tensor(z)
+    calls.clear()
+    monkeypatch.setenv("SN2_DEFER_BN", "0")
+    y, ss = ao.run_mlp(mlp, x, defer_last=True)
+    assert [c["apply"] for c in calls] == [True, True] and ss is None
+    monkeypatch.delenv("SN2_DEFER_BN")
+    calls.clear()
+    ao.run_mlp(mlp, torch.zeros(1000, 11))               # few rows: the model's own torch modules
+    assert calls == []
+    ao.run_mlp(mlp.eval(), x)                            # eval-mode BatchNorm is never fused
+    assert calls == []
+    mlp.train()
+    odd = MLP([11, 24]).train()                          # a width the kernels do not cover
+    assert ao.run_mlp(odd, x).shape == (65536, 24) and calls == []
+    with pytest.raises(RuntimeError, match="fixed-capacity"):
+        ao.run_mlp(odd, x, rows=torch.zeros(1, dtype=torch.int32))
+    rows = torch.zeros(1, dtype=torch.int32)
+    ao.run_mlp(mlp, x, rows=rows)
+    assert all(c["rows"] is rows for c in calls) and len(calls) == 2
