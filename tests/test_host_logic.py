@@ -189,3 +189,41 @@ def test_run_mlp_dispatch_rules(monkeypatch):
     rows = torch.zeros(1, dtype=torch.int32)
     ao.run_mlp(mlp, x, rows=rows)
     assert all(c["rows"] is rows for c in calls) and len(calls) == 2
+
+
+def test_graphed_step_rolls_back_its_warmup():
+    """GraphedTrainStep._snapshot / _restore (the roll-back around the warm-up executions of a capture): parameters,
+    buffers and pre-existing optimizer state come back, state created by the warm-up returns to zero."""
+    from sn2.pipeline import GraphedTrainStep
+
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.BatchNorm1d(3))
+    opt = torch.optim.Adam(net.parameters(), lr=0.1)
+    x = torch.randn(16, 4)
+
+    def one_step():
+        opt.zero_grad()
+        net(x).pow(2).mean().backward()
+        opt.step()
+
+    gs = GraphedTrainStep(net, lambda b: None, optimizer=opt, device=torch.device("cpu"))
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    snap = gs._snapshot()                                  # optimizer state still empty
+    one_step(); one_step()
+    gs._restore(snap)
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    for st in opt.state.values():
+        assert all(float(v.abs().sum()) == 0.0 for v in st.values() if torch.is_tensor(v))
+    one_step()                                             # now with real state: it must be restored, not zeroed
+    mid_params = {k: v.clone() for k, v in net.state_dict().items()}
+    mid_state = [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()} for st in opt.state.values()]
+    snap = gs._snapshot()
+    one_step(); one_step(); one_step()
+    gs._restore(snap)
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, mid_params[k]), k
+    for st, old in zip(opt.state.values(), mid_state):
+        for k, v in st.items():
+            if torch.is_tensor(v):
+                assert torch.equal(v, old[k]), k
