@@ -229,6 +229,83 @@ def test_fp1_head_tensor_core_parity(cuda_device, B, N):
     torch.testing.assert_close(proba_t, proba_s, rtol=1e-4, atol=1e-6)
 
 
+def test_full_size_properties_config2(cuda_device):
+    """BASELINE config 2 at its FULL size (64 plots x 16 384 points), checked through size-independent properties
+    instead of the oracle: FPS structure, exact ball-query sets on sampled centroids (same fp32 arithmetic), list
+    order / cap / self-inclusion on every edge, sub-batch independence (bitwise), and projections whose occupied
+    pixels and means follow from the per-point outputs."""
+    from model.project_to_2d import project_to_2d_rasters_batched, project_to_plotwise_coverages
+    from sn2 import ops
+    from sn2.pipeline import ForwardTrace
+
+    B, N, K = 64, 16384, 2000
+    args, net, _ = _make_models(N, cuda_device)
+    data = _plots(2, B, N, "plain")
+    with torch.no_grad():
+        tr = ForwardTrace()
+        cov, proba = net(data, trace=tr)
+        sub = {k: v[:4].contiguous() for k, v in data.items()}
+        cov_sub, proba_sub = net(sub)
+        pw = project_to_plotwise_coverages(cov, data["cloud"], args)
+        rs = project_to_2d_rasters_batched(data["cloud"], cov, args)
+    t = tr.tensors
+    M1 = t["M1"]
+    dev = cov.device
+    # sub-batch independence: plots do not see each other
+    assert torch.equal(cov_sub, cov[: 4 * N]) and torch.equal(proba_sub, proba[: 4 * N])
+    assert torch.isfinite(cov).all() and torch.isfinite(proba).all()
+    torch.testing.assert_close(proba.sum(1), torch.ones(B * N, device=dev), rtol=1e-5, atol=1e-5)
+    assert (cov >= 0).all() and (cov <= proba + 1e-7).all()          # coverage = proba * density, density in (0, 1)
+
+    # ---- FPS: starts at the first point, in-plot, no repeats, selection distance non-increasing ----------------
+    idx1 = t["idx1"].long().view(B, M1)
+    local = idx1 - torch.arange(B, device=dev)[:, None] * N
+    assert (local >= 0).all() and (local < N).all() and (local[:, 0] == 0).all()
+    assert (torch.sort(local, dim=1).values.diff(dim=1) > 0).all()
+    pos0, pos1 = t["pos0"][:, :3], t["pos1"][:, :3]
+    assert torch.equal(pos1, pos0[idx1.view(-1)])
+    tri = torch.triu(torch.ones(M1, M1, dtype=torch.bool, device=dev))  # j >= k masked out
+    for b in (0, 17, 63):
+        S = pos1[b * M1:(b + 1) * M1]
+        d2 = ((S[:, None, :] - S[None, :, :]) ** 2).sum(-1).masked_fill_(tri, float("inf"))
+        dk = d2.min(dim=1).values[1:]                                   # distance of sample k to samples < k
+        assert (dk[1:] <= dk[:-1] * (1 + 1e-6)).all()
+
+    # ---- ball query: every edge inside the radius, ascending, capped, self included; exact sets on a sample ----
+    rowptr, col = t["rowptr1"].long(), t["col1"].long()
+    cnt = rowptr.diff()
+    assert int(rowptr[-1]) == col.numel() and (cnt >= 1).all() and (cnt <= K).all()
+    rows = torch.repeat_interleave(torch.arange(B * M1, device=dev), cnt)
+    r2 = ops.r2_of(net.sa1_module.r)
+
+    def d2_exact(a, b_):                                                # the kernels' operation order, op by op in fp32
+        dx, dy, dz = a[:, 0] - b_[:, 0], a[:, 1] - b_[:, 1], a[:, 2] - b_[:, 2]
+        return (dx * dx + dy * dy) + dz * dz
+
+    assert (d2_exact(pos0[col], pos1[rows]) < r2).all()
+    assert (col // N == rows // M1).all()                               # neighbours come from the centroid's own plot
+    same = rows[1:] == rows[:-1]
+    assert (col.diff()[same] > 0).all()
+    own = torch.zeros(B * M1, dtype=torch.int32, device=dev).index_add_(0, rows, (col == idx1.view(-1)[rows]).int())
+    assert (own == 1).all()
+    g = torch.Generator().manual_seed(3)
+    for q in torch.randint(0, B * M1, (96,), generator=g).tolist():
+        b = q // M1
+        P = pos0[b * N:(b + 1) * N]
+        inside = torch.nonzero(d2_exact(P, pos1[q:q + 1].expand(N, 3)) < r2).view(-1)[:K] + b * N
+        assert torch.equal(col[rowptr[q]:rowptr[q + 1]], inside), q
+
+    # ---- projections: occupied raster pixels carry the max of their points; plot-wise = mean over occupied pixels ----
+    assert pw.shape == (B, 4) and rs.shape[0] == B
+    occ = ~torch.isnan(rs)
+    assert (occ[:, 0] == occ[:, 1]).all() and (occ[:, 0] == occ[:, 2]).all() and occ.any()
+    c3 = cov.view(B, N, 4)[:, :, [0, 2, 3]]
+    vmax = torch.where(occ, rs, torch.full_like(rs, -1.0)).flatten(1).max(dim=1).values.view(B, 1)  # per plot, over bands
+    assert (vmax.view(-1).float() <= c3.flatten(1).max(dim=1).values + 1e-7).all()
+    torch.testing.assert_close(pw[:, 1], 1.0 - pw[:, 0], rtol=1e-5, atol=1e-6)
+    assert (pw >= 0).all() and (pw <= 1).all()
+
+
 @pytest.mark.parametrize("B,N", [(1, 10000), (4, 4096)])
 def test_projections_parity(cuda_device, B, N):
     from model.project_to_2d import project_to_2d_rasters, project_to_plotwise_coverages, project_to_2d_rasters_batched
