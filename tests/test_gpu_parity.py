@@ -794,6 +794,48 @@ def test_graphed_train_step_matches_eager_loop(cuda_device):
         assert float(diff.max()) < 2.5e-3 + 2e-3 * float(v.abs().max()), (k, float(diff.max()))
 
 
+def test_full_size_training_makes_progress(cuda_device):
+    """BASELINE config 3 at its full size (32 plots x 10 000 points) as the user runs it -- StructurePrefetcher +
+    GraphedTrainStep, every fused block active -- checked through what does not need an oracle: finite losses that
+    go down, BatchNorm bookkeeping that advances once per step, and a single graph capture for a stream of batches
+    whose edge counts differ."""
+    from model.project_to_2d import project_to_plotwise_coverages
+    from sn2.pipeline import GraphedTrainStep, StructurePrefetcher
+
+    B, N, steps = 32, 10000, 16
+    args, net, _ = _make_models(N, cuda_device)
+    net.train()
+    for p in net.parameters():
+        p.grad = torch.zeros_like(p)
+    opt = torch.optim.Adam(net.parameters(), lr=5e-3, capturable=True)
+    g = torch.Generator().manual_seed(4)
+    gt = torch.rand(B, 4, generator=g)
+    batches = []
+    for i in range(4):                                     # four different batches, cycled
+        b = _plots(40 + i, B, N, "plain")
+        b["gt"] = gt
+        batches.append(b)
+
+    def step(batch):
+        opt.zero_grad(set_to_none=False)
+        cov, proba = net(batch)
+        pw = project_to_plotwise_coverages(cov, net.last_cloud_device, args)
+        loss = ((pw - batch["gt"]) ** 2).mean()
+        loss.backward()
+        opt.step()
+        return loss.detach()
+
+    gstep = GraphedTrainStep(net, step, optimizer=opt)
+    losses = [float(gstep(b)) for b in StructurePrefetcher(net, (batches[i % 4] for i in range(steps)))]
+    assert all(np.isfinite(losses)), losses
+    assert min(losses[-4:]) < 0.9 * max(losses[:4]), losses
+    assert gstep.captures == 1 and gstep.replays == steps
+    bn = net.sa1_module.conv.local_nn[0][2]
+    assert int(bn.num_batches_tracked) == steps
+    for prm in net.parameters():
+        assert torch.isfinite(prm).all()
+
+
 def _golden_paths():
     import glob
     import os
