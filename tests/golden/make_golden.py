@@ -60,5 +60,60 @@ def main():
         print(name, {k: v.shape for k, v in out.items() if not k.startswith("sd:")})
 
 
+TRAIN_CASES = {
+    "train_plain_b2_n2048": dict(config=3, B=2, N=2048, variant="plain"),
+}
+
+
+def train_loss(proba, pw, gt, pdf):
+    """The loss the training parity tests use (shape of learning/loss_functions.py: MAE on three coverages, a
+    likelihood term on the class probabilities, an entropy term), written with plain torch ops."""
+    mae = torch.sqrt((pw[:, [0, 2, 3]] - gt[:, [0, 2, 3]]) ** 2 + 1e-4).mean()
+    nll = -torch.log((proba[:, [0, 2, 3]].double() * pdf).sum(1) + 1e-6).mean().float()
+    p = proba[:, 2:]
+    ent = -(p * torch.log(p + 1e-6)).sum(1).mean()
+    return mae + 0.10 * nll + 0.04 * ent
+
+
+def main_train():
+    """Train-mode vectors: the reference's own PointNet2 under model.train() (BatchNorm batch statistics, dropout
+    switched off so that the step is deterministic), plot-wise projection, loss, backward.  Stored: inputs, initial
+    state_dict, loss, all 32 parameter gradients, the state_dict after the forward (running statistics)."""
+    assert reference_root() == "/root/reference", "golden vectors must come from the real reference tree"
+    pn2, p2d = load_reference()
+    for name, c in TRAIN_CASES.items():
+        args = default_args(subsample_size=c["N"])
+        args.drop = 0.0
+        torch.manual_seed(0)
+        net = pn2.PointNet2(args)
+        randomize_bn_(net)
+        net.drop = 0.0
+        net.train()
+        out = {}
+        for k, v in net.state_dict().items():
+            out["sd:" + k] = v.numpy().copy()
+        data = synth_batch(c["config"], c["B"], c["N"], c["variant"])
+        g = torch.Generator().manual_seed(9)
+        gt = torch.rand(c["B"], 4, generator=g)
+        z = data["xyz"][:, 2, :].reshape(-1, 1).double()
+        pdf = torch.cat([torch.exp(-z), 0.5 * torch.exp(-0.5 * (z - 1.0) ** 2), 0.1 + 0.05 * z], dim=1)
+        cov, proba = net(data)
+        pw = p2d.project_to_plotwise_coverages(cov, data["cloud"], args)
+        loss = train_loss(proba, pw, gt, pdf)
+        loss.backward()
+        out.update({"xyz": data["xyz"].numpy(), "cloud": data["cloud"].numpy(), "gt": gt.numpy(), "pdf": pdf.numpy(),
+                    "loss": loss.detach().numpy(), "cov": cov.detach().numpy(), "plotwise": pw.detach().numpy()})
+        for k, p in net.named_parameters():
+            out["grad:" + k] = p.grad.numpy().copy()
+        for k, v in net.state_dict().items():
+            out["after:" + k] = v.numpy().copy()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "loss", float(loss), "grads", sum(1 for k in out if k.startswith("grad:")))
+
+
 if __name__ == "__main__":
-    main()
+    if "--train" in sys.argv:
+        main_train()
+    else:
+        main()
+        main_train()

@@ -840,7 +840,51 @@ def _golden_paths():
     import glob
     import os
 
-    return sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+    return sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "case_*.npz")))
+
+
+def _golden_train_paths():
+    import glob
+    import os
+
+    return sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "train_*.npz")))
+
+
+@pytest.mark.parametrize("path", _golden_train_paths(), ids=lambda p: p.split("/")[-1][:-4])
+def test_cuda_training_step_reproduces_golden_vectors(cuda_device, path):
+    """The CUDA training path against vectors produced by the reference's own files in train mode (committed under
+    tests/golden/, generated by make_golden.py --train): loss, all 32 parameter gradients, running statistics."""
+    from model.point_net2 import PointNet2
+    from model.project_to_2d import project_to_plotwise_coverages
+    from sn2.config import default_args
+
+    z = np.load(path)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd:")}
+    data = {"xyz": torch.from_numpy(z["xyz"]), "cloud": torch.from_numpy(z["cloud"])}
+    B, _, N = data["cloud"].shape
+    args = default_args(subsample_size=N, cuda=cuda_device.index)
+    net = PointNet2(args)
+    net.load_state_dict(sd)
+    net.train()
+    cov, proba = net(data)
+    pw = project_to_plotwise_coverages(cov, data["cloud"], args)
+    loss = _train_loss(cov, proba, pw, torch.from_numpy(z["gt"]).to(cuda_device), torch.from_numpy(z["pdf"]).to(cuda_device))
+    loss.backward()
+    torch.testing.assert_close(loss.detach().cpu(), torch.from_numpy(z["loss"]), rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(cov.detach().cpu(), torch.from_numpy(z["cov"]), rtol=RTOL, atol=ATOL)
+    bad = []
+    for name, p in net.named_parameters():
+        want = torch.from_numpy(z["grad:" + name])
+        scale = want.abs().max().item() + 1e-12
+        err = (p.grad.cpu() - want).abs().max().item()
+        if err > 2e-3 * scale + 1e-7:
+            bad.append(f"{name}: max err {err:.3e} vs scale {scale:.3e}")
+    assert not bad, bad
+    for k, v in net.state_dict().items():
+        if v.is_floating_point():
+            torch.testing.assert_close(v.cpu(), torch.from_numpy(z["after:" + k]), rtol=RTOL, atol=2e-5, msg=k)
+        else:
+            assert int(v) == int(z["after:" + k]), k
 
 
 @pytest.mark.parametrize("path", _golden_paths(), ids=lambda p: p.split("/")[-1][:-4])
