@@ -203,7 +203,13 @@ def run_reference(opts, cfg):
 
     N = cfg["N"]
     plots = 8  # bounded sample: each step = 8 plots of the same workload (OpenMP over plots / queries)
-    torch.set_num_threads(os.cpu_count())
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm (rank 0 alone) is entitled to all host
+    # cores, so under torchrun the value is put back before the oracle's OpenMP runtime is loaded (torch's own pool
+    # is resized explicitly either way)
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        os.environ["OMP_NUM_THREADS"] = str(ncores)
+    torch.set_num_threads(ncores)
     kind, net, plotwise, raster, args = cpu_model(N)
     data = synth_batch(opts.config, plots, N)
     for _ in range(max(1, min(opts.warmup, 1))):
@@ -220,7 +226,7 @@ def run_reference(opts, cfg):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["name"], "plots_per_step": plots, "points_per_plot": N},
         "points_per_s": value * N,
-        "cpu_baseline": {"value": value, "unit": "plots/s", "cores": os.cpu_count(), "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "plots/s", "cores": ncores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "plots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
