@@ -156,8 +156,8 @@ int sn2_fp1_head_fwd_tc(const float *f2, const int *nbr, const float *w, const f
 /* ---- a12: plot-wise coverages.  Replaces project_to_plotwise_coverages (model/project_to_2d.py:7-55).
  * cloud (B,F,N) device (rows 0,1 = normalised x,y), pred [B*N,4].
  * out [B,4] = [low, 1-low, med, high] mean over occupied pixels.
- * Optional (NULL to skip): pix [B*N] int32 = px*(D+1) + py (px, py in [0, D]); pmax [B,3,D*D] fp32 (0 where empty);
- * parg [B,3,D*D] int32 GLOBAL point index of the per-pixel max (first index on ties; -1 empty). */
+ * Optional (NULL to skip): pix [B*N] int32 = px*(D+1) + py (px, py in [0, D]); pmax [B,3,(D+1)*(D+1)] fp32 (0 where empty),
+ * parg [B,3,(D+1)*(D+1)] int32 (both indexed like pix) GLOBAL point index of the per-pixel max (first index on ties; -1 empty). */
 int sn2_project_plotwise(const float *cloud, const float *pred, int B, int N, int F, int D, float *out,
                          int *pix, float *pmax, int *parg, void *stream);
 
@@ -190,7 +190,7 @@ int sn2_edge_msg_bwd(const float *dmsg, const int *col, long long E, const int *
 int sn2_segment_max_fwd(const float *vals, const float *ss, const int *rowptr, int Q, int C, float *out, int *arg,
                         void *stream);
 /* dvals [E,C] (zero-initialised) receives dout at the arg-max edges. */
-int sn2_segment_max_bwd(const float *dout, const int *arg, long long Q, int C, float *dvals, void *stream);
+int sn2_segment_max_bwd(const float *dout, const int *arg, long long Q, int C, long long E, float *dvals, void *stream);
 /* knn_interpolate, k=3 (model/point_net2.py:63): y [Q,C] = ((w0 x0 + w1 x1) + w2 x2) / ((w0 + w1) + w2). */
 int sn2_interp3_fwd(const float *x, int ldx, const int *nbr, const float *w, long long Q, int C, float *y,
                     void *stream);
@@ -200,7 +200,7 @@ int sn2_interp3_bwd(const float *dy, const int *nbr, const float *w, long long Q
 /* knn_interpolate, k=1 from the single plot vector at the origin (fp3): y [B*M,C] = (g[b] * w) / w. */
 int sn2_interp_plot_fwd(const float *g, const float *pos4, int B, int M, int C, float *y, void *stream);
 int sn2_interp_plot_bwd(const float *dy, const float *pos4, int B, int M, int C, float *dg, void *stream);
-/* backward of sn2_project_plotwise: dpred [B*N,4] (zero-initialised) from dout [B,4] and parg [B,3,D,D]. */
+/* backward of sn2_project_plotwise: dpred [B*N,4] (zero-initialised) from dout [B,4] and parg [B,3,D+1,D+1]. */
 int sn2_project_plotwise_bwd(const float *dout, const int *parg, int B, int D, float *dpred, void *stream);
 
 /* Weight / bias gradient of a Linear applied to E rows (E ~ millions, Co, Ci <= 64): dW [Co,Ci] = dy^T x,

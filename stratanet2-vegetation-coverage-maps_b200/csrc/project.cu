@@ -103,19 +103,18 @@ project_plotwise_kernel(const float *__restrict__ cloud, const float4 *__restric
             s_high += v2;
             cnt += 1.f;
         }
-        const int px = p / D1, py = p - px * D1;
-        if (px < D && py < D) {
-            const size_t o = (size_t)b * 3 * D * D + (size_t)px * D + py;
-            if (pmax) {
-                pmax[o] = v0;
-                pmax[o + (size_t)D * D] = v1;
-                pmax[o + 2 * (size_t)D * D] = v2;
-            }
-            if (parg) {
-                parg[o] = occ ? b * N + (int)(0xffffffffu - (unsigned)(k0 & 0xffffffffull)) : -1;
-                parg[o + (size_t)D * D] = occ ? b * N + (int)(0xffffffffu - (unsigned)(k1 & 0xffffffffull)) : -1;
-                parg[o + 2 * (size_t)D * D] = occ ? b * N + (int)(0xffffffffu - (unsigned)(k2 & 0xffffffffull)) : -1;
-            }
+        // aux arrays use the kernel's own (D+1) x (D+1) pixel frame (index = px*(D+1)+py, as `pix`): a point that
+        // lands in row / column D is counted by the forward mean, so the backward must see it too
+        const size_t o = (size_t)b * 3 * P + p;
+        if (pmax) {
+            pmax[o] = v0;
+            pmax[o + P] = v1;
+            pmax[o + 2 * (size_t)P] = v2;
+        }
+        if (parg) {
+            parg[o] = occ ? b * N + (int)(0xffffffffu - (unsigned)(k0 & 0xffffffffull)) : -1;
+            parg[o + P] = occ ? b * N + (int)(0xffffffffu - (unsigned)(k1 & 0xffffffffull)) : -1;
+            parg[o + 2 * (size_t)P] = occ ? b * N + (int)(0xffffffffu - (unsigned)(k2 & 0xffffffffull)) : -1;
         }
     }
     s_low = block_reduce_sum(s_low, sred, tid);

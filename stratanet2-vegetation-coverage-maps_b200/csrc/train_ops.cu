@@ -87,9 +87,18 @@ edge_msg_bwd_kernel(const float *__restrict__ dmsg, const int *__restrict__ col,
 // slots are merged with xor shuffles on (value, edge): larger value, then lower edge index.  WARPS = 1: one warp per
 // row (set-abstraction neighbourhoods, tens of edges); WARPS = 8: one CTA per row (global_max_pool: 32 rows of
 // hundreds of points), warps merged through shared memory.
+// NaN is the largest value (torch.max / torch_scatter propagate it); equal values -> lower edge index.  `e` always
+// stays a valid edge of the row, also when every value is -inf or NaN (a diverged step must give a NaN loss, not an
+// out-of-bounds write in the backward).
+__device__ __forceinline__ bool argmax_better(float ov, int oe, float v, int e)
+{
+    const bool on = ov != ov, vn = v != v;
+    if (on != vn) return on;
+    return ov > v || ((ov == v || on) && oe < e);
+}
 __device__ __forceinline__ void argmax_merge(float &v, int &e, float ov, int oe)
 {
-    if (ov > v || (ov == v && oe < e)) { v = ov; e = oe; }
+    if (argmax_better(ov, oe, v, e)) { v = ov; e = oe; }
 }
 
 template <int C, int WARPS>
@@ -107,7 +116,7 @@ segment_max_fwd_kernel(const float *__restrict__ vals, const float *__restrict__
     const int s = __ldg(rowptr + q), e = __ldg(rowptr + q + 1);
     const int slot = lane / CQ, cq = lane - slot * CQ;
     float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    int be[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+    int be[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};  // no edge seen yet (loses every merge)
     // optional per-channel affine (the producer block's BatchNorm scale | shift) applied on load: with a negative
     // scale the max of the transformed values is not the transform of the max, so it cannot wait until afterwards
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -119,10 +128,11 @@ segment_max_fwd_kernel(const float *__restrict__ vals, const float *__restrict__
     for (int j = first; j < e; j += step) {
         float4 t = __ldg(reinterpret_cast<const float4 *>(vals + (size_t)j * C) + cq);
         t = make_float4(fmaf(t.x, sc.x, sh.x), fmaf(t.y, sc.y, sh.y), fmaf(t.z, sc.z, sh.z), fmaf(t.w, sc.w, sh.w));
-        if (t.x > bv[0]) { bv[0] = t.x; be[0] = j; }
-        if (t.y > bv[1]) { bv[1] = t.y; be[1] = j; }
-        if (t.z > bv[2]) { bv[2] = t.z; be[2] = j; }
-        if (t.w > bv[3]) { bv[3] = t.w; be[3] = j; }
+        // ascending j inside a lane: strict '>' keeps the first edge; the first edge of the slot always enters
+        if (be[0] == 0x7fffffff || t.x > bv[0] || (t.x != t.x && bv[0] == bv[0])) { bv[0] = t.x; be[0] = j; }
+        if (be[1] == 0x7fffffff || t.y > bv[1] || (t.y != t.y && bv[1] == bv[1])) { bv[1] = t.y; be[1] = j; }
+        if (be[2] == 0x7fffffff || t.z > bv[2] || (t.z != t.z && bv[2] == bv[2])) { bv[2] = t.z; be[2] = j; }
+        if (be[3] == 0x7fffffff || t.w > bv[3] || (t.w != t.w && bv[3] == bv[3])) { bv[3] = t.w; be[3] = j; }
     }
 #pragma unroll
     for (int d = CQ; d < 32; d <<= 1) {
@@ -156,13 +166,13 @@ segment_max_fwd_kernel(const float *__restrict__ vals, const float *__restrict__
 }
 
 __global__ void __launch_bounds__(256)
-segment_max_bwd_kernel(const float *__restrict__ dout, const int *__restrict__ arg, long long QC, int C,
+segment_max_bwd_kernel(const float *__restrict__ dout, const int *__restrict__ arg, long long QC, int C, long long E,
                        float *__restrict__ dvals)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= QC) return;
     const int a = __ldg(arg + t);
-    if (a >= 0) dvals[(size_t)a * C + (int)(t % C)] = __ldg(dout + t);  // rows are disjoint: no conflict
+    if (a >= 0 && a < E) dvals[(size_t)a * C + (int)(t % C)] = __ldg(dout + t);  // rows are disjoint: no conflict
 }
 
 // ---- k=3 interpolation ---------------------------------------------------------------------------
@@ -249,7 +259,7 @@ project_plotwise_bwd_kernel(const float *__restrict__ dout, const int *__restric
                             float *__restrict__ dpred)
 {
     __shared__ int s_cnt;
-    const int b = blockIdx.x, tid = threadIdx.x, P = D * D;
+    const int b = blockIdx.x, tid = threadIdx.x, P = (D + 1) * (D + 1);  // the forward's pixel frame
     const int *pa = parg + (size_t)b * 3 * P;
     if (tid == 0) s_cnt = 0;
     __syncthreads();
@@ -329,10 +339,10 @@ extern "C" int sn2_segment_max_fwd(const float *vals, const float *ss, const int
     return SN2_OK;
 }
 
-extern "C" int sn2_segment_max_bwd(const float *dout, const int *arg, long long Q, int C, float *dvals, void *stream)
+extern "C" int sn2_segment_max_bwd(const float *dout, const int *arg, long long Q, int C, long long E, float *dvals, void *stream)
 {
-    if (!dout || !arg || !dvals || Q <= 0 || C <= 0) return SN2_EINVAL;
-    segment_max_bwd_kernel<<<blocks_for(Q * C, 256), 256, 0, (cudaStream_t)stream>>>(dout, arg, Q * C, C, dvals);
+    if (!dout || !arg || !dvals || Q <= 0 || C <= 0 || E < 0) return SN2_EINVAL;
+    segment_max_bwd_kernel<<<blocks_for(Q * C, 256), 256, 0, (cudaStream_t)stream>>>(dout, arg, Q * C, C, E, dvals);
     SN2_LAUNCH_CHECK("segment_max_bwd_kernel");
     return SN2_OK;
 }

@@ -139,13 +139,12 @@ class PointNet2(nn.Module):
             raise RuntimeError("sn2 PointNet2.forward needs a CUDA device (args.cuda); this build has no CPU path")
         device = torch.device("cuda", self.cuda_device)
         with torch.cuda.device(device):
-            if self.training and torch.is_grad_enabled():
+            if self.training:
+                # also under torch.no_grad() (the reference permits it): batch statistics, running-stat updates,
+                # no autograd graph
                 cov, proba, g, cloud_dev = _pipeline.forward_train(
                     self, cloud_data["xyz"], cloud_data["cloud"], device, self.sa1_module.max_num_neighbors, trace, timer,
                     structure=cloud_data.get("sn2_structure"))
-            elif self.training:
-                raise RuntimeError("sn2 PointNet2: training mode under no_grad is not supported (BatchNorm batch "
-                                   "statistics are only implemented on the autograd path); call model.eval()")
             else:
                 cov, proba, g, cloud_dev = _pipeline.forward_eval(
                     self, cloud_data["xyz"], cloud_data["cloud"], device, self.sa1_module.max_num_neighbors, trace, timer)
@@ -154,6 +153,10 @@ class PointNet2(nn.Module):
         # device copy of the normalised cloud, reused by model.project_to_2d to skip a second H2D
         self.last_cloud_device = cloud_dev
         return cov, proba
+
+    def train(self, mode: bool = True):
+        _pipeline.invalidate_packed(self)  # eval weights are BN-folded snapshots: never reuse one across a mode switch
+        return super().train(mode)
 
     # -- layout helpers (reference :155-163) ---------------------------------------------------
     @staticmethod

@@ -42,7 +42,7 @@ SIGNATURES = {
     "sn2_edge_msg_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp],
     "sn2_edge_msg_bwd": [_vp, _vp, _ll, _vp, _i, _vp, _vp],
     "sn2_segment_max_fwd": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
-    "sn2_segment_max_bwd": [_vp, _vp, _ll, _i, _vp, _vp],
+    "sn2_segment_max_bwd": [_vp, _vp, _ll, _i, _ll, _vp, _vp],
     "sn2_interp3_fwd": [_vp, _i, _vp, _vp, _ll, _i, _vp, _vp],
     "sn2_interp3_bwd": [_vp, _vp, _vp, _ll, _i, _vp, _vp],
     "sn2_interp_plot_fwd": [_vp, _vp, _i, _i, _i, _vp, _vp],

@@ -78,7 +78,7 @@ class SegmentMax(torch.autograd.Function):
         (arg,) = ctx.saved_tensors
         Q, C = arg.shape
         dvals = torch.zeros((ctx.E, C), dtype=torch.float32, device=dout.device)
-        check(lib.sn2_segment_max_bwd(dptr(_c(dout), torch.float32), dptr(arg), Q, C, dptr(dvals), stream_ptr()),
+        check(lib.sn2_segment_max_bwd(dptr(_c(dout), torch.float32), dptr(arg), Q, C, ctx.E, dptr(dvals), stream_ptr()),
               "sn2_segment_max_bwd")
         ops._count(1)
         return dvals, None, None

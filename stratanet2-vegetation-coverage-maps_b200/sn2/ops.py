@@ -261,7 +261,8 @@ def fp1_head_fwd(f2, nbr, w, feat, w_host, tensor_core: bool = False):
 
 
 def project_plotwise(cloud_dev, pred, D: int, want_aux: bool = False):
-    """cloud (B,F,N) device, pred (B*N,4) -> out (B,4) [+ pix (B*N), pmax (B,3,D,D), parg (B,3,D,D)]."""
+    """cloud (B,F,N) device, pred (B*N,4) -> out (B,4) [+ pix (B*N), pmax, parg (B,3,D+1,D+1),
+    all three in the (D+1) x (D+1) frame px*(D+1)+py of the reference's unclamped pixel ids]."""
     lib = _lib.load()
     B, F, N = cloud_dev.shape
     dev = cloud_dev.device
@@ -269,8 +270,8 @@ def project_plotwise(cloud_dev, pred, D: int, want_aux: bool = False):
     pix = pmax = parg = None
     if want_aux:
         pix = torch.empty(B * N, dtype=torch.int32, device=dev)
-        pmax = torch.empty((B, 3, D, D), dtype=torch.float32, device=dev)
-        parg = torch.empty((B, 3, D, D), dtype=torch.int32, device=dev)
+        pmax = torch.empty((B, 3, D + 1, D + 1), dtype=torch.float32, device=dev)
+        parg = torch.empty((B, 3, D + 1, D + 1), dtype=torch.int32, device=dev)
     check(lib.sn2_project_plotwise(dptr(cloud_dev, torch.float32), dptr(pred, torch.float32), B, N, F, D, dptr(out), dptr(pix),
                                    dptr(pmax), dptr(parg), stream_ptr()), "sn2_project_plotwise")
     _count(1)

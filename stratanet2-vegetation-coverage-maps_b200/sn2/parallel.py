@@ -6,9 +6,13 @@ places only:
   * the gradient sum -- ONE all-reduce of a flat fp32 bucket holding all 14 997 gradients (59 988 bytes,
     latency bound: a single bucket, no overlap machinery needed);
   * BatchNorm batch statistics -- ``convert_sync_batchnorm`` swaps the model's BatchNorm1d modules for
-    torch SyncBatchNorm (same state_dict keys), which all-gathers per-channel (mean, invstd, count) so a
-    global batch split over G GPUs normalises exactly like the single-process reference, even though the
-    number of edge messages differs per rank.  Without it training is "local-BN" DP (a stated deviation).
+    SyncBatchNorm containers (same state_dict keys).  The fused Linear-ReLU-BatchNorm blocks
+    (sn2/autograd_ops.py::LinReluBN) see that type and sum their RAW fp64 statistics over the ranks -- per
+    channel (sum y, sum y^2, row count) forward and (sum dz, sum dz*y) backward, one small vector each -- so a
+    global batch split over G GPUs normalises exactly like the single-process reference even though the
+    number of edge messages differs per rank (counts are reduced, not assumed equal).  The sum runs either as
+    an NCCL all-reduce or inside the finalize kernels over NVLink peer memory (sn2/comm.py).  Without the
+    conversion training is "local-BN" DP (a stated deviation).
 """
 from __future__ import annotations
 

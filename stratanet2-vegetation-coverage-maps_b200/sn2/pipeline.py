@@ -78,6 +78,13 @@ def _side_streams(device):
     return _SIDE[key]
 
 
+def invalidate_packed(model) -> None:
+    """Drop the cached BN-folded eval weights.  Kernels and CUDA-graph replays write parameters and running
+    statistics through raw pointers, which torch's `_version` counters (the cache key) never see: every train-mode
+    forward, every GraphedTrainStep call and every train()/eval() switch calls this."""
+    object.__setattr__(model, "_sn2_wcache", None)
+
+
 def _packed(model) -> dict:
     ver = weights.params_version(model)
     cache = getattr(model, "_sn2_wcache", None)
@@ -362,6 +369,7 @@ def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num
 
     from .autograd_ops import EdgeMsg, Interp3, InterpPlot, SegmentMax, run_mlp, tall_linear
 
+    invalidate_packed(model)  # running statistics are about to change behind torch's back
     S = structure if structure is not None else TrainStructure(model, xyz, cloud, device, max_num_neighbors, timer)
     S.use_on(torch.cuda.current_stream(device))
     B, N, M1, M2 = S.B, S.N, S.M1, S.M2
@@ -425,9 +433,9 @@ class GraphedTrainStep:
     replayed per batch: the step has ~90 launches of ours and ~300 torch op dispatches, which cost more host time
     (6-7 ms) than the GPU needs to run them (4.6 ms at config 3).
 
-        step = GraphedTrainStep(model, step_fn)          # step_fn(batch) -> loss tensor; it zeroes the grads, calls
-        for batch in StructurePrefetcher(model, loader): # model(batch), the loss, backward(), optimizer.step()
-            loss = step(batch)                           # static tensor, valid until the next call
+        step = GraphedTrainStep(model, step_fn, optimizer)   # step_fn(batch) -> loss tensor; it zeroes the grads,
+        for batch in StructurePrefetcher(model, loader):     # calls model(batch), the loss, backward(), optimizer.step()
+            loss = step(batch)                               # static tensor, valid until the next call
 
     What makes the step graph-safe: the structural stage (FPS, ball query, kNN; it sizes the edge lists on the host)
     stays outside the graph -- prefetched or computed eagerly -- and is copied into fixed-address buffers; the edge
@@ -441,7 +449,11 @@ class GraphedTrainStep:
     Every tensor value of the batch dict (xyz, cloud, targets ...) is copied into a static buffer of the same shape;
     all batches must therefore have the same shapes."""
 
-    def __init__(self, model, step_fn, optimizer=None, device=None, capacity_factor: float = 1.25, max_num_neighbors=None):
+    def __init__(self, model, step_fn, optimizer, device=None, capacity_factor: float = 1.25, max_num_neighbors=None):
+        if optimizer is None or not hasattr(optimizer, "state"):
+            # without it the optimizer state (Adam's moments and step count) could not be rolled back after the
+            # warm-up executions and the graphed loop would silently differ from the eager one
+            raise TypeError("GraphedTrainStep needs the optimizer that step_fn steps (its state is rolled back after capture)")
         self.model, self.step_fn, self.optimizer = model, step_fn, optimizer
         self.device = device if device is not None else next(model.parameters()).device
         self.capacity_factor = capacity_factor
@@ -542,6 +554,7 @@ class GraphedTrainStep:
                     v.record_stream(cur)
         self.graph.replay()
         self.replays += 1
+        invalidate_packed(self.model)  # the replay updated parameters / running statistics through raw pointers
         return self.loss
 
 

@@ -306,6 +306,69 @@ def test_full_size_properties_config2(cuda_device):
     assert (pw >= 0).all() and (pw <= 1).all()
 
 
+def test_full_size_oracle_parity_config2(cuda_device):
+    """BASELINE config 2 at its FULL size against the ORACLE, not through properties: all 64 x 16 384 points, every FPS
+    index, every neighbour list (order included), the fused SA kernels' edge counts, both pixel-id arrays: equal;
+    x1, x2, coverages, probabilities, plot-wise coverages: rtol 1e-3; rasters: equal incl. the NaN pattern.
+    The oracle runs in chunks of 16 plots (eval mode: plots are independent) to bound its memory (~3 GB, ~2 s each)."""
+    from model.project_to_2d import project_to_2d_rasters_batched, project_to_plotwise_coverages
+    from oracle.pointnet2_port import (plotwise_pixel_ids, project_to_2d_rasters_port, project_to_plotwise_coverages_port,
+                                       raster_pixel_ids)
+    from sn2 import ops
+    from sn2.pipeline import ForwardTrace, _packed
+
+    B, N, K, CH = 64, 16384, 2000, 16
+    args, net, port = _make_models(N, cuda_device)
+    data = _plots(2, B, N, "plain")
+    D = args.diam_pix
+    with torch.no_grad():
+        tr = ForwardTrace()
+        cov, proba = net(data, trace=tr)
+        pw = project_to_plotwise_coverages(cov, data["cloud"], args)
+        cloud_d = data["cloud"].to(cuda_device)
+        _, pix = ops.project_plotwise(cloud_d, cov, D, want_aux=True)[:2]
+        rs, rpix = ops.project_rasters(cloud_d, cov, "point_major", D, args.diam_meters, want_pix=True)
+        rs_api = project_to_2d_rasters_batched(data["cloud"], cov, args)
+        W = _packed(net)
+        t = tr.tensors
+        M1, M2 = t["M1"], t["M2"]
+        _, cnt1 = ops.sa_fused_fwd(1, t["pos0"], t["feat0"], t["pos1"], B, N, M1, net.sa1_module.r, K, W["sa1"], want_counts=True)
+        _, cnt2 = ops.sa_fused_fwd(2, t["pos1"], t["x1"], t["pos2"], B, M1, M2, net.sa2_module.r, K, W["sa2"], want_counts=True)
+    assert torch.equal(rs, rs_api)
+    idx1, idx2 = t["idx1"].cpu().long().view(B, M1), t["idx2"].cpu().long().view(B, M2)
+    rp1, col1 = t["rowptr1"].cpu().long(), t["col1"].cpu().long()
+    rp2, col2 = t["rowptr2"].cpu().long(), t["col2"].cpu().long()
+    assert torch.equal(cnt1.cpu().long(), rp1.diff()) and torch.equal(cnt2.cpu().long(), rp2.diff())
+    x1, x2, cov_c, proba_c = t["x1"].cpu(), t["x2"].cpu(), cov.cpu(), proba.cpu()
+    wpix = plotwise_pixel_ids(data["cloud"], D)
+    assert torch.equal(pix.cpu().view(B, N), (wpix[:, 0] * (D + 1) + wpix[:, 1]).int())
+    wr = raster_pixel_ids(data["cloud"], D, args.diam_meters)
+    assert torch.equal(rpix.cpu().view(B, N), (wr[:, 1] * D + wr[:, 0]).int())
+    rs_c = rs.cpu().numpy()
+    for b0 in range(0, B, CH):
+        sub = {k: v[b0:b0 + CH].contiguous() for k, v in data.items()}
+        with torch.no_grad():
+            cov_o, proba_o = port(sub, max_num_neighbors=K, trace=True)
+            pw_o = project_to_plotwise_coverages_port(cov_o, sub["cloud"], args)
+        o = port.trace
+        # the oracle's indices are global inside its 16-plot chunk
+        assert torch.equal(idx1[b0:b0 + CH].reshape(-1) - b0 * N, o["sa1_idx"]), f"FPS level 1, plots {b0}.."
+        assert torch.equal(idx2[b0:b0 + CH].reshape(-1) - b0 * M1, o["sa2_idx"]), f"FPS level 2, plots {b0}.."
+        e0, e1 = int(rp1[b0 * M1]), int(rp1[(b0 + CH) * M1])
+        assert torch.equal(col1[e0:e1] - b0 * N, o["sa1_col"]), f"ball query level 1, plots {b0}.."
+        assert torch.equal(rp1[b0 * M1:(b0 + CH) * M1 + 1].diff(), torch.bincount(o["sa1_row"], minlength=CH * M1))
+        e0, e1 = int(rp2[b0 * M2]), int(rp2[(b0 + CH) * M2])
+        assert torch.equal(col2[e0:e1] - b0 * M1, o["sa2_col"]), f"ball query level 2, plots {b0}.."
+        assert torch.equal(rp2[b0 * M2:(b0 + CH) * M2 + 1].diff(), torch.bincount(o["sa2_row"], minlength=CH * M2))
+        for name, got, want in (("x1", x1[b0 * M1:(b0 + CH) * M1], o["sa1_x"]), ("x2", x2[b0 * M2:(b0 + CH) * M2], o["sa2_x"]),
+                                ("cov", cov_c[b0 * N:(b0 + CH) * N], cov_o), ("proba", proba_c[b0 * N:(b0 + CH) * N], proba_o),
+                                ("plotwise", pw[b0:b0 + CH].cpu(), pw_o)):
+            torch.testing.assert_close(got, want, rtol=RTOL, atol=ATOL, msg=lambda m, n=name: f"{n} (plots {b0}..): {m}")
+        for b in range(b0, b0 + CH, 5):  # rasters from the GPU coverages: exact, NaN pattern included
+            want_r = project_to_2d_rasters_port(data["cloud"][b], cov_c.view(B, N, 4)[b].t(), args)
+            assert np.array_equal(rs_c[b], want_r, equal_nan=True), f"rasters of plot {b}"
+
+
 @pytest.mark.parametrize("B,N", [(1, 10000), (4, 4096)])
 def test_projections_parity(cuda_device, B, N):
     from model.project_to_2d import project_to_2d_rasters, project_to_plotwise_coverages, project_to_2d_rasters_batched
@@ -332,8 +395,9 @@ def test_projections_parity(cuda_device, B, N):
             vals = pred[b * N:(b + 1) * N, ch]
             lin = (wpix[b, 0] * D + wpix[b, 1]).long()
             ref = torch.zeros(D * D).scatter_reduce(0, lin, vals, reduce="amax", include_self=False)
-            assert torch.equal(pmax[b, band].cpu().reshape(-1), ref)
-            arg = parg[b, band].cpu().reshape(-1).long()
+            assert torch.equal(pmax[b, band, :D, :D].cpu().reshape(-1), ref)
+            assert (parg[b, band, D, :] < 0).all() and (parg[b, band, :, D] < 0).all()  # row / column D: unused here
+            arg = parg[b, band, :D, :D].cpu().reshape(-1).long()
             occ = arg >= 0
             first = torch.full((D * D,), N, dtype=torch.int64).scatter_reduce(
                 0, lin[vals == ref[lin]], torch.arange(N)[vals == ref[lin]], reduce="amin", include_self=True)
