@@ -334,7 +334,7 @@ def test_full_size_oracle_parity_config2(cuda_device):
         M1, M2 = t["M1"], t["M2"]
         _, cnt1 = ops.sa_fused_fwd(1, t["pos0"], t["feat0"], t["pos1"], B, N, M1, net.sa1_module.r, K, W["sa1"], want_counts=True)
         _, cnt2 = ops.sa_fused_fwd(2, t["pos1"], t["x1"], t["pos2"], B, M1, M2, net.sa2_module.r, K, W["sa2"], want_counts=True)
-    assert torch.equal(rs, rs_api)
+    assert torch.equal(torch.nan_to_num(rs, nan=-1.0), torch.nan_to_num(rs_api, nan=-1.0))
     idx1, idx2 = t["idx1"].cpu().long().view(B, M1), t["idx2"].cpu().long().view(B, M2)
     rp1, col1 = t["rowptr1"].cpu().long(), t["col1"].cpu().long()
     rp2, col2 = t["rowptr2"].cpu().long(), t["col2"].cpu().long()
@@ -1007,6 +1007,55 @@ def test_error_behaviour(cuda_device):
     args, net, _ = _make_models(512, d)
     with pytest.raises(RuntimeError):  # wrong number of points per plot (reference contract: subsample_size)
         net({"xyz": torch.zeros(1, 3, 400), "cloud": torch.zeros(1, 10, 400)})
-    net.train()
-    with torch.no_grad(), pytest.raises(RuntimeError):  # train-mode statistics need the autograd path
-        net(_plots(1, 1, 512))
+
+
+def test_train_mode_under_no_grad_and_eval_weight_cache(cuda_device):
+    """(1) model.train() under torch.no_grad() is allowed as in the reference (model/point_net2.py:106-153 has no
+    such restriction): batch statistics, running-stat updates, same values as the autograd forward.
+    (2) eval -> train steps that update parameters / running statistics through raw pointers (fused blocks, CUDA-graph
+    replay) -> eval must not reuse the BN-folded weights packed for the first eval."""
+    import copy
+
+    from sn2.pipeline import GraphedTrainStep
+
+    N = 2048
+    args, net, _ = _make_models(N, cuda_device)
+    data = _plots(3, 2, N)
+    with torch.no_grad():
+        cov_e0, _ = net(data)                                  # packs + caches the eval weights
+    twin = copy.deepcopy(net)
+    net.train(); twin.train()
+    with torch.no_grad():
+        cov_ng, proba_ng = net(data)
+    cov_g, proba_g = twin(data)
+    assert not cov_ng.requires_grad and cov_g.requires_grad
+    assert torch.equal(cov_ng, cov_g.detach()) and torch.equal(proba_ng, proba_g.detach())
+    for (k, a), (_, b) in zip(net.state_dict().items(), twin.state_dict().items()):
+        assert torch.equal(a, b), k                            # running statistics / num_batches_tracked advanced alike
+    assert int(net.sa1_module.conv.local_nn[0][2].num_batches_tracked) == 1
+    # graphed training steps, then eval: must equal a model freshly built from the same state
+    opt = torch.optim.Adam(net.parameters(), lr=1e-2, capturable=True)
+
+    def step(batch):
+        opt.zero_grad(set_to_none=False)
+        cov, proba = net(batch)
+        loss = cov.square().mean() + proba[:, 2:].mean()
+        loss.backward()
+        opt.step()
+        return loss.detach()
+
+    for p in net.parameters():
+        p.grad = torch.zeros_like(p)
+    gstep = GraphedTrainStep(net, step, optimizer=opt)
+    for _ in range(3):
+        gstep(data)
+    net.eval()
+    with torch.no_grad():
+        cov_e1, _ = net(data)
+    fresh = _make_models(N, cuda_device)[1]
+    fresh.load_state_dict(net.state_dict())
+    fresh.eval()
+    with torch.no_grad():
+        cov_f, _ = fresh(data)
+    assert torch.equal(cov_e1, cov_f)
+    assert not torch.equal(cov_e1, cov_e0)
