@@ -194,15 +194,28 @@ def time_cpu(N, config_id, plots, repeats):
     return kind, plots / best, best
 
 
+def static_config(cfg, world):
+    """The part of `config` that names the WORKLOAD (identical for our arm and the reference arm)."""
+    if cfg["mode"] != "infer":
+        return {"workload": cfg["name"]}
+    return {"workload": cfg["name"], "plots_per_gpu_per_step": cfg["B"], "points_per_plot": cfg["N"], "max_num_neighbors": 2000,
+            "l2": "inputs larger than L2: steps rotate over 4 distinct input batches (218 MB)" if cfg["B"] > 1 else
+                  "inputs rotate over 64 distinct single plots",
+            "parallelism": f"plot-sharded x{world}"}
+
+
 def run_reference(opts, cfg):
-    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores, on the SAME workload as our
+    arm: every step is one full batch of the config (64 plots x 16 384 points at config 2), steps rotate over the same
+    4 distinct batches.  The oracle evaluates a batch in chunks of 16 plots (eval mode: plots are independent) to bound
+    its memory.  If the first step says K steps would not end within ~5 minutes, the batch is cut to a bounded sample
+    and `config` says so (the rate per plot is what the ratio uses)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from sn2.synth import synth_batch
 
-    N = cfg["N"]
-    plots = 8  # bounded sample: each step = 8 plots of the same workload (OpenMP over plots / queries)
+    N, B = cfg["N"], cfg["B"]
     # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm (rank 0 alone) is entitled to all host
     # cores, so under torchrun the value is put back before the oracle's OpenMP runtime is loaded (torch's own pool
     # is resized explicitly either way)
@@ -211,20 +224,37 @@ def run_reference(opts, cfg):
         os.environ["OMP_NUM_THREADS"] = str(ncores)
     torch.set_num_threads(ncores)
     kind, net, plotwise, raster, args = cpu_model(N)
-    data = synth_batch(opts.config, plots, N)
-    for _ in range(max(1, min(opts.warmup, 1))):
-        cpu_step(net, plotwise, raster, args, data)
+    nrot = 4 if B > 1 else 8
+    rot = [synth_batch(opts.config, B, N, first_plot=r * B) for r in range(nrot)]
+    CH = 16
+
+    def step(data, plots):
+        for b0 in range(0, plots, CH):
+            cpu_step(net, plotwise, raster, args, {k: v[b0:min(b0 + CH, plots)].contiguous() for k, v in data.items()})
+
     t0 = time.perf_counter()
-    for _ in range(opts.steps):
-        cpu_step(net, plotwise, raster, args, data)
+    step(rot[0], min(B, CH))  # warm-up on one chunk (also the probe that sizes the run)
+    per_plot = (time.perf_counter() - t0) / min(B, CH)
+    plots = B
+    budget_s = float(os.environ.get("SN2_REF_BUDGET_S", "300"))
+    if per_plot * B * opts.steps > budget_s:
+        plots = max(1, min(B, int(budget_s / (per_plot * opts.steps))))
+    t0 = time.perf_counter()
+    for i in range(opts.steps):
+        step(rot[i % nrot], plots)
     dt = time.perf_counter() - t0
     value = plots * opts.steps / dt
-    sample = f"{plots} plots x {N} pts per step (bounded sample of {cfg['name']})"
+    config = static_config(cfg, opts.gpus)
+    if plots != B:
+        config["plots_per_gpu_per_step"] = plots
+        config["workload"] += f" [bounded sample: {plots} of {B} plots per step]"
+    sample = (f"{plots} plots x {N} pts per step, {opts.steps} steps rotating over {nrot} distinct batches, evaluated in chunks of {CH} plots; "
+              f"{'reference model files verbatim on restated third-party ops' if kind == 'reference' else 'oracle port'}")
     print(json.dumps({
         "impl": "reference", "metric": "plots/sec (PointNet2 eval forward + project_to_2d)", "value": value, "unit": "plots/s",
         "n_gpus": opts.gpus, "steps": opts.steps, "warmup": opts.warmup, "ms_per_step": 1e3 * dt / opts.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["name"], "plots_per_step": plots, "points_per_plot": N},
+        "config": config,
         "points_per_s": value * N,
         "cpu_baseline": {"value": value, "unit": "plots/s", "cores": ncores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "plots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -251,9 +281,8 @@ def init_dist(dev):
 
 
 def train_loss(proba, pw, gt, pdf):
-    """Reference training loss (learning/train.py:52-66, learning/loss_functions.py:9-57), synthetic pdf."""
-    # columns 0, 2, 3 as slices: an index list would put a sort + index_put over every point into backward and a
-    # host->device copy of the indices into the step (not capturable in a CUDA graph)
+    """Synthetic-pdf variant of the training loss used by round-1 tests / tools (kept for them); the bench uses the
+    reference loss itself, sn2.losses.training_loss."""
     sel = lambda t: torch.cat([t[:, :1], t[:, 2:]], dim=1)  # noqa: E731
     mae = torch.sqrt((sel(pw) - sel(gt)) ** 2 + 1e-4).mean()
     nll = -torch.log((sel(proba).double() * pdf).sum(1) + 1e-6).mean().float()
@@ -262,78 +291,111 @@ def train_loss(proba, pw, gt, pdf):
     return mae + 0.10 * nll + 0.04 * ent
 
 
-def run_train(opts, cfg):
-    """Config 3: strong scaling -- the global batch of 32 plots is split by plot over the ranks."""
+def synthetic_kde_lut(dev):
+    """A smooth positive 3-column density on the reference's grid size (5000 knots, learning/kde_mixture.py:89-91) in
+    place of the fitted KDE mixture (KDEpy is not installed)."""
+    from sn2.losses import KdeLut
+
+    X = np.linspace(-30.0, 30.0, 5000)
+    a = np.abs(X)
+    return KdeLut(X, np.stack([np.exp(-a), 0.5 * np.exp(-0.5 * (a - 1.0) ** 2), 0.1 + 0.05 * a]), dev)
+
+
+_DIST = {}
+
+
+def dist_ctx():
+    """(world, rank, local, device); NCCL process group created once per process."""
+    if not _DIST:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        rank = int(os.environ.get("RANK", "0"))
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+        if world > 1:
+            init_dist(dev)
+        _DIST.update(world=world, rank=rank, local=local, dev=dev)
+    return _DIST["world"], _DIST["rank"], _DIST["local"], _DIST["dev"]
+
+
+def run_train(opts, cfg, scaling="strong", quick=False):
+    """Config 3: one training step = train-mode forward (BatchNorm batch statistics over the GLOBAL batch) + plot-wise
+    projection + the reference loss (MAE + 0.1 NLL under a KDE look-up + 0.04 entropy) + backward + gradient
+    all-reduce + Adam, data-parallel by plot.  scaling = "strong": the global batch of 32 plots is split over the
+    ranks; "weak": 32 plots per rank.  Returns the result dict (rank 0 prints it)."""
     import torch.distributed as dist
     from model.project_to_2d import project_to_plotwise_coverages
-    from sn2 import ops, parallel
+    from sn2 import comm as sn2_comm
+    from sn2 import losses, ops, parallel
+    from sn2.optim import FusedAdam
     from sn2.pipeline import GraphedTrainStep, StageTimer, StructurePrefetcher
     from sn2.synth import synth_batch
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        init_dist(dev)
-    Bg, N = cfg["B"], cfg["N"]
+    world, rank, local, dev = dist_ctx()
+    N = cfg["N"]
+    Bg = cfg["B"] * (world if scaling == "weak" else 1)
     W = max(opts.warmup, 3)
+    steps = opts.steps if not quick else min(opts.steps, 20)
     args, net = make_model(N, local)
     net.train()
+    comm = None
     if world > 1:
         net = parallel.convert_sync_batchnorm(net)  # reference-exact BatchNorm over the GLOBAL batch
-    bucket = parallel.GradBucket(net)
-    use_graph = world == 1 and not opts.no_graph  # SyncBatchNorm / NCCL stay outside graphs: multi-GPU uses the prefetch loop
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-3, capturable=use_graph)  # learning/train.py:180-185
-    full = synth_batch(opts.config, Bg, N)
-    g = torch.Generator().manual_seed(9)
-    full["gt"] = torch.rand(Bg, 4, generator=g)
-    mine = parallel.shard_plots(full, rank, world)
+        comm = sn2_comm.get_comm()
+    use_graph = not opts.no_graph
+    opt = FusedAdam(net.parameters(), lr=args.lr, weight_decay=args.wd, comm=comm)  # learning/train.py:180-185
+    lut = synthetic_kde_lut(dev)
+    if scaling == "weak":
+        mine = synth_batch(3, cfg["B"], N, first_plot=rank * cfg["B"])
+        g = torch.Generator().manual_seed(9 + rank)
+        mine["gt"] = torch.rand(cfg["B"], 4, generator=g)
+    else:
+        full = synth_batch(3, Bg, N)
+        g = torch.Generator().manual_seed(9)
+        full["gt"] = torch.rand(Bg, 4, generator=g)
+        mine = parallel.shard_plots(full, rank, world)
     Bl = mine["cloud"].shape[0]
     host = {k: v.pin_memory() for k, v in mine.items()}
     dev_in = {k: v.to(dev) for k, v in mine.items()}
-    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    loss_host = torch.empty((), dtype=torch.float64).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
-    def pdf_of(xyz):
-        z = xyz[:, 2, :].reshape(-1, 1).double()
-        return torch.cat([torch.exp(-z), 0.5 * torch.exp(-0.5 * (z - 1.0) ** 2), 0.1 + 0.05 * z], dim=1)
-
-    def step(inp, timer=None, read_loss=False):
-        bucket.zero()
-        cov, proba = net({k: inp[k] for k in ("xyz", "cloud", "sn2_structure") if k in inp}, timer=timer)
+    def step_fn(batch):
+        """learning/train.py:52-66 (no host synchronisation inside: graph-safe); returns the loss tensor."""
+        opt.zero_grad()
+        cov, proba = net(batch)
         pw = project_to_plotwise_coverages(cov, net.last_cloud_device, args)
-        xyz_d = inp["xyz"].to(dev, non_blocking=True)
-        loss = train_loss(proba, pw, inp["gt"].to(dev, non_blocking=True), pdf_of(xyz_d))
+        pdf = lut.pdf(net.last_cloud_device, args.z_max)
+        loss = losses.training_loss(pw, batch["gt"], proba, pdf, args.m, args.e)[0]
         loss.backward()
-        bucket.allreduce(Bl, Bg)
-        opt.step()
+        opt.step(grad_scale=Bl / Bg)
+        return loss.detach()
+
+    def eager_step(inp, timer=None, read_loss=False):
+        b = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in inp.items()}
+        if timer is not None:  # per-stage events of the structural stage (fps1 ...) come from the model's own timer hooks
+            opt.zero_grad()
+            cov, proba = net({k: b[k] for k in ("xyz", "cloud")}, timer=timer)
+            pw = project_to_plotwise_coverages(cov, net.last_cloud_device, args)
+            loss = losses.training_loss(pw, b["gt"], proba, lut.pdf(net.last_cloud_device, args.z_max), args.m, args.e)[0]
+            loss.backward()
+            opt.step(grad_scale=Bl / Bg)
+        else:
+            loss = step_fn(b)
         if read_loss:
             loss_host.copy_(loss.detach(), non_blocking=True)
 
-    def graph_step(batch):
-        """The same step as a graph-safe closure (no host synchronisation inside): returns the loss tensor."""
-        bucket.zero()
-        cov, proba = net(batch)
-        pw = project_to_plotwise_coverages(cov, net.last_cloud_device, args)
-        loss = train_loss(proba, pw, batch["gt"], pdf_of(batch["xyz"]))
-        loss.backward()
-        bucket.allreduce(Bl, Bg)
-        opt.step()
-        return loss.detach()
-
-    gstep = GraphedTrainStep(net, graph_step, optimizer=opt, device=dev) if use_graph else None
+    gstep = GraphedTrainStep(net, step_fn, opt, device=dev) if use_graph else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, n):
         evs = []
         barrier()
-        for _ in range(steps):
+        for _ in range(n):
             flush.fill_(1)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -343,93 +405,103 @@ def run_train(opts, cfg):
         barrier()
         return sum(a.elapsed_time(b) for a, b in evs)
 
-    def timed_prefetch(src, steps, read_loss):
+    def timed_prefetch(src, n, read_loss):
         """The training loop as a user writes it with StructurePrefetcher: the structural stage (FPS, ball query,
         kNN) of batch i+1 runs on a side stream under step i.  One event pair around the whole loop (L2 flush
         included); the first batch's structural stage is inside the region, none is computed beyond the last."""
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        trace = os.environ.get("SN2_BENCH_TRACE") == "1"
-        t_prev, host_ms = time.perf_counter(), []
-        for batch in StructurePrefetcher(net, (src for _ in range(steps)), dev):
-            if trace:
-                host_ms.append(round((time.perf_counter() - t_prev) * 1e3, 2))
-                t_prev = time.perf_counter()
-            flush.fill_(1)
-            if gstep is not None:  # whole step = input copies into the static buffers + one graph launch
-                loss = gstep(batch)
-                if read_loss:
-                    loss_host.copy_(loss, non_blocking=True)
-            else:
-                step(batch, None, read_loss)
-        b.record()
-        barrier()
-        if trace and rank == 0:
-            print(f"[trace] host ms between steps ({'host' if src is host else 'resident'} inputs): {host_ms}", file=sys.stderr)
+        with no_gc():
+            a.record()
+            for batch in StructurePrefetcher(net, (src for _ in range(n)), dev):
+                flush.fill_(1)
+                if gstep is not None:  # whole step = input copies into the static buffers + one graph launch
+                    loss = gstep(batch)
+                    if read_loss:
+                        loss_host.copy_(loss, non_blocking=True)
+                else:
+                    eager_step(batch, None, read_loss)
+            b.record()
+            barrier()
         return a.elapsed_time(b)
 
     # W untimed steps of EACH mode right before it is timed: graph capture empties the caching allocator
     # (torch.cuda.graph calls empty_cache), so the first eager steps after it pay their cudaMallocs again
-    timed_prefetch(dev_in, W, False)   # captures the graph (single GPU)
+    timed_prefetch(dev_in, W, False)   # captures the graph (every rank, together)
     sampler = ClockSampler(local)
     sampler.start()
     sampler.wait_ready()
     timer = StageTimer()
-    for _ in range(W):
-        step(dev_in)
-    ms_serial = timed(lambda: step(dev_in, timer), opts.steps)
-    for _ in range(W):
-        step(host, read_loss=True)
-    ms_serial_e2e = timed(lambda: step(host, None, True), opts.steps)
+    ms_serial = ms_serial_e2e = None
+    if not quick:
+        for _ in range(W):
+            eager_step(dev_in)
+        ms_serial = timed(lambda: eager_step(dev_in, timer), steps)
+        for _ in range(W):
+            eager_step(host, read_loss=True)
+        ms_serial_e2e = timed(lambda: eager_step(host, None, True), steps)
     timed_prefetch(dev_in, W, False)
     l0, r0 = ops.LAUNCHES, (gstep.replays if gstep is not None else 0)
-    ms_res = timed_prefetch(dev_in, opts.steps, False)
+    ms_res = timed_prefetch(dev_in, steps, False)
     launches = ops.LAUNCHES - l0  # structural stage (launched live) ...
     if gstep is not None:        # ... + our kernels inside each graph replay (counted at capture)
         launches += (gstep.replays - r0) * gstep.launches_per_replay
     timed_prefetch(host, W, True)
-    ms_e2e = timed_prefetch(host, opts.steps, True)
+    ms_e2e = timed_prefetch(host, steps, True)
     clocks = sampler.stop()
-    t = torch.tensor([ms_res, ms_e2e, ms_serial, ms_serial_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_res, ms_e2e, ms_serial or 0.0, ms_serial_e2e or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_res, ms_e2e, ms_serial, ms_serial_e2e = (float(v) for v in t)
-    value = Bg * opts.steps / (ms_res / 1e3)
-    per_step = {k: v / opts.steps for k, v in timer.totals_ms().items()}
-    M1 = ops.m_of(N, args.ratio1)
-    hbm_peak, peak_src = peaks()
-    ach = (12 * N + 4 * M1) * Bl / (per_step["fps1"] / 1e3) / 1e9
+    ms_res, ms_e2e = float(t[0]), float(t[1])
+    comm_err = comm.status()[1] if comm is not None else 0
+    value = Bg * steps / (ms_res / 1e3)
+    mode = "peer" if comm is not None else ("nccl" if world > 1 else "single process")
+    per_block = 2  # collectives per Linear-ReLU-BatchNorm block and step: statistics forward, sums backward
     out = {
         "metric": "plots/sec (PointNet2 training step: fwd + projection + loss + bwd + all-reduce + Adam)", "value": value,
-        "unit": "plots/s", "n_gpus": world, "steps": opts.steps, "warmup": W, "ms_per_step": ms_res / opts.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "unit": "plots/s", "n_gpus": world, "steps": steps, "warmup": W, "ms_per_step": ms_res / steps,
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["name"], "global_batch": Bg, "plots_per_gpu": Bl, "points_per_plot": N,
-                   "batchnorm": "SyncBatchNorm over the global batch" if world > 1 else "single process",
+                   "batchnorm": "SyncBatchNorm over the global batch (raw fp64 sums + counts)" if world > 1 else "single process",
+                   "loss": "reference loss: MAE + 0.10 NLL (fp64, KDE look-up on the device, 5000 knots) + 0.04 entropy",
+                   "optimizer": "FusedAdam (lr 1e-3, wd 1e-3): gradient all-reduce + Adam in one kernel over flat buckets",
                    "l2": "flushed between timed steps (256 MiB write, inside the timed region)",
                    "overlap": "StructurePrefetcher: FPS / ball query / kNN of batch i+1 on a side stream under step i",
-                   "cuda_graph": ("GraphedTrainStep: fwd + loss + bwd + Adam replayed as one CUDA graph (edge lists at fixed "
-                                  "capacity, live counts on the device)") if use_graph else "off (multi-GPU: SyncBatchNorm + NCCL run eagerly)",
+                   "cuda_graph": ("GraphedTrainStep: fwd + loss + bwd + all-reduces + Adam replayed as ONE CUDA graph per rank (edge lists at "
+                                  "fixed capacity, live counts on the device)") if use_graph else "off",
                    "parallelism": f"dp{world} by plot"},
         "points_per_s": value * N,
-        "serial": {"value": Bg * opts.steps / (ms_serial / 1e3), "ms_per_step": ms_serial / opts.steps,
-                   "e2e": Bg * opts.steps / (ms_serial_e2e / 1e3), "unit": "plots/s",
-                   "note": "plain loop, no prefetch; per-step event pairs, L2 flush outside them"},
-        "e2e": {"value": Bg * opts.steps / (ms_e2e / 1e3), "unit": "plots/s", "ms_per_step": ms_e2e / opts.steps,
-                "h2d_bytes_per_step": int(sum(v.numel() * 4 for v in host.values())), "d2h_bytes_per_step": 4,
+        "collectives": {"backend": mode,
+                        "how": ("one-shot all-reduces over NVLink peer stores INSIDE the BatchNorm finalize / backward-coefficient / Adam "
+                                "kernels (csrc/comm.cu): no NCCL call and no extra launch on the step's data path") if comm is not None else
+                               ("torch.distributed (NCCL) all-reduce calls between the kernels" if world > 1 else "none"),
+                        "allreduce_calls_per_step": 0 if comm is not None or world == 1 else 7 * per_block + 1,
+                        "fused_exchanges_per_step": 7 * per_block + 1 if comm is not None else 0,
+                        "bytes_per_step_to_each_peer": 8 * (2 * 260 + 7) + 8 * 2 * 260 + 4 * 14997,
+                        "peer_error_word": comm_err},
+        "e2e": {"value": Bg * steps / (ms_e2e / 1e3), "unit": "plots/s", "ms_per_step": ms_e2e / steps,
+                "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())), "d2h_bytes_per_step": 8,
                 "api": ("StructurePrefetcher + GraphedTrainStep(" if use_graph else "StructurePrefetcher + (") +
-                       "PointNet2.forward (train) + project_to_plotwise_coverages + loss.backward + GradBucket.allreduce + Adam)"},
-        "gpu_launches": launches, "clocks": clocks,
-        "stage_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
-        "roofline": {"kernel": "fps1", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                     "traffic": None, "peak_source": peak_src, "ms_per_launch": per_step["fps1"],
-                     "note": "largest single custom kernel of the step (a serial chain on one SM per plot, latency bound; it "
-                             "runs on the side stream under the previous step); stage times are from the serial pass"},
+                       "PointNet2.forward (train) + project_to_plotwise_coverages + sn2.losses.training_loss + backward + FusedAdam.step)"},
+        "gpu_launches": launches, "graph_eager_fallback_steps": gstep.eager_steps if gstep is not None else None, "clocks": clocks,
     }
-    if rank == 0:
-        print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    if not quick:
+        ms_serial, ms_serial_e2e = float(t[2]), float(t[3])
+        per_step = {k: v / steps for k, v in timer.totals_ms().items()}
+        M1 = ops.m_of(N, args.ratio1)
+        hbm_peak, peak_src = peaks()
+        out["serial"] = {"value": Bg * steps / (ms_serial / 1e3), "ms_per_step": ms_serial / steps,
+                         "e2e": Bg * steps / (ms_serial_e2e / 1e3), "unit": "plots/s",
+                         "note": "plain eager loop, no prefetch, no graph; per-step event pairs, L2 flush outside them"}
+        out["stage_ms_per_step"] = {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}
+        if "fps1" in per_step:
+            ach = (12 * N + 4 * M1) * Bl / (per_step["fps1"] / 1e3) / 1e9
+            out["roofline"] = {"kernel": "fps1", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                               "traffic": None, "peak_source": peak_src, "ms_per_launch": per_step["fps1"],
+                               "note": "largest single custom kernel of the step (a serial chain on one SM per plot, latency bound; it "
+                                       "runs on the side stream under the previous step); stage times are from the serial pass"}
+    del gstep
+    return out
 
 
 def run_parcel(opts, cfg):
@@ -441,13 +513,7 @@ def run_parcel(opts, cfg):
     from sn2.pipeline import InferencePipeline
     from sn2.synth import synth_batch
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        init_dist(dev)
+    world, rank, local, dev = dist_ctx()
     B, N = cfg["B"], cfg["N"]
     args, net = make_model(N, local)
     D = args.diam_pix
@@ -457,7 +523,7 @@ def run_parcel(opts, cfg):
     mine = np.arange(rank, P, world)  # round-robin shard
     off_dev = torch.from_numpy(offsets[mine]).to(dev)
     nb = (len(mine) + B - 1) // B
-    pool = [synth_batch(opts.config, B, N, first_plot=(rank * 4 + r) * B) for r in range(4)]  # 256 distinct plots, cycled
+    pool = [synth_batch(4, B, N, first_plot=(rank * 4 + r) * B) for r in range(4)]  # 256 distinct plots, cycled
     pool_host = [{k: v.pin_memory() for k, v in d.items()} for d in pool]
     pool_dev = [{k: v.to(dev) for k, v in d.items()} for d in pool]
     mosaic_host = torch.empty((4, H, W), dtype=torch.float64).pin_memory() if rank == 0 else None
@@ -531,10 +597,7 @@ def run_parcel(opts, cfg):
                 "d2h_bytes_per_step": int(4 * H * W * 8), "api": "InferencePipeline.submit + MapFusion.add/finalize (pinned host in, mosaic out)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": None,
     }
-    if rank == 0:
-        print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    return out
 
 
 def main():
@@ -546,6 +609,10 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="config 3: eager prefetch loop instead of the CUDA-graph step")
+    ap.add_argument("--train-scaling", default="strong", choices=["strong", "weak"], help="--config 3: split 32 plots, or 32 per GPU")
+    ap.add_argument("--extras", default="auto", choices=["auto", "all", "none"],
+                    help="also measure configs 1, 3 (weak + strong), 4 in the same run and attach them to the JSON line "
+                         "(auto: when --config is the default 2)")
     ap.add_argument("--pipeline", type=int, default=3, help="batches in flight for value / e2e (0 = serial steps only)")
     ap.add_argument("--prewarm-s", type=float, default=1.5, help="seconds of untimed steps before anything is timed (clock / cache ramp)")
     opts = ap.parse_args()
@@ -556,24 +623,56 @@ def main():
         os.environ["NCCL_DEBUG"] = "WARN"
     if opts.impl == "reference":
         return run_reference(opts, cfg)
+    world, rank, local, dev = dist_ctx()
     if cfg["mode"] == "train":
-        return run_train(opts, cfg)
-    if cfg["mode"] == "parcel":
-        return run_parcel(opts, cfg)
+        out = run_train(opts, cfg, opts.train_scaling)
+    elif cfg["mode"] == "parcel":
+        out = run_parcel(opts, cfg)
+    else:
+        out = run_infer(opts, cfg)
+    extras = opts.extras == "all" or (opts.extras == "auto" and opts.config == 2)
+    if extras:
+        # The other BASELINE configs under the same (driver-run) command, each a bounded measurement of its own:
+        # config 3 (the one path with collectives) weak AND strong, config 4 (plot-sharded parcel + one all-reduce),
+        # config 1 (single plots).  Failures are reported in place, they never take the headline down.
+        def guarded(fn):
+            try:
+                r = fn()
+                torch.cuda.synchronize()
+                return r
+            except Exception as e:  # noqa: BLE001
+                return {"error": f"{type(e).__name__}: {e}"[:300]}
+        keep = ("metric", "value", "unit", "ms_per_step", "scaling", "config", "collectives", "e2e", "gpu_launches", "serial",
+                "graph_eager_fallback_steps", "n_gpus", "steps")
+        slim = lambda d: {k: d[k] for k in keep if k in d} if "error" not in d else d  # noqa: E731
+        if opts.config != 3:
+            out["train"] = {sc: slim(guarded(lambda sc=sc: run_train(opts, CONFIGS[3], sc, quick=True))) for sc in ("weak", "strong")}
+        if opts.config != 4:
+            out["parcel"] = slim(guarded(lambda: run_parcel(opts, CONFIGS[4])))
+        if opts.config != 1 and world == 1:
+            o1 = argparse.Namespace(**vars(opts))
+            o1.config = 1
+            out["single_plot"] = slim(guarded(lambda: run_infer(o1, CONFIGS[1], cpu_baseline=False)))
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
 
+        from sn2 import comm as sn2_comm
+
+        sn2_comm.close_all()
+        dist.destroy_process_group()
+
+
+def run_infer(opts, cfg, cpu_baseline=True):
+    """Configs 1 / 2: eval forward + both projections on B plots per step and rank (weak scaling: plots are independent)."""
     import torch.distributed as dist
     from model.project_to_2d import project_to_2d_rasters_batched, project_to_plotwise_coverages
     from sn2 import ops
     from sn2.pipeline import StageTimer, forward_eval
     from sn2.synth import synth_batch
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        init_dist(dev)
+    world, rank, local, dev = dist_ctx()
     B, N = cfg["B"], cfg["N"]
     W = max(opts.warmup, 3)
     args, net = make_model(N, local)
@@ -765,16 +864,52 @@ def main():
             roof["fps_distance_evals_per_s"] = evals / (per_step[dom] / 1e3)
             roof["fps_ns_per_iteration"] = per_step[dom] * 1e6 / m
 
+    # ---- every stage against both rooflines (SURVEY.md §8d formulas; E1 / E2 = edge counts of THIS batch) ----------
+    from sn2.pipeline import ForwardTrace
+    with torch.no_grad():
+        tr = ForwardTrace()
+        net(dev_in, trace=tr)
+        E1, E2 = int(tr.tensors["rowptr1"][-1]) / B, int(tr.tensors["rowptr2"][-1]) / B
+        del tr
+    D2 = D * D
+    per_plot = {  # stage: (algorithmic bytes, algorithmic flops [reference formulation], what bounds it)
+        "ingest": (4 * 13 * N + 4 * 12 * N, 0, "hbm"),
+        "fps1": (12 * N + 4 * M1, 8.0 * N * M1, "latency chain (M dependent arg-max iterations on one SM per plot)"),
+        "fps2": (12 * M1 + 4 * M2, 8.0 * M1 * M2, "latency chain; runs on a side stream under sa1_fused"),
+        "sa1_fused": (4 * 11 * N + 4 * M1 + 4 * 16 * M1, 864.0 * E1, "fp32 issue + gather latency"),
+        "sa2_fused": (4 * 19 * M1 + 4 * M2 + 4 * 32 * M2, 1216.0 * E2, "fp32 issue + gather latency"),
+        "global_sa": (4 * 35 * M2 + 256, 4480.0 * M2, "fp32 issue (tiny)"),
+        "fp3": (4 * 32 * M2 + 256 + 4 * 64 * M2, 12288.0 * M2, "fp32 issue (tiny)"),
+        "knn2": (12 * (M1 + M2) + 24 * M1, 0, "L1/L2 gather; side stream (time includes waiting for SMs)"),
+        "fp2": (4 * 64 * M2 + 4 * 16 * M1 + 24 * M1 + 4 * 34 * M1, 5440.0 * M1, "fp32 issue"),
+        "knn1": (12 * (N + M1) + 24 * N, 0, "L1/L2 gather; side stream (time includes waiting for SMs)"),
+        "fp1_head": (4 * 34 * M1 + 32 * N + 24 * N + 32 * N, (2856.0 + 1088 + 160) * N, "fp32 issue"),
+        "project_plotwise": (8 * N + 16 * N + 16, 0, "hbm (tiny)"),
+        "project_rasters": (8 * N + 16 * N + 8 * 3 * D2, 0, "hbm (tiny)"),
+    }
+    fp32_peak = 148 * 128 * 2 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12  # TFLOP/s: 128 FMA / clk / SM
+    roofline_all = {}
+    for k, (by, fl, bound) in per_plot.items():
+        if k not in per_step or per_step[k] <= 0:
+            continue
+        sec = per_step[k] / 1e3
+        e = {"ms": round(per_step[k], 4), "algorithmic_bytes": int(by * B), "hbm_gbs": by * B / sec / 1e9,
+             "hbm_frac": by * B / sec / 1e9 / hbm_peak, "bound": bound}
+        if fl:
+            e["algorithmic_flops"] = fl * B
+            e["fp32_tflops"] = fl * B / sec / 1e12
+            e["fp32_issue_frac"] = fl * B / sec / 1e12 / fp32_peak
+        roofline_all[k] = e
+
     out = {
         "metric": "plots/sec (PointNet2 eval forward + project_to_2d)", "value": value, "unit": "plots/s",
         "n_gpus": world, "steps": opts.steps, "warmup": W, "ms_per_step": ms_res_used / opts.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["name"], "plots_per_gpu_per_step": B, "points_per_plot": N, "max_num_neighbors": 2000,
-                   "batches_in_flight": depth or 1, "cuda_graph_per_batch": bool(use_graph and opts.pipeline),
-                   "passes_ms_per_step": pipe_passes,
-                   "l2": ("inputs larger than L2: steps rotate over 4 distinct input batches (218 MB), K steps timed as one region"
-                          if opts.pipeline else "flushed between timed steps (256 MiB write outside the event pairs)"),
-                   "parallelism": f"plot-sharded x{world}"},
+        "config": static_config(cfg, world),
+        "measurement": {"batches_in_flight": depth or 1, "cuda_graph_per_batch": bool(use_graph and opts.pipeline),
+                        "passes_ms_per_step": pipe_passes,
+                        "timed_region": ("K submits timed as one region (median of 3 passes)" if opts.pipeline else
+                                         "per-step event pairs, L2 flushed between steps (256 MiB write outside the pairs)")},
         "points_per_s": value * N,
         "serial": {"value": serial_value, "ms_per_step": ms_res / opts.steps, "e2e_value": serial_e2e,
                    "e2e_ms_per_step": ms_e2e / opts.steps,
@@ -782,23 +917,30 @@ def main():
         "e2e": {"value": e2e_value, "unit": "plots/s", "ms_per_step": ms_e2e_used / opts.steps,
                 "h2d_bytes_per_step": int(sum(v.numel() * 4 for v in host.values())),
                 "d2h_bytes_per_step": int(pw_host.numel() * 4 + rs_host.numel() * 8),
-                "api": "model.point_net2.PointNet2.forward + model.project_to_2d (pinned host in, host out)"},
+                "api": (f"sn2.pipeline.InferencePipeline.submit / result ({depth} batches in flight): H2D from pinned host memory -> PointNet2 eval "
+                        "forward -> project_to_plotwise_coverages + project_to_2d_rasters -> D2H into pinned host memory, per batch"
+                        if opts.pipeline else
+                        "model.point_net2.PointNet2.forward + model.project_to_2d (pinned host in, host out), one batch at a time")},
+        "e2e_dropin": {"value": serial_e2e, "unit": "plots/s", "ms_per_step": ms_e2e / opts.steps,
+                       "api": "model.point_net2.PointNet2.forward + model.project_to_2d.project_to_plotwise_coverages / "
+                              "project_to_2d_rasters_batched, one call per batch, pinned host in, host out (the reference's own call sequence, "
+                              "predict.py:103-126), L2 flushed between steps"},
         "gpu_launches": launches,
         "clocks": clocks,
         "stage_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
+        "stage_note": "stage times come from the serial pass; fps2 / knn2 / knn1 run on side streams concurrently with sa1_fused, so their "
+                      "event pairs include waiting for SMs (knn2 alone: 0.07 ms under ncu)",
         "roofline": roof,
+        "roofline_all": roofline_all,
     }
-    if rank == 0 and world == 1 and not opts.no_cpu_baseline:
+    if rank == 0 and world == 1 and not opts.no_cpu_baseline and cpu_baseline:
         sample_plots = 16 if cfg["B"] >= 16 else cfg["B"]
         kind, v, best = time_cpu(N, opts.config, sample_plots, repeats=2)
         out["cpu_baseline"] = {"value": v, "unit": "plots/s", "cores": os.cpu_count(), "kind": kind,
                                "sample": f"{sample_plots} plots x {N} pts, best of 2 after 1 warm-up ({best:.2f} s); "
                                          "reference model files verbatim on restated third-party ops" if kind == "reference"
                                else f"{sample_plots} plots x {N} pts, best of 2 after 1 warm-up ({best:.2f} s); oracle port"}
-    if rank == 0:
-        print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    return out
 
 
 if __name__ == "__main__":

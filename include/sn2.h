@@ -213,7 +213,7 @@ int sn2_linear_wgrad(const float *dy, const float *x, long long E, int Co, int C
 /* ---- train-mode MLP block Linear -> ReLU -> BatchNorm1d (batch statistics), csrc/train_mlp.cu ----------------
  * Replaces, for one block of the reference's MLP() (model/point_net2.py:45-53) applied to R rows, the torch
  * sequence addmm / relu / batch_norm forward and their three backward nodes.  Supported (Ci, Co): (11,16) (16,16)
- * (19,32) (80,34) (42,34).  All pointers are device pointers.
+ * (19,32) (80,34) (42,34) and, as tiled kernels for the short wide blocks, (35,64) (96,64): every block of the network.  All pointers are device pointers.
  *   sn2_lrb_fwd        y [R,Co] = relu(x W^T + b); stats [2*Co+1] fp64 = {sum y, sum y^2, rows} (zeroed here);
  *                      rows = R, or min(R, *rows_dev) when rows_dev is given.  x must be 16-byte aligned (its row
  *                      tiles are fetched with TMA bulk copies).
@@ -254,6 +254,60 @@ int sn2_lrb_block_bwd(const float *dz, const float *y, const float *x, const flo
                       const double *stats, long long R, const int *rows_dev, int Co, int Ci, double *sums,
                       float *dgamma, float *dbeta, float *dx, float *partial, int nblk, float *dW, float *db,
                       void *stream);
+
+/* ---- train-mode head + point-wise losses, csrc/train_head.cu ---------------------------------------------------
+ * sn2_head_fwd   replaces model/point_net2.py:141-153 under train(): relu(lin1) -> lin2 -> softmax(4) x sigmoid(1) on
+ *                f1 [R,34] (row stride 34; in_ss nullable = scale|shift [2*34] of the producing block, applied on
+ *                load) with the LIVE parameter tensors W1 [16,34], b1 [16], W2 [5,16], b2 [5] (device) -> cov, proba [R,4].
+ * sn2_head_bwd   recomputes the head from f1; df1 [R,34] (nullable) = gradient of the (BatchNorm-applied) row; dW1, db1,
+ *                dW2, db2 via `partial` [nblk, sn2_head_bwd_partials()] and a fixed-order reduction.  dcov / dproba
+ *                [R,4] nullable (= zero).  dropout p must be 0 (config.py:76 default); otherwise the caller uses torch.
+ * sn2_pointwise_loss_fwd/bwd   learning/loss_functions.py:19-57: out[0] = mean_i -log((p0+p1) pdf0 + p2 pdf1 + p3 pdf2)
+ *                (fp64, pdf [R,3] fp64), out[1] = mean binary entropy of columns 2,3 (EPS 1e-4); sums [2] fp64 scratch;
+ *                bwd: dproba [R,4] = g[0] d out[0] + g[1] d out[1], g [2] fp64 on the device.
+ * sn2_kde_lut    pdf [B*N,3] fp64 = linear interpolation (scipy interp1d / learning/kde_mixture.py:64-75) of Y [3,K]
+ *                over sorted knots X [K] (fp64) at z = fp32(cloud[b,2,n] * z_max), clamped to the grid. */
+int sn2_head_fwd(const float *f1, const float *in_ss, const float *W1, const float *b1, const float *W2, const float *b2,
+                 long long R, float *cov, float *proba, void *stream);
+int sn2_head_bwd_partials(void);
+int sn2_head_bwd(const float *f1, const float *in_ss, const float *W1, const float *b1, const float *W2, const float *b2,
+                 const float *dcov, const float *dproba, long long R, float *df1, float *partial, int nblk, float *dW1,
+                 float *db1, float *dW2, float *db2, void *stream);
+int sn2_pointwise_loss_fwd(const float *proba, const double *pdf, long long R, double *sums, double *out, void *stream);
+int sn2_pointwise_loss_bwd(const float *proba, const double *pdf, const double *g, long long R, float *dproba, void *stream);
+int sn2_kde_lut(const float *cloud, int B, int F, int N, float z_max, const double *X, const double *Y, int K, double *pdf,
+                void *stream);
+
+/* ---- peer-memory collectives for data-parallel training, csrc/comm.cu ----------------------------
+ * The reference has no distributed code; these stand where a DistributedDataParallel / SyncBatchNorm wrapper around
+ * learning/train.py:52-66 would call NCCL.  One region per rank (the ONLY device memory this library allocates),
+ * exported / imported with CUDA IPC; a communicator is the table of all ranks' regions.  Collectives are one-shot
+ * all-reduces over NVLink peer stores, executed inside the kernels that need the result; all collectives of a rank
+ * must be enqueued on one stream and in the same order on every rank.  comm == NULL means a single rank (no exchange).
+ *   sn2_bn_finalize_sync   sn2_bn_finalize with stats [2Co+1] summed over the ranks first (in place).
+ *   sn2_bn_bwd_sync        sn2_bn_param_grad on this rank's sums, then sums [2Co] summed over the ranks (in place).
+ *   sn2_adam_step          grad <- sum_r gscale_r * grad_r (in place), then torch.optim.Adam's update of the flat
+ *                          parameter bucket (L2 weight decay, bias correction) with lr and step read from the device.
+ *   sn2_comm_status        synchronous: collectives completed, sticky error word (non-zero: a wait timed out). */
+size_t sn2_comm_region_bytes(void);
+int sn2_comm_max_world(void);
+int sn2_comm_max_bytes(void);
+int sn2_comm_region_alloc(void **region);
+int sn2_comm_region_free(void *region);
+int sn2_comm_ipc_export(void *region, void *handle64_host);
+int sn2_comm_ipc_import(const void *handle64_host, void **peer_region);
+int sn2_comm_ipc_release(void *peer_region);
+int sn2_comm_create(int rank, int world, void *const *regions_host, void **comm_out);
+int sn2_comm_destroy(void *comm);
+int sn2_comm_status(void *comm, long long *seq_out, long long *err_out);
+int sn2_comm_allreduce_f64(void *comm, double *buf, int n, void *stream);
+int sn2_comm_allreduce_f32(void *comm, float *buf, int n, float scale, void *stream);
+int sn2_bn_finalize_sync(void *comm, double *stats, const float *gamma, const float *beta, float eps, float momentum,
+                         float *running_mean, float *running_var, long long *num_batches_tracked, float *ss, int Co,
+                         void *stream);
+int sn2_bn_bwd_sync(void *comm, double *sums, const float *ss, int Co, float *dgamma, float *dbeta, void *stream);
+int sn2_adam_step(void *comm, float *grad, float gscale, float *param, float *m, float *v, long long n, const float *lr_dev,
+                  float b1, float b2, float eps, float wd, long long *step_dev, void *stream);
 
 /* ================= local-map fusion (BASELINE config 4), csrc/fusion.cu =============
  * Weighted-average mosaic of per-plot rasters into the parcel grid; replaces add_weights_band_to_rasters +

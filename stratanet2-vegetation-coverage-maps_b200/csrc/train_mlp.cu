@@ -590,15 +590,245 @@ static int launch_lrb_bwd(const float *dz, const float *y, const float *x, const
     return SN2_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The two wide, short blocks -- SA3 [35 -> 64] and FP3 [96 -> 64] over the B * M2 sa2 points (20 000 rows at config 3)
+// -- do not fit the row-per-thread kernels above (64 accumulators + 64 + 64 statistics per thread).  Same interface,
+// different mapping: 32-row tiles in shared memory, thread = (row group, output channel) forward and in the
+// reductions, thread = (row, input column) for dx, thread = set of (output, input) pairs for the weight gradient.
+// A few tens of microseconds each; they exist so that EVERY block of the network runs the same fused
+// Linear-ReLU-BatchNorm path (statistics as raw fp64 sums: one code path for SyncBatchNorm).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int LS_T = 256, LS_TR = 32;
+
+template <int CI, int CO>
+struct LrbSmall {
+    static constexpr int G = LS_T / CO;                 // row groups
+    static constexpr int RG = (LS_TR + G - 1) / G;      // rows per group and tile
+    static constexpr int XS = CI + 1;                   // odd / padded row strides
+    static constexpr int DS = CO + 1;
+    static constexpr int NP = CO * (CI + 1);
+    static constexpr int NPT = (NP + LS_T - 1) / LS_T;  // (output, input) pairs per thread
+    static constexpr size_t SMEM_FWD = sizeof(float) * ((size_t)CI * CO + CO + LS_TR * XS) + sizeof(double) * 2 * CO;
+    static constexpr size_t SMEM_BWD = sizeof(float) * ((size_t)CI * CO + LS_TR * XS + LS_TR * DS + 3 * CO);
+    static_assert(LS_T % CO == 0, "CO must divide the CTA size");
+};
+
+template <int CI>
+__device__ __forceinline__ void ls_load_x(const float *__restrict__ x, const float *__restrict__ in_ss, long long base, int rows, float *xS)
+{
+    for (int e = threadIdx.x; e < rows * CI; e += LS_T) {
+        const int r = e / CI, k = e - r * CI;
+        float v = __ldg(x + base * CI + e);
+        if (in_ss) v = fmaf(v, __ldg(in_ss + k), __ldg(in_ss + CI + k));
+        xS[r * (CI + 1) + k] = v;
+    }
+}
+
+template <int CI, int CO>
+__global__ void __launch_bounds__(LS_T)
+lrb_small_fwd_kernel(const float *__restrict__ x, const float *__restrict__ in_ss, const float *__restrict__ W,
+                     const float *__restrict__ b, long long R, const int *__restrict__ rows_dev, float *__restrict__ y,
+                     double *__restrict__ stats)
+{
+    if (rows_dev) R = min(R, (long long)__ldg(rows_dev));
+    using L = LrbSmall<CI, CO>;
+    extern __shared__ __align__(16) unsigned char lrb_smem[];
+    double *red = reinterpret_cast<double *>(lrb_smem);
+    float *Wt = reinterpret_cast<float *>(red + 2 * CO);  // [CI][CO]
+    float *bS = Wt + CI * CO;
+    float *xS = bS + CO;
+    const int tid = threadIdx.x, g = tid / CO, o = tid - g * CO;
+    for (int e = tid; e < CI * CO; e += LS_T) {
+        const int k = e / CO, oo = e - k * CO;
+        Wt[e] = __ldg(W + oo * CI + k);
+    }
+    for (int e = tid; e < CO; e += LS_T) bS[e] = __ldg(b + e);
+    for (int e = tid; e < 2 * CO; e += LS_T) red[e] = 0.0;
+    float s1 = 0.f, s2 = 0.f;
+    const long long ntiles = (R + LS_TR - 1) / LS_TR;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long base = tile * LS_TR;
+        const int rows = (int)min((long long)LS_TR, R - base);
+        __syncthreads();
+        ls_load_x<CI>(x, in_ss, base, rows, xS);
+        __syncthreads();
+        float acc[L::RG];
+#pragma unroll
+        for (int i = 0; i < L::RG; ++i) acc[i] = bS[o];
+        for (int k = 0; k < CI; ++k) {
+            const float w = Wt[k * CO + o];
+#pragma unroll
+            for (int i = 0; i < L::RG; ++i) acc[i] = fmaf(xS[(g * L::RG + i) * L::XS + k], w, acc[i]);  // rows past `rows`: stale, unused
+        }
+#pragma unroll
+        for (int i = 0; i < L::RG; ++i) {
+            const int r = g * L::RG + i;
+            if (r < rows) {
+                const float v = fmaxf(acc[i], 0.f);
+                y[(base + r) * CO + o] = v;
+                s1 += v;
+                s2 = fmaf(v, v, s2);
+            }
+        }
+    }
+    __syncthreads();
+    atomicAdd(red + o, (double)s1);
+    atomicAdd(red + CO + o, (double)s2);
+    __syncthreads();
+    for (int e = tid; e < 2 * CO; e += LS_T) atomicAdd(stats + e, red[e]);
+}
+
+template <int CO>
+__global__ void __launch_bounds__(LS_T)
+lrb_small_bwd_reduce_kernel(const float *__restrict__ dz, const float *__restrict__ y, long long R,
+                            const int *__restrict__ rows_dev, double *__restrict__ sums)
+{
+    if (rows_dev) R = min(R, (long long)__ldg(rows_dev));
+    __shared__ double red[2 * CO];
+    const int tid = threadIdx.x, G = LS_T / CO, g = tid / CO, o = tid - g * CO;
+    for (int e = tid; e < 2 * CO; e += LS_T) red[e] = 0.0;
+    float a1 = 0.f, a2 = 0.f;
+    for (long long r = (long long)blockIdx.x * G + g; r < R; r += (long long)gridDim.x * G) {
+        const float d = __ldg(dz + r * CO + o);
+        a1 += d;
+        a2 = fmaf(d, __ldg(y + r * CO + o), a2);
+    }
+    __syncthreads();
+    atomicAdd(red + o, (double)a1);
+    atomicAdd(red + CO + o, (double)a2);
+    __syncthreads();
+    for (int e = tid; e < 2 * CO; e += LS_T) atomicAdd(sums + e, red[e]);
+}
+
+template <int CI, int CO>
+__global__ void __launch_bounds__(LS_T)
+lrb_small_bwd_kernel(const float *__restrict__ dz, const float *__restrict__ y, const float *__restrict__ x,
+                     const float *__restrict__ in_ss, const float *__restrict__ W, const float *__restrict__ ss,
+                     const double *__restrict__ sums, const double *__restrict__ stats, long long R,
+                     const int *__restrict__ rows_dev, float *__restrict__ dx, float *__restrict__ partial)
+{
+    if (rows_dev) R = min(R, (long long)__ldg(rows_dev));
+    using L = LrbSmall<CI, CO>;
+    extern __shared__ __align__(16) unsigned char lrb_smem[];
+    float *Ws = reinterpret_cast<float *>(lrb_smem);  // [CO][CI]
+    float *xS = Ws + CO * CI;                          // [32][CI+1], column CI = 1 (bias)
+    float *dyS = xS + LS_TR * L::XS;                   // [32][CO+1]
+    float *cA = dyS + LS_TR * L::DS, *cB = cA + CO, *cC = cB + CO;
+    const int tid = threadIdx.x, g = tid / CO, o = tid - g * CO;
+    for (int e = tid; e < CO * CI; e += LS_T) Ws[e] = __ldg(W + e);
+    if (tid < CO) {
+        const double n = stats[2 * CO];
+        const float sc = ss[tid], mean = ss[2 * CO + tid], inv = ss[3 * CO + tid];
+        const double S1 = sums[tid], S2 = sums[CO + tid];
+        const float m1 = (float)(S1 / n);
+        const float m2 = (float)((double)inv * (S2 - (double)mean * S1) / n);
+        const float kb = -inv * m2;
+        cA[tid] = sc;
+        cB[tid] = sc * kb;
+        cC[tid] = sc * (-m1 - mean * kb);
+    }
+    float acc[L::NPT];
+#pragma unroll
+    for (int j = 0; j < L::NPT; ++j) acc[j] = 0.f;
+    const long long ntiles = (R + LS_TR - 1) / LS_TR;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long base = tile * LS_TR;
+        const int rows = (int)min((long long)LS_TR, R - base);
+        __syncthreads();
+        ls_load_x<CI>(x, in_ss, base, rows, xS);
+        if (tid < LS_TR) xS[tid * L::XS + CI] = 1.f;
+#pragma unroll
+        for (int i = 0; i < L::RG; ++i) {
+            const int r = g * L::RG + i;
+            float d = 0.f;
+            if (r < rows) {
+                const float v = __ldg(y + (base + r) * CO + o);
+                d = v > 0.f ? fmaf(cA[o], __ldg(dz + (base + r) * CO + o), fmaf(cB[o], v, cC[o])) : 0.f;
+            }
+            if (r < LS_TR) dyS[r * L::DS + o] = d;
+        }
+        __syncthreads();
+        if (dx) {
+            for (int e = tid; e < rows * CI; e += LS_T) {
+                const int r = e / CI, k = e - r * CI;
+                float a = 0.f;
+#pragma unroll 8
+                for (int oo = 0; oo < CO; ++oo) a = fmaf(dyS[r * L::DS + oo], Ws[oo * CI + k], a);
+                dx[base * CI + e] = a;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < L::NPT; ++j) {
+            const int pr = tid + j * LS_T;
+            if (pr < L::NP) {
+                const int oo = pr / (CI + 1), k = pr - oo * (CI + 1);
+                float a = acc[j];
+                for (int r = 0; r < rows; ++r) a = fmaf(dyS[r * L::DS + oo], xS[r * L::XS + k], a);
+                acc[j] = a;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < L::NPT; ++j) {
+        const int pr = tid + j * LS_T;
+        if (pr < L::NP) partial[(size_t)blockIdx.x * L::NP + pr] = acc[j];
+    }
+}
+
+template <int CI, int CO>
+static int launch_lrb_small_fwd(const float *x, const float *in_ss, const float *W, const float *b, long long R, const int *rows_dev,
+                                float *y, double *stats, cudaStream_t st)
+{
+    using L = LrbSmall<CI, CO>;
+    auto kern = lrb_small_fwd_kernel<CI, CO>;
+    SN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM_FWD), "lrb_small_fwd attr");
+    SN2_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * CO, st), "lrb_small_fwd memset");
+    set_count_kernel<<<1, 1, 0, st>>>(stats, CO, R, rows_dev);
+    const int grid = (int)min((R + LS_TR - 1) / LS_TR, (long long)148 * 2);
+    kern<<<grid, LS_T, L::SMEM_FWD, st>>>(x, in_ss, W, b, R, rows_dev, y, stats);
+    SN2_LAUNCH_CHECK("lrb_small_fwd_kernel");
+    return SN2_OK;
+}
+
+template <int CO>
+static int launch_lrb_small_bwd_reduce(const float *dz, const float *y, long long R, const int *rows_dev, double *sums, cudaStream_t st)
+{
+    SN2_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * CO, st), "lrb_small_bwd_reduce memset");
+    const int G = LS_T / CO;
+    const int grid = (int)min((R + G - 1) / G, (long long)148 * 2);
+    lrb_small_bwd_reduce_kernel<CO><<<grid, LS_T, 0, st>>>(dz, y, R, rows_dev, sums);
+    SN2_LAUNCH_CHECK("lrb_small_bwd_reduce_kernel");
+    return SN2_OK;
+}
+
+template <int CI, int CO>
+static int launch_lrb_small_bwd(const float *dz, const float *y, const float *x, const float *in_ss, const float *W, const float *ss,
+                                const double *sums, const double *stats, long long R, const int *rows_dev, float *dx, float *partial,
+                                int nblk, float *dW, float *db, cudaStream_t st)
+{
+    using L = LrbSmall<CI, CO>;
+    auto kern = lrb_small_bwd_kernel<CI, CO>;
+    SN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM_BWD), "lrb_small_bwd attr");
+    const int grid = (int)min((R + LS_TR - 1) / LS_TR, (long long)min(nblk, 148));
+    kern<<<grid, LS_T, L::SMEM_BWD, st>>>(dz, y, x, in_ss, W, ss, sums, stats, R, rows_dev, dx, partial);
+    SN2_LAUNCH_CHECK("lrb_small_bwd_kernel");
+    lrb_wgrad_reduce_kernel<<<(L::NP * 32 + 255) / 256, 256, 0, st>>>(partial, grid, CO, CI, dW, db);
+    SN2_LAUNCH_CHECK("lrb_wgrad_reduce_kernel");
+    return SN2_OK;
+}
+
 }  // namespace sn2
 
-// (Ci, Co) pairs of the train-mode blocks that see >= 65 536 rows: SA1 [11,16,16], SA2 [19,32], FP2 [80,34], FP1 [42,34]
+// (Ci, Co) pairs of the train-mode blocks: SA1 [11,16,16], SA2 [19,32], FP2 [80,34], FP1 [42,34] (row-per-thread, TMA fed)
 #define SN2_LRB_SHAPES(X) X(11, 16) X(16, 16) X(19, 32) X(80, 34) X(42, 34)
+// SA3 [35,64], FP3 [96,64]: the tiled kernels
+#define SN2_LRB_SMALL_SHAPES(X) X(35, 64) X(96, 64)
 
 extern "C" int sn2_lrb_supported(int Co, int Ci)
 {
 #define X(ci, co) if (Ci == ci && Co == co) return 1;
     SN2_LRB_SHAPES(X)
+    SN2_LRB_SMALL_SHAPES(X)
 #undef X
     return 0;
 }
@@ -607,6 +837,9 @@ extern "C" int sn2_lrb_fwd(const float *x, const float *in_ss, const float *W, c
                            int Co, int Ci, float *y, double *stats, void *stream)
 {
     if (!x || !W || !b || !y || !stats || R <= 0) return SN2_EINVAL;
+#define X(ci, co) if (Ci == ci && Co == co) return sn2::launch_lrb_small_fwd<ci, co>(x, in_ss, W, b, R, rows_dev, y, stats, (cudaStream_t)stream);
+    SN2_LRB_SMALL_SHAPES(X)
+#undef X
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return SN2_EINVAL;  // TMA bulk copies read 16-byte aligned tiles
 #define X(ci, co) if (Ci == ci && Co == co) return sn2::launch_lrb_fwd<ci, co>(x, in_ss, W, b, R, rows_dev, y, stats, (cudaStream_t)stream);
     SN2_LRB_SHAPES(X)
@@ -644,6 +877,7 @@ extern "C" int sn2_lrb_bwd_reduce(const float *dz, const float *y, long long R, 
     case 16: return sn2::launch_lrb_bwd_reduce<16>(dz, y, R, rows_dev, sums, (cudaStream_t)stream);
     case 32: return sn2::launch_lrb_bwd_reduce<32>(dz, y, R, rows_dev, sums, (cudaStream_t)stream);
     case 34: return sn2::launch_lrb_bwd_reduce<34>(dz, y, R, rows_dev, sums, (cudaStream_t)stream);
+    case 64: return sn2::launch_lrb_small_bwd_reduce<64>(dz, y, R, rows_dev, sums, (cudaStream_t)stream);
     default: return SN2_EUNSUPPORTED;
     }
 }
@@ -661,6 +895,11 @@ extern "C" int sn2_lrb_bwd(const float *dz, const float *y, const float *x, cons
                            float *partial, int nblk, float *dW, float *db, void *stream)
 {
     if (!dz || !y || !x || !W || !ss || !sums || !stats || !partial || !dW || !db || R <= 0 || nblk <= 0) return SN2_EINVAL;
+#define X(ci, co)                  \
+    if (Ci == ci && Co == co)      \
+        return sn2::launch_lrb_small_bwd<ci, co>(dz, y, x, in_ss, W, ss, sums, stats, R, rows_dev, dx, partial, nblk, dW, db, (cudaStream_t)stream);
+    SN2_LRB_SMALL_SHAPES(X)
+#undef X
     if (((reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x) |
           reinterpret_cast<uintptr_t>(dx)) & 15) != 0)
         return SN2_EINVAL;  // TMA bulk copies move 16-byte aligned tiles

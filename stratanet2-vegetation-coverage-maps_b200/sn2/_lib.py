@@ -59,12 +59,35 @@ SIGNATURES = {
     "sn2_bn_apply": [_vp, _vp, _ll, _vp, _i, _vp, _vp],
     "sn2_lrb_bwd_reduce": [_vp, _vp, _ll, _vp, _i, _vp, _vp],
     "sn2_lrb_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp],
+    "sn2_head_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp],
+    "sn2_head_bwd_partials": [],
+    "sn2_head_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp],
+    "sn2_pointwise_loss_fwd": [_vp, _vp, _ll, _vp, _vp, _vp],
+    "sn2_pointwise_loss_bwd": [_vp, _vp, _vp, _ll, _vp, _vp],
+    "sn2_kde_lut": [_vp, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp],
+    "sn2_comm_region_bytes": [],
+    "sn2_comm_max_world": [],
+    "sn2_comm_max_bytes": [],
+    "sn2_comm_region_alloc": [_vp],
+    "sn2_comm_region_free": [_vp],
+    "sn2_comm_ipc_export": [_vp, _vp],
+    "sn2_comm_ipc_import": [_vp, _vp],
+    "sn2_comm_ipc_release": [_vp],
+    "sn2_comm_create": [_i, _i, _vp, _vp],
+    "sn2_comm_destroy": [_vp],
+    "sn2_comm_status": [_vp, _vp, _vp],
+    "sn2_comm_allreduce_f64": [_vp, _vp, _i, _vp],
+    "sn2_comm_allreduce_f32": [_vp, _vp, _i, _f, _vp],
+    "sn2_bn_finalize_sync": [_vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp],
+    "sn2_bn_bwd_sync": [_vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "sn2_adam_step": [_vp, _vp, _f, _vp, _vp, _vp, _ll, _vp, _f, _f, _f, _f, _vp, _vp],
     "sn2_fuse_accumulate": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "sn2_fuse_finalize": [_vp, _vp, _vp, _i, _i, _vp, _vp],
     "sn2_project_plotwise": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "sn2_project_rasters": [_vp, _vp, _ll, _ll, _ll, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp],
 }
-_RESTYPES = {"sn2_error_string": ctypes.c_char_p, "sn2_last_cuda_error": ctypes.c_char_p}
+_RESTYPES = {"sn2_error_string": ctypes.c_char_p, "sn2_last_cuda_error": ctypes.c_char_p,
+             "sn2_comm_region_bytes": ctypes.c_size_t}
 
 
 def load(require_cuda: bool = True):

@@ -11,6 +11,7 @@ import ctypes
 import torch
 
 from . import _lib, ops
+from . import comm as _comm
 from ._lib import check, dptr, stream_ptr
 
 
@@ -222,9 +223,17 @@ class LinReluBN(torch.autograd.Function):
         gp, btp = dptr(_c(gamma), torch.float32), dptr(_c(beta), torch.float32)
         st = stream_ptr()
         group = _sync_group(bn)
+        peer = _comm.get_comm(group) if group is not None else None
         if group is None:
             check(lib.sn2_lrb_block_fwd(dptr(x, torch.float32), ip, wp, bp, gp, btp, float(bn.eps), float(bn.momentum), rm, rv, nbt,
                                         R, rp, Co, Ci, dptr(y), dptr(stats), dptr(ss), dptr(z), st), "sn2_lrb_block_fwd")
+        elif peer is not None:
+            # the statistics are summed over the ranks INSIDE the finalize kernel (NVLink peer stores, csrc/comm.cu)
+            check(lib.sn2_lrb_fwd(dptr(x, torch.float32), ip, wp, bp, R, rp, Co, Ci, dptr(y), dptr(stats), st), "sn2_lrb_fwd")
+            check(lib.sn2_bn_finalize_sync(peer.handle, dptr(stats), gp, btp, float(bn.eps), float(bn.momentum), rm, rv, nbt,
+                                           dptr(ss), Co, st), "sn2_bn_finalize_sync")
+            if apply:
+                check(lib.sn2_bn_apply(dptr(y), dptr(ss), R, rp, Co, dptr(z), st), "sn2_bn_apply")
         else:
             check(lib.sn2_lrb_fwd(dptr(x, torch.float32), ip, wp, bp, R, rp, Co, Ci, dptr(y), dptr(stats), st), "sn2_lrb_fwd")
             torch.distributed.all_reduce(stats, group=group)
@@ -234,7 +243,7 @@ class LinReluBN(torch.autograd.Function):
                 check(lib.sn2_bn_apply(dptr(y), dptr(ss), R, rp, Co, dptr(z), st), "sn2_bn_apply")
         ops._count(5 if apply else 4)
         ctx.save_for_backward(x, y, weight, ss, stats)
-        ctx.group, ctx.rows, ctx.in_ss = group, rows, in_ss
+        ctx.group, ctx.rows, ctx.in_ss, ctx.peer = group, rows, in_ss, peer
         if apply:
             return z
         ctx.mark_non_differentiable(ss)
@@ -262,6 +271,11 @@ class LinReluBN(torch.autograd.Function):
             check(lib.sn2_lrb_block_bwd(dptr(dz, torch.float32), dptr(y), dptr(x), ip, wp, dptr(ss), dptr(stats), R, rp, Co, Ci, dptr(sums),
                                         dgp, dbp, dptr(dx), dptr(partial), LinReluBN.NBLK, dptr(dW), dptr(db), st),
                   "sn2_lrb_block_bwd")
+        elif ctx.peer is not None:
+            check(lib.sn2_lrb_bwd_reduce(dptr(dz, torch.float32), dptr(y), R, rp, Co, dptr(sums), st), "sn2_lrb_bwd_reduce")
+            check(lib.sn2_bn_bwd_sync(ctx.peer.handle, dptr(sums), dptr(ss), Co, dgp, dbp, st), "sn2_bn_bwd_sync")
+            check(lib.sn2_lrb_bwd(dptr(dz), dptr(y), dptr(x), ip, wp, dptr(ss), dptr(sums), dptr(stats), R, rp, Co, Ci, dptr(dx),
+                                  dptr(partial), LinReluBN.NBLK, dptr(dW), dptr(db), st), "sn2_lrb_bwd")
         else:
             check(lib.sn2_lrb_bwd_reduce(dptr(dz, torch.float32), dptr(y), R, rp, Co, dptr(sums), st), "sn2_lrb_bwd_reduce")
             check(lib.sn2_bn_param_grad(dptr(sums), dptr(ss), Co, dgp, dbp, st), "sn2_bn_param_grad")  # this rank's sums
@@ -270,6 +284,47 @@ class LinReluBN(torch.autograd.Function):
                                   dptr(partial), LinReluBN.NBLK, dptr(dW), dptr(db), st), "sn2_lrb_bwd")
         ops._count(5)
         return dx, dW, db, dgb[0], dgb[1], None, None, None, None
+
+
+class Head(torch.autograd.Function):
+    """relu(lin1) -> lin2 -> softmax(4) x sigmoid(1) of reference model/point_net2.py:141-153 (dropout p = 0) in one
+    kernel each way; the backward recomputes the head from its input row, nothing else is saved.
+    in_ss: scale | shift of the producing LinReluBN block when its BatchNorm transform was deferred."""
+
+    NBLK = 148 * 4
+
+    @staticmethod
+    def forward(ctx, f1, W1, b1, W2, b2, in_ss=None):
+        lib = _lib.load()
+        f1 = _c(f1)
+        R = f1.shape[0]
+        if f1.shape[1] != 34 or tuple(W1.shape) != (16, 34) or tuple(W2.shape) != (5, 16):
+            raise RuntimeError("sn2 Head: built for lin1 [34 -> 16], lin2 [16 -> 5] (the reference head)")
+        cov = torch.empty((R, 4), dtype=torch.float32, device=f1.device)
+        proba = torch.empty((R, 4), dtype=torch.float32, device=f1.device)
+        check(lib.sn2_head_fwd(dptr(f1, torch.float32), dptr(in_ss, torch.float32), dptr(_c(W1), torch.float32), dptr(_c(b1)),
+                               dptr(_c(W2)), dptr(_c(b2)), R, dptr(cov), dptr(proba), stream_ptr()), "sn2_head_fwd")
+        ops._count(1)
+        ctx.save_for_backward(f1, W1, b1, W2, b2)
+        ctx.in_ss = in_ss
+        return cov, proba
+
+    @staticmethod
+    def backward(ctx, dcov, dproba):
+        lib = _lib.load()
+        f1, W1, b1, W2, b2 = ctx.saved_tensors
+        R, dev = f1.shape[0], f1.device
+        df1 = torch.empty_like(f1) if ctx.needs_input_grad[0] else None
+        grads = torch.empty(16 * 34 + 16 + 5 * 16 + 5, dtype=torch.float32, device=dev)
+        dW1, db1, dW2, db2 = grads[:544].view(16, 34), grads[544:560], grads[560:640].view(5, 16), grads[640:645]
+        partial = torch.empty((Head.NBLK, int(lib.sn2_head_bwd_partials())), dtype=torch.float32, device=dev)
+        dcp = dptr(_c(dcov), torch.float32) if dcov is not None else None
+        dpp = dptr(_c(dproba), torch.float32) if dproba is not None else None
+        check(lib.sn2_head_bwd(dptr(f1), dptr(ctx.in_ss, torch.float32), dptr(_c(W1)), dptr(_c(b1)), dptr(_c(W2)), dptr(_c(b2)), dcp, dpp, R,
+                               dptr(df1), dptr(partial), Head.NBLK, dptr(dW1), ctypes.c_void_p(db1.data_ptr()),
+                               ctypes.c_void_p(dW2.data_ptr()), ctypes.c_void_p(db2.data_ptr()), stream_ptr()), "sn2_head_bwd")
+        ops._count(2)
+        return df1, dW1, db1, dW2, db2, None
 
 
 def _sync_group(bn):
@@ -303,8 +358,8 @@ def tall_linear(lin, x):
 
 
 def run_mlp(seq, x, rows=None, defer_last: bool = False):
-    """Apply a reference MLP (Sequential of (Linear, ReLU, BatchNorm1d) blocks).  Blocks that see >= 65 536 rows in
-    training run as the fused LinReluBN (SN2_FUSED_MLP=0 -> the torch modules, with TallLinear where it pays); between
+    """Apply a reference MLP (Sequential of (Linear, ReLU, BatchNorm1d) blocks).  Blocks of a supported shape (all seven of
+    the network; SN2_FUSED_MLP_MIN_ROWS sets a row floor) in training run as the fused LinReluBN (SN2_FUSED_MLP=0 -> the torch modules, with TallLinear where it pays); between
     two fused blocks the BatchNorm transform is not materialised (the consumer applies it on load).
     rows: device int32 [1] live row count when x is a fixed-capacity buffer (graph replay); needs the fused blocks.
     defer_last: return (y, ss) instead of z when the last block is fused -- for SegmentMax(y, rowptr, ss); ss is
@@ -315,7 +370,8 @@ def run_mlp(seq, x, rows=None, defer_last: bool = False):
     tall = os.environ.get("SN2_TALL_LINEAR", "1") == "1"
     defer_ok = os.environ.get("SN2_DEFER_BN", "1") == "1"
     blocks = list(seq)
-    fusable = [fused and x.shape[0] >= 65536 and _fusable_block(lib, b, x) for b in blocks]
+    min_rows = int(os.environ.get("SN2_FUSED_MLP_MIN_ROWS", "1"))  # every block of the network has a fused kernel
+    fusable = [fused and x.shape[0] >= min_rows and _fusable_block(lib, b, x) for b in blocks]
     in_ss = None
     for i, block in enumerate(blocks):
         lin = block[0]

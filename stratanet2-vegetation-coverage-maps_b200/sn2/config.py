@@ -25,6 +25,11 @@ def default_args(**overrides) -> Namespace:
         patience_in_epochs=30,          # config.py:92
         epoch_to_start_early_stop=250,  # config.py:90
         log_embeddings=False,           # config.py:41
+        m=0.10,                         # config.py:70  weight of the NLL term
+        e=0.2 / 5,                      # config.py:71  weight of the entropy term
+        z_max=24.24,                    # config.py:73
+        znorm_radius_in_meters=1.5,     # config.py:72
+        lr=1e-3, wd=0.001, step_size=1, lr_decay=0.985, batch_size=20,  # config.py:84-98
         current_fold_id=0,
         stats_path=".",
     )

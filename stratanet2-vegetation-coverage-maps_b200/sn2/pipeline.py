@@ -367,7 +367,7 @@ def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num
     backward).  `structure`: a TrainStructure prepared ahead of time (StructurePrefetcher)."""
     import torch.nn.functional as F
 
-    from .autograd_ops import EdgeMsg, Interp3, InterpPlot, SegmentMax, run_mlp, tall_linear
+    from .autograd_ops import EdgeMsg, Head, Interp3, InterpPlot, SegmentMax, run_mlp, tall_linear
 
     invalidate_packed(model)  # running statistics are about to change behind torch's back
     S = structure if structure is not None else TrainStructure(model, xyz, cloud, device, max_num_neighbors, timer)
@@ -384,15 +384,27 @@ def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num
     x1, _ = SegmentMax.apply(y1, rowptr1, ss1)
     y2, ss2 = run_mlp(sa2.conv.local_nn, EdgeMsg.apply(x1, pos1, pos2, rowptr2, col2, rows2), rows2, defer_last=True)
     x2, _ = SegmentMax.apply(y2, rowptr2, ss2)
-    g, _ = SegmentMax.apply(model.sa3_module.nn(torch.cat([x2, pos2[:, :3]], dim=1)), plot_ptr)
-    f3 = model.fp3_module.nn(torch.cat([InterpPlot.apply(g, pos2, M2), x2], dim=1))
+    y3, ss3 = run_mlp(model.sa3_module.nn, torch.cat([x2, pos2[:, :3]], dim=1), defer_last=True)
+    g, _ = SegmentMax.apply(y3, plot_ptr, ss3)
+    f3 = run_mlp(model.fp3_module.nn, torch.cat([InterpPlot.apply(g, pos2, M2), x2], dim=1))
     f2 = run_mlp(model.fp2_module.nn, torch.cat([Interp3.apply(f3, nbr2, w2), x1], dim=1))
-    f1 = run_mlp(model.fp1_module.nn, torch.cat([Interp3.apply(f2, nbr1, w1), feat0], dim=1))
-    h = F.relu(tall_linear(model.lin1, f1))
-    h = F.dropout(h, p=model.drop, training=True)
-    scores = tall_linear(model.lin2, h)
-    proba = torch.softmax(scores[:, :4], dim=1)
-    cov = proba * torch.sigmoid(scores[:, 4:5])
+    fused_head = model.drop == 0.0 and os.environ.get("SN2_FUSED_HEAD", "1") == "1"
+    y1f, ss1f = run_mlp(model.fp1_module.nn, torch.cat([Interp3.apply(f2, nbr1, w1), feat0], dim=1), defer_last=True) \
+        if fused_head else (run_mlp(model.fp1_module.nn, torch.cat([Interp3.apply(f2, nbr1, w1), feat0], dim=1)), None)
+    if fused_head:
+        # FP1's BatchNorm transform is applied on load by the head kernel; lin1 / lin2 / softmax / sigmoid fused
+        cov, proba = Head.apply(y1f, model.lin1.weight, model.lin1.bias, model.lin2.weight, model.lin2.bias, ss1f)
+        f1 = None
+        if trace is not None:
+            with torch.no_grad():
+                f1 = y1f * ss1f[:34] + ss1f[34:68] if ss1f is not None else y1f
+    else:
+        f1 = y1f
+        h = F.relu(tall_linear(model.lin1, f1))
+        h = F.dropout(h, p=model.drop, training=True)
+        scores = tall_linear(model.lin2, h)
+        proba = torch.softmax(scores[:, :4], dim=1)
+        cov = proba * torch.sigmoid(scores[:, 4:5])
     if trace is not None:
         trace.tensors.update(cloud_dev=cloud_d, pos0=pos0, feat0=feat0, idx1=idx1, pos1=pos1, rowptr1=rowptr1, col1=col1,
                              x1=x1, idx2=idx2, pos2=pos2, rowptr2=rowptr2, col2=col2, x2=x2, G=g, fp3=f3, fp2=f2, fp1=f1,
@@ -442,9 +454,12 @@ class GraphedTrainStep:
     lists have a fixed capacity and every edge-level kernel reads the live edge count from device memory
     (`rows_dev` in include/sn2.h), so all shapes inside the graph are static.  If a batch exceeds the capacity the
     graph is re-captured with a larger one.  `step_fn` must not synchronise with the host (no .item(), no printing
-    of tensors); the optimizer must be capture-safe (e.g. torch.optim.Adam(..., capturable=True)); BatchNorm must
-    not be SyncBatchNorm (single process).  Python numbers read inside `step_fn` (learning rate, loss weights) are
-    baked in: use tensors updated in place, or `recapture()`.  The three warm-up executions that capture needs are rolled back
+    of tensors); the optimizer must be capture-safe (sn2.optim.FusedAdam, or torch.optim.Adam(..., capturable=True)).
+    Data-parallel jobs capture too: with sn2.comm's peer communicator the SyncBatchNorm statistics and the gradient
+    sum are ordinary kernels of ours (every rank captures at its first call, together; a later batch that does not
+    fit the graph runs eagerly on that rank instead of re-capturing, see __call__).  Python numbers read inside
+    `step_fn` (loss weights; the learning rate of a torch optimizer) are baked in: use tensors updated in place, or
+    `recapture()`; FusedAdam reads its learning rate from the device and follows a scheduler without re-capture.  The three warm-up executions that capture needs are rolled back
     (parameters, buffers and optimizer state are restored), so results match the eager loop step for step.
     Every tensor value of the batch dict (xyz, cloud, targets ...) is copied into a static buffer of the same shape;
     all batches must therefore have the same shapes."""
@@ -464,7 +479,14 @@ class GraphedTrainStep:
         self.loss = None
         self.captures = 0
         self.replays = 0
+        self.eager_steps = 0
         self.launches_per_replay = 0
+
+    @staticmethod
+    def _collective() -> bool:
+        import torch.distributed as dist
+
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
     # -- state roll-back around the warm-up executions ---------------------------------------------------------
     def _snapshot(self):
@@ -541,9 +563,23 @@ class GraphedTrainStep:
         if S.stream != cur:
             cur.wait_event(S.done)
         st = self.static_struct
-        if (self.graph is None or S.col1.numel() > st.cap1 or S.col2.numel() > st.cap2 or (S.B, S.N) != (st.B, st.N)
-                or any(torch.is_tensor(v) and k in self.static_batch and tuple(v.shape) != tuple(self.static_batch[k].shape)
-                       for k, v in batch.items() if k != "sn2_structure")):
+        if hasattr(self.optimizer, "sync_hyperparameters"):
+            self.optimizer.sync_hyperparameters()  # e.g. FusedAdam: a scheduler's new learning rate -> device scalar
+        misfit = self.graph is not None and (
+            S.col1.numel() > st.cap1 or S.col2.numel() > st.cap2 or (S.B, S.N) != (st.B, st.N)
+            or any(torch.is_tensor(v) and k in self.static_batch and tuple(v.shape) != tuple(self.static_batch[k].shape)
+                   for k, v in batch.items() if k != "sn2_structure"))
+        if misfit and self._collective():
+            # Data-parallel job: a re-capture would run three warm-up executions on THIS rank only and every one of them
+            # contains collectives the other ranks do not expect.  The eager step issues exactly the collectives of one
+            # replay, so this batch runs eagerly (dynamic shapes) and the graph stays as it is.
+            eager = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in batch.items()}
+            eager["sn2_structure"] = S
+            self.loss.copy_(self.step_fn(eager))
+            self.eager_steps += 1
+            invalidate_packed(self.model)
+            return self.loss
+        if self.graph is None or misfit:
             self._capture(batch, S)  # first call, edge capacity exceeded, or a batch of another shape (last of an epoch)
         else:
             st.load(S)

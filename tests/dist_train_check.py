@@ -1,5 +1,16 @@
-"""Run under torchrun on >= 2 GPUs: data-parallel training step (plots sharded, SyncBatchNorm, one flat
-gradient all-reduce) must reproduce the single-GPU full-batch gradients.  Prints DIST_TRAIN_OK."""
+"""Run under torchrun on >= 2 GPUs (tests/test_gpu_parity.py::test_data_parallel_* and the round's gpurun logs):
+
+  1. PeerComm known answers: fp64 / fp32 one-shot all-reduces over NVLink peer memory, 200 back-to-back collectives
+     (slot reuse), rank-order sums bit-identical on every rank.
+  2. Data-parallel training step -- plots sharded by rank, SyncBatchNorm statistics summed inside the finalize
+     kernels, flat gradient summed inside the FusedAdam kernel -- against the CPU ORACLE's full-batch gradients and
+     running statistics (the restated reference, oracle/pointnet2_port.py), not against our own single-GPU path.
+  3. The same step captured in ONE CUDA graph per rank (GraphedTrainStep + StructurePrefetcher) for 5 optimizer steps,
+     one of them with a batch that overflows the edge capacity on purpose (eager fall-back on that rank only), against
+     a single-process eager loop on the full batch; replicas bit-identical across ranks afterwards.
+
+Prints DIST_TRAIN_OK (rank 0).  SN2_COMM=nccl runs 2 and 3 on the NCCL all-reduce path instead."""
+import copy
 import os
 import sys
 
@@ -10,26 +21,58 @@ sys.path.insert(0, os.path.join(ROOT, "stratanet2-vegetation-coverage-maps_b200"
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from bench import train_loss  # noqa: E402
 from model.point_net2 import PointNet2  # noqa: E402
 from model.project_to_2d import project_to_plotwise_coverages  # noqa: E402
-from sn2 import parallel  # noqa: E402
+from sn2 import comm as sn2_comm  # noqa: E402
+from sn2 import losses, parallel  # noqa: E402
 from sn2.config import default_args  # noqa: E402
+from sn2.optim import FusedAdam  # noqa: E402
+from sn2.pipeline import GraphedTrainStep, StructurePrefetcher  # noqa: E402
 from sn2.synth import randomize_bn_, synth_batch  # noqa: E402
 
 
-def grads(net, args, batch, dev, local_plots, global_plots, reduce=True):
-    bucket = parallel.GradBucket(net)
-    bucket.zero()
-    cov, proba = net({"xyz": batch["xyz"], "cloud": batch["cloud"]})
-    pw = project_to_plotwise_coverages(cov, net.last_cloud_device, args)
-    z = batch["xyz"][:, 2, :].reshape(-1, 1).double().to(dev)
-    pdf = torch.cat([torch.exp(-z), 0.5 * torch.exp(-0.5 * (z - 1.0) ** 2), 0.1 + 0.05 * z], dim=1)
-    loss = train_loss(proba, pw, batch["gt"].to(dev), pdf)
+def pdf_of(xyz):
+    z = xyz[:, 2, :].reshape(-1, 1).double()
+    return torch.cat([torch.exp(-z), 0.5 * torch.exp(-0.5 * (z - 1.0) ** 2), 0.1 + 0.05 * z], dim=1)
+
+
+def make_batch(seed, B, N, scale=1.0):
+    b = synth_batch(seed, B, N)
+    b["xyz"] = b["xyz"] * scale
+    b["gt"] = torch.rand(B, 4, generator=torch.Generator().manual_seed(seed))
+    return b
+
+
+def check_peer_comm(comm, rank, world, dev):
+    ok = True
+    for it in range(200):
+        n = 1 + (it * 37) % 129
+        a = (torch.arange(n, dtype=torch.float64, device=dev) + 1.0) * (rank + 1) * (1.0 + it)
+        comm.all_reduce_(a)
+        want = (torch.arange(n, dtype=torch.float64, device=dev) + 1.0) * (world * (world + 1) / 2) * (1.0 + it)
+        ok = ok and bool(torch.equal(a, want))
+    f = torch.full((14997,), float(rank + 1), dtype=torch.float32, device=dev)
+    comm.all_reduce_(f, scale=0.5)
+    ok = ok and bool(torch.equal(f, torch.full_like(f, 0.5 * world * (world + 1) / 2)))
+    seq, err = comm.status()
+    return ok and err == 0 and seq == 201
+
+
+def oracle_step(sd0, full, N):
+    """Full-batch gradients + running statistics of the restated reference on the CPU (rank 0 only)."""
+    from oracle.pointnet2_port import PointNet2Port, project_to_plotwise_coverages_port
+
+    args_cpu = default_args(subsample_size=N)
+    port = PointNet2Port(args_cpu)
+    port.load_state_dict({k: v.cpu() for k, v in sd0.items()})
+    port.train()
+    cov, proba = port({"xyz": full["xyz"], "cloud": full["cloud"]})
+    pw = project_to_plotwise_coverages_port(cov, full["cloud"], args_cpu)
+    loss = losses.training_loss(pw, full["gt"], proba, pdf_of(full["xyz"]), fused=False)[0]
     loss.backward()
-    if reduce:
-        bucket.allreduce(local_plots, global_plots)
-    return bucket.flat.clone(), {k: v.clone() for k, v in net.state_dict().items() if "running" in k}
+    flat = torch.cat([p.grad.reshape(-1) for p in port.parameters()])
+    stats = {k: v.clone() for k, v in port.state_dict().items() if "running" in k}
+    return flat, stats, float(loss)
 
 
 def main():
@@ -37,35 +80,119 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    B, N = 4, 2048
-    args = default_args(subsample_size=N, cuda=local)
-    full = synth_batch(5, B, N)
-    full["gt"] = torch.rand(B, 4, generator=torch.Generator().manual_seed(2))
+    comm = sn2_comm.get_comm()
+    mode = "peer" if comm is not None else "nccl"
+    results = {}
+    if comm is not None:
+        results["peer_comm_known_answers"] = check_peer_comm(comm, rank, world, dev)
 
+    B, N = max(4, world), 2048
+    args = default_args(subsample_size=N, cuda=local)
+    full = make_batch(5, B, N)
     torch.manual_seed(0)
     ref = PointNet2(args)
     randomize_bn_(ref)
     ref.train()
     sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
-    want, want_stats = grads(ref, args, full, dev, B, B, reduce=False)  # every rank computes the full-batch reference itself
 
+    # ---- 2. one data-parallel step against the oracle -------------------------------------------------------
     net = PointNet2(args)
     net.load_state_dict(sd0)
     net.train()
     net = parallel.convert_sync_batchnorm(net)
+    opt = FusedAdam(net.parameters(), lr=0.0, comm=comm)  # lr = 0: the step only performs the gradient all-reduce
     mine = parallel.shard_plots(full, rank, world)
-    got, got_stats = grads(net, args, mine, dev, mine["cloud"].shape[0], B)
-
+    Bl = mine["cloud"].shape[0]
+    opt.zero_grad()
+    cov, proba = net({"xyz": mine["xyz"], "cloud": mine["cloud"]})
+    pw = project_to_plotwise_coverages(cov, net.last_cloud_device, args)
+    loss = losses.training_loss(pw, mine["gt"].to(dev), proba, pdf_of(mine["xyz"]).to(dev))[0]
+    loss.backward()
+    opt.step(grad_scale=Bl / B)
+    got = opt.flat_grad.clone()
+    got_stats = {k: v.clone() for k, v in net.state_dict().items() if "running" in k}
+    want = torch.empty_like(got)
+    if rank == 0:
+        w, want_stats, loss_o = oracle_step(sd0, full, N)
+        want.copy_(w)
+    dist.broadcast(want, 0)
     scale = want.abs().max().item()
     err = (got - want).abs().max().item()
-    ok = err <= 2e-3 * scale
-    for k in want_stats:
-        ok = ok and torch.allclose(got_stats[k], want_stats[k], rtol=1e-3, atol=1e-5)
+    results["grads_vs_oracle"] = err <= 2e-3 * scale
+    if rank == 0:
+        results["running_stats_vs_oracle"] = all(torch.allclose(got_stats[k].cpu(), want_stats[k], rtol=1e-3, atol=2e-5) for k in want_stats)
+
+    # ---- 3. graphed data-parallel loop vs a single-process eager loop on the full batch ------------------------
+    batches = [make_batch(20 + i, B, N, scale=(0.8 if i == 3 else 1.0)) for i in range(5)]  # batch 3: denser -> more edges
+    solo = PointNet2(args)
+    solo.load_state_dict(sd0)
+    solo.train()
+    solo_opt = FusedAdam(solo.parameters(), lr=1e-3, weight_decay=1e-3)
+    solo_opt.nccl_group = False
+    solo_losses = []
+    for b in batches:
+        solo_opt.zero_grad()
+        cov, proba = solo({"xyz": b["xyz"], "cloud": b["cloud"]})
+        pw = project_to_plotwise_coverages(cov, solo.last_cloud_device, args)
+        l_ = losses.training_loss(pw, b["gt"].to(dev), proba, pdf_of(b["xyz"]).to(dev))[0]
+        l_.backward()
+        solo_opt.step()
+        solo_losses.append(float(l_))
+
+    dp = PointNet2(args)
+    dp.load_state_dict(sd0)
+    dp.train()
+    dp = parallel.convert_sync_batchnorm(dp)
+    dp_opt = FusedAdam(dp.parameters(), lr=1e-3, weight_decay=1e-3, comm=comm)
+
+    def step_fn(batch):
+        dp_opt.zero_grad()
+        cov, proba = dp(batch)
+        pw = project_to_plotwise_coverages(cov, dp.last_cloud_device, args)
+        l_ = losses.training_loss(pw, batch["gt"], proba, batch["pdf"])[0]
+        l_.backward()
+        dp_opt.step(grad_scale=Bl / B)
+        return l_.detach()
+
+    gstep = GraphedTrainStep(dp, step_fn, dp_opt, capacity_factor=1.02)
+    shards = []
+    for b in batches:
+        s = parallel.shard_plots(b, rank, world)
+        s["pdf"] = pdf_of(s["xyz"])
+        shards.append(s)
+    dp_losses = []
+    for batch in StructurePrefetcher(dp, shards):
+        l_ = gstep(batch).clone()
+        # the loss of the global batch is the plot-weighted mean of the ranks' losses (equal point counts per plot)
+        l_ = l_ * (Bl / B)
+        dist.all_reduce(l_)
+        dp_losses.append(float(l_))
+    results["graph_captured_once"] = gstep.captures == 1
+    results["losses_vs_single_process"] = bool(torch.allclose(torch.tensor(dp_losses), torch.tensor(solo_losses), rtol=2e-3, atol=1e-6))
+    bad = 0.0
+    for (k, v), (_, v2) in zip(solo.state_dict().items(), dp.state_dict().items()):
+        if v.is_floating_point():
+            diff = (v2 - v).abs()
+            bad = max(bad, float((diff > 5e-4 + 2e-3 * v.abs()).float().mean()))
+    results["params_vs_single_process"] = bad < 5e-3
+    flat = dp_opt.flat_param.clone()
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    results["replicas_bit_identical"] = all(bool(torch.equal(g, gathered[0])) for g in gathered)
+    if comm is not None:
+        results["comm_healthy"] = comm.status()[1] == 0
+
+    ok = all(results.values())
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    for r in range(world):
+        if r == rank and (rank == 0 or not ok):
+            print(f"[rank {rank}] mode={mode} world={world} grad err {err:.3e} (scale {scale:.3e}) eager_steps={gstep.eager_steps} "
+                  f"losses dp {[round(x, 5) for x in dp_losses]} solo {[round(x, 5) for x in solo_losses]} {results}", flush=True)
+        dist.barrier()
     if rank == 0:
-        print(f"world={world} max grad err {err:.3e} (scale {scale:.3e})")
-        print("DIST_TRAIN_OK" if flag.item() == 1.0 else "DIST_TRAIN_FAIL")
+        print("DIST_TRAIN_OK" if flag.item() == 1.0 else "DIST_TRAIN_FAIL", flush=True)
+    sn2_comm.close_all()
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1.0 else 1)
 

@@ -548,20 +548,23 @@ def test_training_ops_known_answers(cuda_device):
     assert torch.allclose(x.grad.view(-1), torch.tensor([1 / 3, 1 / 3, 1 / 3, 0.], device=cuda_device))
 
 
-def test_data_parallel_training_matches_single_gpu(cuda_device):
-    """2-rank NCCL run (skipped on a 1-GPU box): sharded plots + SyncBatchNorm + one flat gradient all-reduce
-    reproduce the single-GPU full-batch gradients and running statistics."""
+@pytest.mark.parametrize("world,backend", [(2, "peer"), (2, "nccl"), (4, "peer"), (8, "peer")])
+def test_data_parallel_training_matches_oracle(cuda_device, world, backend):
+    """Multi-rank run of tests/dist_train_check.py (skipped when the box has fewer GPUs): peer-memory all-reduce known
+    answers, data-parallel gradients / running statistics against the CPU oracle, the CUDA-graphed data-parallel loop
+    against a single-process loop, replicas bit-identical."""
     import os
     import subprocess
     import sys
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs >= {world} GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29731", os.path.join(root, "tests", "dist_train_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert "DIST_TRAIN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29731 + world), os.path.join(root, "tests", "dist_train_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env={**os.environ, "SN2_COMM": backend})
+    assert "DIST_TRAIN_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    assert f"mode={backend}" in r.stdout, r.stdout[-2000:]
 
 
 def test_submodule_forward_matches_reference_modules(cuda_device):
@@ -690,7 +693,7 @@ def test_tall_linear_weight_gradient(cuda_device, Co, Ci):
 
 
 @pytest.mark.parametrize("Ci,Co,R", [(11, 16, 300001), (16, 16, 131072), (19, 32, 99999), (80, 34, 70001), (42, 34, 65537),
-                                     (16, 16, 37), (42, 34, 129)])
+                                     (16, 16, 37), (42, 34, 129), (35, 64, 20000), (96, 64, 20001), (35, 64, 19), (96, 64, 2500)])
 def test_fused_lin_relu_bn_block(cuda_device, Ci, Co, R):
     """LinReluBN (csrc/train_mlp.cu) against the torch modules of one reference MLP() block in float64:
     output, all five gradients, running statistics and num_batches_tracked."""
@@ -725,6 +728,171 @@ def test_fused_lin_relu_bn_block(cuda_device, Ci, Co, R):
     torch.testing.assert_close(bn.running_mean.double(), ref[2].running_mean, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(bn.running_var.double(), ref[2].running_var, rtol=1e-5, atol=1e-6)
     assert int(bn.num_batches_tracked) == int(ref[2].num_batches_tracked) == 1
+
+
+def test_fused_head_matches_torch(cuda_device):
+    """sn2_head_fwd / sn2_head_bwd (lin1 + ReLU + lin2 + softmax x sigmoid, reference model/point_net2.py:141-153)
+    against the same ops in torch float64: outputs, the row gradient and the four parameter gradients, with and without
+    the producing block's BatchNorm transform applied on load."""
+    from sn2.autograd_ops import Head
+
+    g = torch.Generator().manual_seed(11)
+    for R, use_ss in ((70001, False), (129, True), (40000, True)):
+        f1 = torch.randn(R, 34, generator=g).to(cuda_device)
+        lin1, lin2 = torch.nn.Linear(34, 16).to(cuda_device), torch.nn.Linear(16, 5).to(cuda_device)
+        ss = torch.cat([torch.randn(34, generator=g) * 0.5 + 1.0, torch.randn(34, generator=g) * 0.2, torch.zeros(68)]).to(cuda_device) if use_ss else None
+        dcov, dproba = torch.randn(R, 4, generator=g).to(cuda_device), torch.randn(R, 4, generator=g).to(cuda_device)
+        x1 = f1.clone().requires_grad_(True)
+        cov, proba = Head.apply(x1, lin1.weight, lin1.bias, lin2.weight, lin2.bias, ss)
+        torch.autograd.backward([cov, proba], [dcov, dproba])
+        got = [x1.grad] + [p.grad.clone() for p in (lin1.weight, lin1.bias, lin2.weight, lin2.bias)]
+        for p in (lin1.weight, lin1.bias, lin2.weight, lin2.bias):
+            p.grad = None
+        # float64 reference
+        x2 = f1.double().requires_grad_(True)
+        W1, b1, W2, b2 = (p.detach().double().requires_grad_(True) for p in (lin1.weight, lin1.bias, lin2.weight, lin2.bias))
+        z = x2 * ss[:34].double() + ss[34:68].double() if use_ss else x2
+        sc = torch.relu(z @ W1.t() + b1) @ W2.t() + b2
+        proba_r = torch.softmax(sc[:, :4], dim=1)
+        cov_r = proba_r * torch.sigmoid(sc[:, 4:5])
+        if use_ss:  # Head returns the gradient with respect to the transformed row z
+            zz = z.detach().requires_grad_(True)
+            sc2 = torch.relu(zz @ W1.t() + b1) @ W2.t() + b2
+            p2 = torch.softmax(sc2[:, :4], dim=1)
+            torch.autograd.backward([p2 * torch.sigmoid(sc2[:, 4:5]), p2], [dcov.double(), dproba.double()])
+            want_dx = zz.grad
+        else:
+            torch.autograd.backward([cov_r, proba_r], [dcov.double(), dproba.double()])
+            want_dx = x2.grad
+        want = [want_dx, W1.grad, b1.grad, W2.grad, b2.grad]
+        torch.testing.assert_close(cov.detach().double(), cov_r.detach(), rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(proba.detach().double(), proba_r.detach(), rtol=1e-4, atol=1e-6)
+        scale = float(R) ** 0.5
+        for name, a, b in zip(("df1", "dW1", "db1", "dW2", "db2"), got, want):
+            torch.testing.assert_close(a.double(), b, rtol=1e-3, atol=(1e-5 if name == "df1" else 1e-4 * scale), msg=lambda m, n=name: f"{n} (R={R}): {m}")
+
+
+def test_pointwise_losses_and_kde_lut(cuda_device):
+    """sn2.losses: the KDE look-up against scipy's interp1d (what learning/kde_mixture.py:64-75 calls), the fused
+    NLL + entropy pass and its backward against the reference formulas in torch (learning/loss_functions.py:19-57;
+    the reference's own file is imported when /root/reference or oracle/_ref is reachable)."""
+    from scipy.interpolate import interp1d
+
+    from sn2 import losses
+    from sn2.config import default_args
+
+    args = default_args(cuda=cuda_device.index)
+    B, N = 3, 5000
+    data = _plots(7, B, N)
+    cloud_d = data["cloud"].to(cuda_device)
+    X = np.sort(np.concatenate([np.linspace(-26.0, 26.0, 4999), [0.0]]))  # a knot exactly at z = 0 (the fake ground points)
+    X = np.unique(X)
+    a = np.abs(X)
+    Y = np.stack([np.exp(-a), 0.5 * np.exp(-0.5 * (a - 1.0) ** 2), 0.1 + 0.05 * a])
+    lut = losses.KdeLut(X, Y, cuda_device)
+    pdf = lut.pdf(cloud_d, args.z_max)
+    z = (data["cloud"][:, 2, :] * args.z_max).reshape(-1).numpy().astype(np.float64)       # learning/loss_functions.py:31-36
+    want = np.stack([interp1d(X, Y[c], kind="linear", assume_sorted=False)(z) for c in range(3)], axis=1)
+    np.testing.assert_allclose(pdf.cpu().numpy(), want, rtol=1e-12, atol=1e-15)
+
+    g = torch.Generator().manual_seed(4)
+    proba = torch.softmax(torch.randn(B * N, 4, generator=g) * 2, dim=1).to(cuda_device)
+    p1 = proba.clone().requires_grad_(True)
+    out = losses.pointwise_losses(p1, pdf)
+    (0.1 * out[0] + 0.04 * out[1]).backward()
+    p2 = proba.clone().requires_grad_(True)
+    nll = losses.get_NLL_loss(p2, pdf)[0]
+    ent = losses.get_entropy_loss(p2)
+    (0.1 * nll + 0.04 * ent).backward()
+    torch.testing.assert_close(out[0], nll, rtol=1e-10, atol=0)
+    torch.testing.assert_close(out[1].float(), ent, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(p1.grad, p2.grad, rtol=1e-4, atol=1e-10)
+    gt = torch.rand(B, 4, generator=g).to(cuda_device)
+    pw = torch.rand(B, 4, generator=g).to(cuda_device)
+    total, l_abs, l_log, l_e = losses.training_loss(pw, gt, proba, pdf)
+    total_t = losses.training_loss(pw, gt, proba, pdf, fused=False)[0]
+    torch.testing.assert_close(total, total_t, rtol=1e-7, atol=0)
+    assert total.dtype == torch.float64                                                       # as the reference's sum
+    # the reference's own loss file, when reachable (it needs scipy only)
+    import importlib.util
+    import os
+    for root in ("/root/reference", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")):
+        path = os.path.join(root, "learning", "loss_functions.py")
+        if os.path.exists(path):
+            spec = importlib.util.spec_from_file_location("ref_loss_functions", path)
+            ref = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(ref)
+            torch.testing.assert_close(l_abs.cpu(), ref.get_absolute_loss(pw.cpu(), gt.cpu()), rtol=1e-6, atol=0)
+            torch.testing.assert_close(l_e.float().cpu(), ref.get_entropy_loss(proba.cpu()), rtol=1e-5, atol=1e-7)
+
+            class _K:  # KdeMixture.predict stand-in: the same interp1d objects
+                f = [interp1d(X, Y[c], kind="linear", assume_sorted=False) for c in range(3)]
+
+                def predict(self, zz):
+                    return tuple(fc(zz) for fc in self.f)
+            rargs = default_args()
+            rargs.kde_mixture = _K()
+            torch.testing.assert_close(l_log.cpu(), ref.get_NLL_loss(proba.cpu(), data["cloud"], rargs)[0], rtol=1e-9, atol=0)
+            break
+
+
+def test_fused_adam_matches_torch_adam(cuda_device):
+    """sn2.optim.FusedAdam (one kernel over flat buckets, lr / step on the device) against torch.optim.Adam with the
+    reference's settings and StepLR schedule (learning/train.py:180-185) over 12 steps of random gradients."""
+    import copy
+
+    from sn2.optim import FusedAdam
+
+    args, net, _ = _make_models(512, cuda_device)
+    twin = copy.deepcopy(net)
+    opt_t = torch.optim.Adam(twin.parameters(), lr=1e-3, weight_decay=1e-3)
+    opt_f = FusedAdam(net.parameters(), lr=1e-3, weight_decay=1e-3)
+    sch_t = torch.optim.lr_scheduler.StepLR(opt_t, step_size=1, gamma=0.985)
+    sch_f = torch.optim.lr_scheduler.StepLR(opt_f, step_size=1, gamma=0.985)
+    assert sum(p.numel() for p in net.parameters()) == 14997 == opt_f.flat_param.numel()
+    g = torch.Generator().manual_seed(0)
+    for it in range(12):
+        opt_f.zero_grad()
+        for p, q in zip(net.parameters(), twin.parameters()):
+            gr = (torch.randn(p.shape, generator=g) * (10.0 ** (it % 3 - 2))).to(cuda_device)
+            p.grad.add_(gr)       # accumulates into the bucket view, as autograd does
+            q.grad = gr.clone()
+        opt_f.step()
+        opt_t.step()
+        if it % 4 == 3:
+            sch_f.step()
+            sch_t.step()
+    assert int(opt_f.step_dev) == 12
+    for (k, p), (_, q) in zip(net.named_parameters(), twin.named_parameters()):
+        torch.testing.assert_close(p, q, rtol=1e-5, atol=2e-7, msg=lambda m, n=k: f"{n}: {m}")
+    # the model still works after its parameters became views of the flat bucket (state_dict round trip included)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net.load_state_dict(sd)
+    assert net.lin1.weight.data_ptr() >= opt_f.flat_param.data_ptr()
+
+
+def test_segment_max_nan_and_minus_inf_rows(cuda_device):
+    """a row whose values are all -inf / NaN must yield a valid arg (first edge / first NaN), so that the
+    backward never writes out of bounds; NaN propagates like torch.max."""
+    from sn2.autograd_ops import SegmentMax
+
+    C = 16
+    vals = torch.randn(40, C, device=cuda_device)
+    vals[0:5] = float("-inf")            # row 0: all -inf
+    vals[5:9, 3] = float("nan")          # row 1: channel 3 all NaN
+    vals[12, 7] = float("nan")           # row 2: one NaN among finite values
+    rowptr = torch.tensor([0, 5, 9, 20, 40], dtype=torch.int32, device=cuda_device)
+    v = vals.clone().requires_grad_(True)
+    out, arg = SegmentMax.apply(v, rowptr)
+    assert (arg >= 0).all() and (arg < 40).all()
+    assert (arg[0] == 0).all() and torch.isinf(out[0]).all()
+    assert int(arg[1, 3]) == 5 and torch.isnan(out[1, 3])
+    assert int(arg[2, 7]) == 12 and torch.isnan(out[2, 7])
+    want = torch.stack([vals[0:5].max(0).values, vals[5:9].max(0).values, vals[9:20].max(0).values, vals[20:40].max(0).values])
+    assert torch.equal(torch.nan_to_num(out, nan=123.0, neginf=-1e30), torch.nan_to_num(want, nan=123.0, neginf=-1e30))
+    out.nan_to_num(0.0, 0.0, 0.0).sum().backward()   # must not fault
+    torch.cuda.synchronize()
+    assert v.grad.shape == vals.shape
 
 
 def test_deferred_batchnorm_matches_materialised(cuda_device, monkeypatch):

@@ -177,8 +177,13 @@ def test_run_mlp_dispatch_rules(monkeypatch):
     assert [c["apply"] for c in calls] == [True, True] and ss is None
     monkeypatch.delenv("SN2_DEFER_BN")
     calls.clear()
-    ao.run_mlp(mlp, torch.zeros(1000, 11))               # few rows: the model's own torch modules
+    ao.run_mlp(mlp, torch.zeros(1000, 11))               # round 2: every block is fused whatever its row count ...
+    assert len(calls) == 2
+    calls.clear()
+    monkeypatch.setenv("SN2_FUSED_MLP_MIN_ROWS", "65536")  # ... unless a floor is asked for (the model's own torch modules)
+    ao.run_mlp(mlp, torch.zeros(1000, 11))
     assert calls == []
+    monkeypatch.delenv("SN2_FUSED_MLP_MIN_ROWS")
     ao.run_mlp(mlp.eval(), x)                            # eval-mode BatchNorm is never fused
     assert calls == []
     mlp.train()
