@@ -31,6 +31,12 @@ from sn2.pipeline import GraphedTrainStep, StructurePrefetcher  # noqa: E402
 from sn2.synth import randomize_bn_, synth_batch  # noqa: E402
 
 
+# Per-tensor max-norm bound against the CPU oracle evaluated in FLOAT64.  Measured (tools/diag_train_oracle.py, this batch): the
+# CUDA path is within 7e-6 of the float64 oracle on all 32 tensors, while the float32 CPU oracle itself is 1e-3 .. 8e-2 away
+# from it depending on the host thread count (fp32 summation order in its GEMMs / BatchNorm) -- so float64 is the arbiter.
+GRAD_TOL = 2e-4
+
+
 def pdf_of(xyz):
     z = xyz[:, 2, :].reshape(-1, 1).double()
     return torch.cat([torch.exp(-z), 0.5 * torch.exp(-0.5 * (z - 1.0) ** 2), 0.1 + 0.05 * z], dim=1)
@@ -65,14 +71,15 @@ def oracle_step(sd0, full, N):
     args_cpu = default_args(subsample_size=N)
     port = PointNet2Port(args_cpu)
     port.load_state_dict({k: v.cpu() for k, v in sd0.items()})
+    port = port.double()  # the restated index ops (fps / radius / knn) convert positions to fp32 internally: same indices
     port.train()
-    cov, proba = port({"xyz": full["xyz"], "cloud": full["cloud"]})
+    cov, proba = port({"xyz": full["xyz"].double(), "cloud": full["cloud"].double()})
     pw = project_to_plotwise_coverages_port(cov, full["cloud"], args_cpu)
-    loss = losses.training_loss(pw, full["gt"], proba, pdf_of(full["xyz"]), fused=False)[0]
+    loss = losses.training_loss(pw, full["gt"].double(), proba, pdf_of(full["xyz"]), fused=False)[0]
     loss.backward()
-    flat = torch.cat([p.grad.reshape(-1) for p in port.parameters()])
-    stats = {k: v.clone() for k, v in port.state_dict().items() if "running" in k}
-    return flat, stats, float(loss)
+    flat = torch.cat([p.grad.reshape(-1) for p in port.parameters()]).float()
+    stats = {k: v.clone().float() for k, v in port.state_dict().items() if "running" in k}
+    return flat, stats, float(loss.detach())
 
 
 def main():
@@ -118,7 +125,38 @@ def main():
     dist.broadcast(want, 0)
     scale = want.abs().max().item()
     err = (got - want).abs().max().item()
-    results["grads_vs_oracle"] = err <= 2e-3 * scale
+    # per tensor, relative to the tensor's own largest entry (as tests/test_gpu_parity.py::test_training_step_gradients_match_oracle)
+    worst, off = (0.0, ""), 0
+    for name, p in net.named_parameters():
+        k = p.numel()
+        sc = want[off:off + k].abs().max().item() + 1e-12
+        e = (got[off:off + k] - want[off:off + k]).abs().max().item() / sc
+        if os.environ.get("SN2_DIST_VERBOSE") == "1" and rank == 0:
+            print(f"  grad {name:45s} scale {sc:.3e} rel err {e:.2e}", flush=True)
+        worst = max(worst, (e, name))
+        off += k
+    results["grads_vs_oracle"] = worst[0] <= GRAD_TOL
+    # the same batch on ONE GPU (plain BatchNorm over the full batch), every rank for itself
+    one = PointNet2(args)
+    one.load_state_dict(sd0)
+    one.train()
+    one_opt = FusedAdam(one.parameters(), lr=0.0)
+    one_opt.nccl_group = False
+    one_opt.zero_grad()
+    cov1, proba1 = one({"xyz": full["xyz"], "cloud": full["cloud"]})
+    pw1 = project_to_plotwise_coverages(cov1, one.last_cloud_device, args)
+    losses.training_loss(pw1, full["gt"].to(dev), proba1, pdf_of(full["xyz"]).to(dev))[0].backward()
+    solo_g = one_opt.flat_grad
+    worst1, off = (0.0, ""), 0
+    for name, p in net.named_parameters():
+        k = p.numel()
+        sc = solo_g[off:off + k].abs().max().item() + 1e-12
+        e = (got[off:off + k] - solo_g[off:off + k]).abs().max().item() / sc
+        if os.environ.get("SN2_DIST_VERBOSE") == "1" and rank == 0:
+            print(f"  vs one GPU {name:45s} scale {sc:.3e} rel err {e:.2e}", flush=True)
+        worst1 = max(worst1, (e, name))
+        off += k
+    results["grads_vs_one_gpu"] = worst1[0] <= 2e-3
     if rank == 0:
         results["running_stats_vs_oracle"] = all(torch.allclose(got_stats[k].cpu(), want_stats[k], rtol=1e-3, atol=2e-5) for k in want_stats)
 
@@ -187,7 +225,7 @@ def main():
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     for r in range(world):
         if r == rank and (rank == 0 or not ok):
-            print(f"[rank {rank}] mode={mode} world={world} grad err {err:.3e} (scale {scale:.3e}) eager_steps={gstep.eager_steps} "
+            print(f"[rank {rank}] mode={mode} world={world} grad err {err:.3e} (scale {scale:.3e}) worst tensor {worst[1]} {worst[0]:.2e} eager_steps={gstep.eager_steps} "
                   f"losses dp {[round(x, 5) for x in dp_losses]} solo {[round(x, 5) for x in solo_losses]} {results}", flush=True)
         dist.barrier()
     if rank == 0:

@@ -472,54 +472,58 @@ def _train_loss(cov, proba, pw, gt, pdf):
     return mae + 0.10 * nll + 0.04 * ent
 
 
-@pytest.mark.parametrize("B,N,variant,gtol", [(2, 2048, "plain", 2e-3), (3, 1500, "cm", 2e-3), (8, 10000, "plain", 8e-2)])
+@pytest.mark.parametrize("B,N,variant,gtol", [(2, 2048, "plain", 1e-4), (3, 1500, "cm", 1e-4), (4, 2048, "plain", 1e-4), (8, 10000, "plain", 5e-4)])
 def test_training_step_gradients_match_oracle(cuda_device, B, N, variant, gtol):
-    """Config-3-style step: train-mode forward (BatchNorm batch stats), plot-wise projection, reference loss,
-    backward.  All 32 parameter gradients, the running statistics and the loss match the CPU oracle.
+    """Config-3-style step: train-mode forward (BatchNorm batch stats), plot-wise projection, the reference loss
+    (sn2.losses.training_loss = learning/train.py:58-62), backward.  All 32 parameter gradients, the running statistics
+    and the loss against the CPU oracle evaluated in FLOAT64.
 
-    Gradient tolerance (max-norm, relative to the largest entry of each tensor): 2e-3 on small batches.  At
-    8 x 10 000 points the gradient of this network is itself only defined to a few percent in fp32: the CPU
-    oracle evaluated in float64 vs float32 differs by 1-4 % per tensor (arg-max routing of the max aggregations
-    and of the projection flips between near-equal candidates; measured with the oracle alone),
-    and the CUDA path lands inside the same band (0.2-6 %).  Loss and running statistics stay at rtol 1e-3."""
+    Why float64: measured with tools/diag_train_oracle.py, the CUDA path (fp32 arithmetic, fp64 BatchNorm statistics)
+    is within 1e-5 of the float64 oracle on every tensor, whereas the float32 CPU oracle is itself 1e-3 .. 8e-2 away
+    from the float64 one and changes with the host thread count (fp32 summation order in its GEMMs and BatchNorm).
+    Round 1 compared against the fp32 oracle and needed 8e-2 at 8 x 10 000 points; that was the oracle's noise, not the
+    kernels'.  Index decisions are unaffected: the restated fps / radius / knn convert positions to fp32 internally."""
     from model.project_to_2d import project_to_plotwise_coverages
     from oracle.pointnet2_port import project_to_plotwise_coverages_port
+    from sn2 import losses
 
     args, net, port = _make_models(N, cuda_device)
-    from sn2.synth import randomize_bn_
-    net.train(); port.train()
+    net.train()
+    port = port.double()
+    port.train()
     data = _plots(3, B, N, variant)
     g = torch.Generator().manual_seed(9)
     gt = torch.rand(B, 4, generator=g)
     z = data["xyz"][:, 2, :].reshape(-1, 1).double()
     pdf = torch.cat([torch.exp(-z), 0.5 * torch.exp(-0.5 * (z - 1.0) ** 2), 0.1 + 0.05 * z], dim=1)
 
-    cov_o, proba_o = port(data)
-    loss_o = _train_loss(cov_o, proba_o, project_to_plotwise_coverages_port(cov_o, data["cloud"], default_args_cpu(N)), gt, pdf)
+    cov_o, proba_o = port({"xyz": data["xyz"].double(), "cloud": data["cloud"].double()})
+    pw_o = project_to_plotwise_coverages_port(cov_o, data["cloud"], default_args_cpu(N))
+    loss_o = losses.training_loss(pw_o, gt.double(), proba_o, pdf, fused=False)[0]
     loss_o.backward()
 
     cov, proba = net(data)
     pw = project_to_plotwise_coverages(cov, data["cloud"], args)
-    loss = _train_loss(cov, proba, pw, gt.to(cuda_device), pdf.to(cuda_device))
+    loss = losses.training_loss(pw, gt.to(cuda_device), proba, pdf.to(cuda_device))[0]
     loss.backward()
 
-    torch.testing.assert_close(loss.detach().cpu(), loss_o.detach(), rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(loss.detach().cpu(), loss_o.detach(), rtol=1e-5, atol=1e-6)
     go = dict(port.named_parameters())
     checked, bad = 0, []
     for name, p in net.named_parameters():
         want = go[name].grad
         assert p.grad is not None, name
         scale = want.abs().max().item() + 1e-12
-        err = (p.grad.cpu() - want).abs().max().item()
+        err = (p.grad.cpu().double() - want).abs().max().item()
         print(f"grad {name}: max err {err:.3e} scale {scale:.3e} rel {err / scale:.2e}")
-        if err > gtol * scale + 1e-7:
+        if err > gtol * scale + 1e-9:
             bad.append(f"{name}: max err {err:.3e} vs scale {scale:.3e}")
         checked += 1
     assert checked == 32
     assert not bad, bad
     for (n1, b1), (n2, b2) in zip(net.named_buffers(), port.named_buffers()):
         assert n1 == n2
-        torch.testing.assert_close(b1.cpu(), b2, rtol=RTOL, atol=2e-5, msg=n1)  # running stats, fp32 means over ~1e6 rows
+        torch.testing.assert_close(b1.cpu().double(), b2.double(), rtol=1e-4, atol=2e-6, msg=n1)  # running statistics
 
 
 def default_args_cpu(N):
