@@ -320,10 +320,19 @@ int sn2_fuse_accumulate(const double *rasters, const int *offsets, int P, int D,
 int sn2_fuse_finalize(const double *num, const double *den, const double *wsum, int H, int W, double *out,
                       void *stream);
 
+/* ---- device-side loader transforms, csrc/loader.cu -------------------------------------------
+ * augment (data_loader/loader.py:161-214) + rescale_cloud (:135-158) of a batch: in [B,10,N] fp32 = centred raw plots (metres,
+ * raw feature units, fake ground points included).  angle [B] float64 radians + flip [B,2] uint8 (nullable together: no
+ * rotation / flips), noise [B,6,N] float64 standard-normal draws for x, y, R, G, B, NIR (nullable: no noise).
+ * Out: xyz [B,3,N] (rotated / flipped positions, metres) and cloud [B,10,N] (augmented, rescaled): the model input. */
+int sn2_augment_rescale(const float *in, int B, int N, const double *angle, const unsigned char *flip, const double *noise,
+                        float z_max, float *xyz, float *cloud, void *stream);
+
 /* ================= parcel tiling / plot preparation / band finalisation, csrc/parcel.cu ====
  * sn2_parcel_grid_build  uniform xy grid (cell side `cell`, nx*ny cells from (x0,y0)) over a parcel cloud of P points:
- *                        cell_start [nx*ny+1], sorted_idx [P] (point indices grouped by cell); cell_of [P], count and
- *                        cursor [nx*ny] are scratch.  Stands where prepare.py:75-76 builds a KDTree over the parcel.
+ *                        cell_start [nx*ny+1], sorted4 [P] float4 = (x, y, z, index bits) grouped by cell (16-byte aligned),
+ *                        pos_of [P] = position of every point in sorted4; cell_of [P], count and cursor [nx*ny] are scratch.
+ *                        Stands where prepare.py:75-76 builds a KDTree over the parcel.  cell >= 1.05 * znorm_radius.
  * sn2_extract_plots      one CTA per plot centre (centers [C,2] float64): points with float64 d2 <= radius^2 in ascending
  *                        index (inference/prepare_utils.py:47-53), plots with <= min_points points skipped (:67-69,
  *                        prepare.py:91-94), z - min z within znorm_radius (utils/load_data.py:237-249), centred, the fake
@@ -335,11 +344,11 @@ int sn2_fuse_finalize(const double *num, const double *den, const double *wsum, 
  * sn2_finalize_mosaic    fused [4,H,W] float64 (Vb, Vm, Vh, weights; NaN = none) -> out [5,H,W] = (Vb, Vm_soft, Vh, Vm_hard,
  *                        weights) per inference/geotiff_raster.py:121-146, 273-291 (without the admissibility band);
  *                        hist [10002] uint32 and scratch [4] float64 are workspace; scratch[2] = threshold, [3] = target. */
-int sn2_parcel_grid_build(const float *x, const float *y, long long P, float x0, float y0, float cell, int nx, int ny,
-                          int *cell_of, int *count, int *cell_start, int *cursor, int *sorted_idx, void *stream);
+int sn2_parcel_grid_build(const float *x, const float *y, const float *z, long long P, float x0, float y0, float cell, int nx, int ny,
+                          int *cell_of, int *count, int *cell_start, int *cursor, float *sorted4, int *pos_of, void *stream);
 int sn2_plot_capacity(void);
 int sn2_extract_plots(const float *xyz, const float *feat, long long P, float x0, float y0, float cell, int nx, int ny,
-                      const int *cell_start, const int *sorted_idx, const double *centers, const unsigned *seeds, int C, int S,
+                      const int *cell_start, const float *sorted4, const int *pos_of, const double *centers, const unsigned *seeds, int C, int S,
                       float radius, float znorm_radius, float z_max, int diam_meters, int min_points, float *out_xyz,
                       float *out_cloud, int *out_n, int *out_src, void *stream);
 unsigned sn2_sample_hash(unsigned seed, unsigned j);

@@ -91,19 +91,48 @@ pgrid_scan_kernel(const int *__restrict__ count, int n, int *__restrict__ start,
     if (tid == 0) start[n] = carry;
 }
 
+// cell-grouped copy of the cloud: sorted4[k] = (x, y, z, parcel index as int bits); pos_of[parcel index] = k
 __global__ void __launch_bounds__(256)
-pgrid_scatter_kernel(const int *__restrict__ cell_of, long long P, int *__restrict__ cursor, int *__restrict__ sorted_idx)
+pgrid_scatter_kernel(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
+                     const int *__restrict__ cell_of, long long P, int *__restrict__ cursor, float4 *__restrict__ sorted4,
+                     int *__restrict__ pos_of)
 {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x)
-        sorted_idx[atomicAdd(cursor + __ldg(cell_of + i), 1)] = (int)i;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+        const int k = atomicAdd(cursor + __ldg(cell_of + i), 1);
+        sorted4[k] = make_float4(__ldg(x + i), __ldg(y + i), __ldg(z + i), __int_as_float((int)i));
+        pos_of[i] = k;
+    }
+}
+
+// d2(p, q) <= r2 evaluated as the reference does (float64 on the fp32 coordinates), with an fp32 pre-test that settles
+// every pair that is not within 1e-5 (relative) of the boundary
+__device__ __forceinline__ bool within_f64(float px, float py, float qx, float qy, float r2f, double r2)
+{
+    const float dx = qx - px, dy = qy - py;
+    const float d2 = fmaf(dx, dx, dy * dy);
+    if (d2 < r2f * 0.99999f) return true;
+    if (d2 > r2f * 1.00001f + 1e-30f) return false;
+    const double ex = (double)qx - (double)px, ey = (double)qy - (double)py;
+    return ex * ex + ey * ey <= r2;
+}
+__device__ __forceinline__ bool within_center_f64(double cx, double cy, float qx, float qy, float r2f, double r2)
+{
+    const float dx = qx - (float)cx, dy = qy - (float)cy;  // (float)cx is off by <= half an ulp of cx: covered by the margin below
+    const float d2 = fmaf(dx, dx, dy * dy);
+    const float slack = 1e-5f * r2f + 4.f * sqrtf(r2f) * (fabsf((float)cx) + fabsf((float)cy)) * 1.2e-7f;
+    if (d2 < r2f - slack) return true;
+    if (d2 > r2f + slack) return false;
+    const double ex = (double)qx - cx, ey = (double)qy - cy;
+    return ex * ex + ey * ey <= r2;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // plot extraction: one CTA per plot centre
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int EX_T = 1024;
-constexpr int EX_CAP = 16384;        // points of the parcel inside one plot disk (32 pts/m^2 -> ~10 000; 10 B of smem each)
-constexpr int EX_ZC = 16;            // z-normalisation sub-grid: EX_ZC x EX_ZC cells over the plot's bounding square
+constexpr int EX_BITS = 65536;       // points under one disk's bounding square (with a one-cell margin)
+constexpr int EX_ROWS = 32;          // grid rows under it
+constexpr int EX_CAP = 24576;        // points of the parcel inside one plot disk (32 pts/m^2 -> ~10 000; 8 B of smem each)
 
 // counter-based hash (two rounds of a 32-bit mix): the canonical replacement for np.random in sample_cloud
 __host__ __device__ __forceinline__ unsigned sample_hash(unsigned plot_seed, unsigned j)
@@ -166,8 +195,9 @@ struct ExtractArgs {
     const float *x, *y, *z;      // parcel cloud rows 0..2 (fp32, absolute coordinates, metres)
     const float *feat;           // rows 3..9: [7][P] (R, G, B, NIR, intensity, return_num, num_returns)
     long long P;
-    PGrid grid;
-    const int *cell_start, *sorted_idx;
+    PGrid grid;                  // cell side >= 1.05 * znorm_radius
+    const int *cell_start, *pos_of;
+    const float4 *sorted4;
     const double *centers;       // [C][2] float64
     const unsigned *seeds;       // [C] per-plot seed of the sampling hash
     int C, S;
@@ -185,34 +215,63 @@ extract_plots_kernel(ExtractArgs a)
     extern __shared__ __align__(16) unsigned char ex_smem[];
     unsigned *idx = reinterpret_cast<unsigned *>(ex_smem);                  // [EX_CAP] parcel indices, sorted ascending
     float *zmin = reinterpret_cast<float *>(idx + EX_CAP);                  // [EX_CAP] local minimum of z per point
-    __shared__ int zc_start[EX_ZC * EX_ZC + 1], zc_fill[EX_ZC * EX_ZC];
     __shared__ int s_n, warp_tot[32];
     __shared__ unsigned hist[256];
     __shared__ unsigned s_prefix, s_need;
-    unsigned short *zc_list = reinterpret_cast<unsigned short *>(zmin + EX_CAP);  // [EX_CAP] positions grouped by z-cell
+    // in-disk flag of every point under the disk's bounding square: one bit per position of the cell-grouped copy, row by row
+    __shared__ unsigned inbits[EX_BITS / 32];
+    __shared__ int row_start[EX_ROWS], row_bit0[EX_ROWS + 1];
 
     const int c = blockIdx.x, tid = threadIdx.x;
     const double cx = a.centers[2 * c], cy = a.centers[2 * c + 1];
     const double r2 = (double)a.radius * (double)a.radius;
+    const float r2f = a.radius * a.radius;
+    const PGrid g = a.grid;
     if (tid == 0) s_n = 0;
     __syncthreads();
 
-    // ---- 1. ball query over the grid cells under the disk's bounding square (float64 test on the fp32 coordinates) ----
-    {
-        const PGrid g = a.grid;
-        int cx0 = (int)floorf(((float)(cx - a.radius) - g.x0) * g.inv_cell) - 1, cx1 = (int)floorf(((float)(cx + a.radius) - g.x0) * g.inv_cell) + 1;
-        int cy0 = (int)floorf(((float)(cy - a.radius) - g.y0) * g.inv_cell) - 1, cy1 = (int)floorf(((float)(cy + a.radius) - g.y0) * g.inv_cell) + 1;
-        cx0 = max(cx0, 0); cy0 = max(cy0, 0); cx1 = min(cx1, g.nx - 1); cy1 = min(cy1, g.ny - 1);
-        for (int gy = cy0; gy <= cy1; ++gy) {
-            // cells of one grid row are contiguous in the sorted list: one flat range per row
-            const int s = __ldg(a.cell_start + gy * g.nx + cx0), e = __ldg(a.cell_start + gy * g.nx + cx1 + 1);
-            for (int k = s + tid; k < e; k += EX_T) {
-                const int p = __ldg(a.sorted_idx + k);
-                const double dx = (double)__ldg(a.x + p) - cx, dy = (double)__ldg(a.y + p) - cy;
-                if (dx * dx + dy * dy <= r2) {
-                    const int pos = atomicAdd(&s_n, 1);
-                    if (pos < EX_CAP) idx[pos] = (unsigned)p;
-                }
+    // ---- 1. ball query: the grid rows under the disk's bounding square; the cells of a row are one contiguous range of
+    //         the cell-grouped copy, read as float4 (coalesced).  The in-disk flags are kept as a bit set for step 3. ------
+    int cx0 = (int)floorf(((float)(cx - a.radius) - g.x0) * g.inv_cell) - 1, cx1 = (int)floorf(((float)(cx + a.radius) - g.x0) * g.inv_cell) + 1;
+    int cy0 = (int)floorf(((float)(cy - a.radius) - g.y0) * g.inv_cell) - 1, cy1 = (int)floorf(((float)(cy + a.radius) - g.y0) * g.inv_cell) + 1;
+    cx0 = max(cx0, 0); cy0 = max(cy0, 0); cx1 = min(cx1, g.nx - 1); cy1 = min(cy1, g.ny - 1);
+    const int nrows = cy1 - cy0 + 1;
+    if (nrows > EX_ROWS || cx1 < cx0 || nrows <= 0) {  // a disk far outside the grid, or cells much smaller than the kernel is laid out for
+        if (tid == 0) a.out_n[c] = nrows > EX_ROWS ? -1 : 0;
+        return;
+    }
+    if (tid == 0) {
+        int bit = 0;
+        for (int j = 0; j < nrows; ++j) {
+            const int s = __ldg(a.cell_start + (cy0 + j) * g.nx + cx0), e = __ldg(a.cell_start + (cy0 + j) * g.nx + cx1 + 1);
+            row_start[j] = s;
+            row_bit0[j] = bit;
+            bit += (e - s + 31) & ~31;
+        }
+        row_bit0[nrows] = bit;
+    }
+    for (int i = tid; i < EX_BITS / 32; i += EX_T) inbits[i] = 0u;
+    __syncthreads();
+    const int nbits = row_bit0[nrows];
+    if (nbits > EX_BITS) {
+        if (tid == 0) a.out_n[c] = -nbits;
+        return;
+    }
+    for (int j = 0; j < nrows; ++j) {
+        const int s = row_start[j], e = __ldg(a.cell_start + (cy0 + j) * g.nx + cx1 + 1);
+        for (int k0 = s; k0 < e; k0 += EX_T) {
+            const int k = k0 + tid;
+            bool in = false;
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < e) {
+                q = __ldg(a.sorted4 + k);
+                in = within_center_f64(cx, cy, q.x, q.y, r2f, r2);
+            }
+            const unsigned word = __ballot_sync(SN2_FULL, in);  // k - s is a multiple of 32 at lane 0: one word per warp
+            if ((tid & 31) == 0 && word) inbits[(row_bit0[j] + (k - s)) >> 5] = word;
+            if (in) {
+                const int pos = atomicAdd(&s_n, 1);
+                if (pos < EX_CAP) idx[pos] = (unsigned)__float_as_int(q.w);
             }
         }
     }
@@ -227,58 +286,54 @@ extract_plots_kernel(ExtractArgs a)
 
     // ---- 2. canonical order: ascending parcel index -------------------------------------------------------------
     int n2 = 1;
-    while (n2 < n) n2 <<= 1;
+    while (n2 < n) n2 <<= 1;  // <= 32768: the padding may run into the zmin area behind idx, which is not in use yet
     for (int i = n + tid; i < n2; i += EX_T) idx[i] = 0xffffffffu;
     __syncthreads();
     bitonic_sort_u32(idx, n2);
 
-    // ---- 3. z normalisation: z - min z over the plot's points within znorm_radius in xy (load_data.py:237-249) ----
-    // plot points binned into EX_ZC x EX_ZC cells of side >= znorm_radius over the bounding square: 3 x 3 cells per point
-    const float sq0x = (float)(cx - a.radius), sq0y = (float)(cy - a.radius);
-    // 5 % wider than the search radius: a pair at distance exactly znorm_radius (cm-quantised LAS coordinates) stays within
-    // one cell of each other whatever the fp32 rounding of the cell index
-    const float zcell = fmaxf(2.f * a.radius / EX_ZC, 1.05f * a.znorm_radius);
-    const float inv_zcell = 1.f / zcell;
-    auto zcell_of = [&](float px, float py) {
-        int ix = (int)floorf((px - sq0x) * inv_zcell), iy = (int)floorf((py - sq0y) * inv_zcell);
-        ix = min(max(ix, 0), EX_ZC - 1);
-        iy = min(max(iy, 0), EX_ZC - 1);
-        return iy * EX_ZC + ix;
-    };
-    for (int i = tid; i < EX_ZC * EX_ZC; i += EX_T) zc_fill[i] = 0;
-    __syncthreads();
-    for (int i = tid; i < n; i += EX_T) atomicAdd(&zc_fill[zcell_of(__ldg(a.x + idx[i]), __ldg(a.y + idx[i]))], 1);
-    __syncthreads();
-    if (tid == 0) {
-        int acc = 0;
-        for (int i = 0; i < EX_ZC * EX_ZC; ++i) {
-            zc_start[i] = acc;
-            acc += zc_fill[i];
-            zc_fill[i] = zc_start[i];
-        }
-        zc_start[EX_ZC * EX_ZC] = acc;
-    }
-    __syncthreads();
-    for (int i = tid; i < n; i += EX_T)
-        zc_list[atomicAdd(&zc_fill[zcell_of(__ldg(a.x + idx[i]), __ldg(a.y + idx[i]))], 1)] = (unsigned short)i;
-    __syncthreads();
+    // ---- 3. z normalisation: z - min z over the PLOT's points within znorm_radius in xy (load_data.py:237-249) ---------
+    // One warp per parcel cell under the disk: lanes = the cell's points, and the candidates -- the 3 x 3 cells around it
+    // (cell side >= 1.05 * znorm_radius), three contiguous ranges of the cell-grouped copy -- are walked by the whole warp
+    // together (every lane reads the same float4: one broadcast load, no divergence).  A candidate counts only if it lies in
+    // this plot's disk too (the reference searches inside the extracted cloud); that test is lane independent.
     {
         const double zr2 = (double)a.znorm_radius * (double)a.znorm_radius;
-        const int reach = (int)ceilf(a.znorm_radius * inv_zcell);  // 1 when the cells are at least znorm_radius wide
-        for (int i = tid; i < n; i += EX_T) {
-            const int p = idx[i];
-            const float pxf = __ldg(a.x + p), pyf = __ldg(a.y + p);
-            const double px = pxf, py = pyf;
-            const int zc = zcell_of(pxf, pyf), ix = zc % EX_ZC, iy = zc / EX_ZC;
-            float m = INFINITY;
-            for (int jy = max(iy - reach, 0); jy <= min(iy + reach, EX_ZC - 1); ++jy)
-                for (int jx = max(ix - reach, 0); jx <= min(ix + reach, EX_ZC - 1); ++jx)
-                    for (int k = zc_start[jy * EX_ZC + jx]; k < zc_start[jy * EX_ZC + jx + 1]; ++k) {
-                        const int q = idx[zc_list[k]];
-                        const double dx = (double)__ldg(a.x + q) - px, dy = (double)__ldg(a.y + q) - py;
-                        if (dx * dx + dy * dy <= zr2) m = fminf(m, __ldg(a.z + q));
+        const float zr2f = a.znorm_radius * a.znorm_radius;
+        const int lane = tid & 31, warp = tid >> 5;
+        const int ncx = cx1 - cx0 + 1, ncells = ncx * nrows;
+        for (int cell = warp; cell < ncells; cell += EX_T / 32) {
+            const int ry = cell / ncx, iy = cy0 + ry, ix = cx0 + cell % ncx;
+            const int s = __ldg(a.cell_start + iy * g.nx + ix), e = __ldg(a.cell_start + iy * g.nx + ix + 1);
+            const int bit_s = row_bit0[ry] + (s - row_start[ry]);
+            for (int base = s; base < e; base += 32) {
+                const int k = base + lane, b = bit_s + (k - s);
+                const bool mine = k < e && ((inbits[b >> 5] >> (b & 31)) & 1u);
+                if (!__any_sync(SN2_FULL, mine)) continue;
+                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (mine) p = __ldg(a.sorted4 + k);
+                float m = p.z;
+                for (int jr = max(ry - 1, 0); jr <= min(ry + 1, nrows - 1); ++jr) {
+                    const int jy = cy0 + jr;
+                    const int rs = __ldg(a.cell_start + jy * g.nx + max(ix - 1, cx0)), re = __ldg(a.cell_start + jy * g.nx + min(ix + 1, cx1) + 1);
+                    const int bit_r = row_bit0[jr] + (rs - row_start[jr]);
+                    for (int kk = rs; kk < re; ++kk) {
+                        const int bb = bit_r + (kk - rs);
+                        if (!((inbits[bb >> 5] >> (bb & 31)) & 1u)) continue;                 // not in this plot (uniform branch)
+                        const float4 q = __ldg(a.sorted4 + kk);                                // uniform address: broadcast
+                        if (mine && q.z < m && within_f64(p.x, p.y, q.x, q.y, zr2f, zr2)) m = q.z;
                     }
-            zmin[i] = m;
+                }
+                if (mine) {  // position of this point in the plot's ascending index list
+                    const unsigned key = (unsigned)__float_as_int(p.w);
+                    int lo = 0, hi = n - 1;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (idx[mid] < key) lo = mid + 1;
+                        else hi = mid;
+                    }
+                    zmin[lo] = m;
+                }
+            }
         }
     }
     __syncthreads();
@@ -491,10 +546,11 @@ finalize_bands_kernel(const double *__restrict__ in, long long HW, const double 
 
 using namespace sn2;
 
-extern "C" int sn2_parcel_grid_build(const float *x, const float *y, long long P, float x0, float y0, float cell, int nx, int ny,
-                                     int *cell_of, int *count, int *cell_start, int *cursor, int *sorted_idx, void *stream)
+extern "C" int sn2_parcel_grid_build(const float *x, const float *y, const float *z, long long P, float x0, float y0, float cell, int nx,
+                                     int ny, int *cell_of, int *count, int *cell_start, int *cursor, float *sorted4, int *pos_of,
+                                     void *stream)
 {
-    if (!x || !y || !cell_of || !count || !cell_start || !cursor || !sorted_idx || P <= 0 || P > 0x7fffffffll || nx <= 0 || ny <= 0 || !(cell > 0.f))
+    if (!x || !y || !z || !cell_of || !count || !cell_start || !cursor || !sorted4 || !pos_of || (reinterpret_cast<uintptr_t>(sorted4) & 15) || P <= 0 || P > 0x7fffffffll || nx <= 0 || ny <= 0 || !(cell > 0.f))
         return SN2_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     PGrid g{x0, y0, 1.f / cell, nx, ny};
@@ -504,7 +560,7 @@ extern "C" int sn2_parcel_grid_build(const float *x, const float *y, long long P
     SN2_LAUNCH_CHECK("pgrid_count_kernel");
     pgrid_scan_kernel<<<1, 1024, 0, st>>>(count, nx * ny, cell_start, cursor);
     SN2_LAUNCH_CHECK("pgrid_scan_kernel");
-    pgrid_scatter_kernel<<<grid, 256, 0, st>>>(cell_of, P, cursor, sorted_idx);
+    pgrid_scatter_kernel<<<grid, 256, 0, st>>>(x, y, z, cell_of, P, cursor, reinterpret_cast<float4 *>(sorted4), pos_of);
     SN2_LAUNCH_CHECK("pgrid_scatter_kernel");
     return SN2_OK;
 }
@@ -512,20 +568,21 @@ extern "C" int sn2_parcel_grid_build(const float *x, const float *y, long long P
 extern "C" int sn2_plot_capacity(void) { return EX_CAP; }
 
 extern "C" int sn2_extract_plots(const float *xyz, const float *feat, long long P, float x0, float y0, float cell, int nx, int ny,
-                                 const int *cell_start, const int *sorted_idx, const double *centers, const unsigned *seeds, int C,
+                                 const int *cell_start, const float *sorted4, const int *pos_of, const double *centers, const unsigned *seeds, int C,
                                  int S, float radius, float znorm_radius, float z_max, int diam_meters, int min_points,
                                  float *out_xyz, float *out_cloud, int *out_n, int *out_src, void *stream)
 {
-    if (!xyz || !feat || !cell_start || !sorted_idx || !centers || !seeds || !out_xyz || !out_cloud || !out_n || C <= 0 || S <= 0 ||
+    if (cell < 1.05f * znorm_radius) return SN2_EINVAL;  // the 3 x 3-cell neighbourhood must cover the z-normalisation radius
+    if (!xyz || !feat || !cell_start || !sorted4 || !pos_of || !centers || !seeds || !out_xyz || !out_cloud || !out_n || C <= 0 || S <= 0 ||
         P <= 0 || diam_meters <= 0 || diam_meters > 64 || !(radius > 0.f) || !(znorm_radius > 0.f))
         return SN2_EINVAL;
     ExtractArgs a;
     a.x = xyz; a.y = xyz + P; a.z = xyz + 2 * P; a.feat = feat; a.P = P;
     a.grid = PGrid{x0, y0, 1.f / cell, nx, ny};
-    a.cell_start = cell_start; a.sorted_idx = sorted_idx; a.centers = centers; a.seeds = seeds; a.C = C; a.S = S;
+    a.cell_start = cell_start; a.sorted4 = reinterpret_cast<const float4 *>(sorted4); a.pos_of = pos_of; a.centers = centers; a.seeds = seeds; a.C = C; a.S = S;
     a.radius = radius; a.znorm_radius = znorm_radius; a.z_max = z_max; a.diam_meters = diam_meters; a.min_points = min_points;
     a.out_xyz = out_xyz; a.out_cloud = out_cloud; a.out_n = out_n; a.out_src = out_src;
-    const size_t smem = (size_t)EX_CAP * (sizeof(unsigned) + sizeof(float) + sizeof(unsigned short));
+    const size_t smem = (size_t)EX_CAP * (sizeof(unsigned) + sizeof(float));
     auto kern = extract_plots_kernel;
     SN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "extract_plots attr");
     kern<<<C, EX_T, smem, (cudaStream_t)stream>>>(a);

@@ -81,9 +81,10 @@ SIGNATURES = {
     "sn2_bn_finalize_sync": [_vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp],
     "sn2_bn_bwd_sync": [_vp, _vp, _vp, _i, _vp, _vp, _vp],
     "sn2_adam_step": [_vp, _vp, _f, _vp, _vp, _vp, _ll, _vp, _f, _f, _f, _f, _vp, _vp],
-    "sn2_parcel_grid_build": [_vp, _vp, _ll, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "sn2_augment_rescale": [_vp, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp],
+    "sn2_parcel_grid_build": [_vp, _vp, _vp, _ll, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "sn2_plot_capacity": [],
-    "sn2_extract_plots": [_vp, _vp, _ll, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "sn2_extract_plots": [_vp, _vp, _ll, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "sn2_sample_hash": [ctypes.c_uint, ctypes.c_uint],
     "sn2_finalize_mosaic": [_vp, _i, _i, _vp, _vp, _vp, _vp],
     "sn2_fuse_accumulate": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],

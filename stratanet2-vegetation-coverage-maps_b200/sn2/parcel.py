@@ -63,9 +63,10 @@ def keep_points_in_shape(centers: np.ndarray, polygon_xy: np.ndarray, inclusion_
 
 class ParcelCloud:
     """A parcel's LAS cloud in HBM: float32 rows (x, y, z, R, G, B, NIR, intensity, return_num, num_returns) as
-    ``load_las_file`` returns them (utils/load_data.py:149-184), plus a uniform xy grid over it (cells of 5 m)."""
+    ``load_las_file`` returns them (utils/load_data.py:149-184), plus a cell-grouped float4 copy of (x, y, z, index) over a
+    uniform xy grid (cells of 1.6 m >= 1.05 x the z-normalisation radius: a point's 3 x 3 cells hold all its neighbours)."""
 
-    def __init__(self, cloud, device, cell: float = 5.0):
+    def __init__(self, cloud, device, cell: float = 1.6):
         cloud = torch.as_tensor(cloud)
         if cloud.dim() != 2 or cloud.shape[0] != 10 or cloud.dtype != torch.float32:
             raise RuntimeError("sn2 ParcelCloud: expected a float32 [10, P] array (the layout of load_las_file)")
@@ -81,10 +82,11 @@ class ParcelCloud:
         self.ny = max(1, int(math.floor((self.y_max - self.y_min) / cell)) + 1)
         i32 = lambda n: torch.empty(n, dtype=torch.int32, device=self.device)  # noqa: E731
         cell_of, count, cursor = i32(self.P), i32(self.nx * self.ny), i32(self.nx * self.ny)
-        self.cell_start, self.sorted_idx = i32(self.nx * self.ny + 1), i32(self.P)
-        check(lib.sn2_parcel_grid_build(dptr(self.xyz[0]), dptr(self.xyz[1]), self.P, self.x_min, self.y_min, self.cell, self.nx, self.ny,
-                                        dptr(cell_of), dptr(count), dptr(self.cell_start), dptr(cursor), dptr(self.sorted_idx),
-                                        stream_ptr()), "sn2_parcel_grid_build")
+        self.cell_start, self.pos_of = i32(self.nx * self.ny + 1), i32(self.P)
+        self.sorted4 = torch.empty((self.P, 4), dtype=torch.float32, device=self.device)
+        check(lib.sn2_parcel_grid_build(dptr(self.xyz[0]), dptr(self.xyz[1]), dptr(self.xyz[2]), self.P, self.x_min, self.y_min, self.cell,
+                                        self.nx, self.ny, dptr(cell_of), dptr(count), dptr(self.cell_start), dptr(cursor),
+                                        dptr(self.sorted4), dptr(self.pos_of), stream_ptr()), "sn2_parcel_grid_build")
         ops._count(3)
 
 
@@ -104,7 +106,7 @@ def extract_plots(parcel: ParcelCloud, centers, args, seeds=None, want_src: bool
     n = torch.empty(C, dtype=torch.int32, device=dev)
     src = torch.empty((C, S), dtype=torch.int32, device=dev) if want_src else None
     check(lib.sn2_extract_plots(dptr(parcel.xyz), dptr(parcel.feat), parcel.P, parcel.x_min, parcel.y_min, parcel.cell, parcel.nx,
-                                parcel.ny, dptr(parcel.cell_start), dptr(parcel.sorted_idx), dptr(cen), dptr(sd), C, S,
+                                parcel.ny, dptr(parcel.cell_start), dptr(parcel.sorted4), dptr(parcel.pos_of), dptr(cen), dptr(sd), C, S,
                                 float(args.diam_meters // 2), float(args.znorm_radius_in_meters), float(args.z_max),
                                 int(args.diam_meters), MIN_N_POINTS_FOR_INFERENCE, dptr(xyz), dptr(cloud), dptr(n), dptr(src),
                                 stream_ptr()), "sn2_extract_plots")

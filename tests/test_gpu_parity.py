@@ -1346,3 +1346,93 @@ def test_predict_parcel_end_to_end(cuda_device):
         assert np.mean(np.abs(got[b][ok] - want[b][ok]) > 1e-3 * np.abs(want[b][ok]) + 1e-5) < 2e-3
     assert abs(float(info["threshold"]) - thr) <= 2e-4                      # neighbouring thresholds when the soft band moves by 1e-3
     assert np.mean(got[3][ok] != want[3][ok]) < 5e-3                         # hard band: only pixels within 1e-3 of the threshold
+
+
+def test_device_loader_transforms_match_numpy_restatement(cuda_device):
+    """sn2.loader.augment_rescale (csrc/loader.cu) against oracle/loader_port.py (augment + rescale_cloud of
+    data_loader/loader.py:135-214, numpy) with the same draws: bit-exact positions and features except where cos / sin
+    differ in the last bit between libm and CUDA (then 1 ulp)."""
+    from oracle import loader_port
+    from sn2.loader import augment_rescale, draw_augmentation
+
+    B, N = 5, 3000
+    rng = np.random.default_rng(1)
+    raw = np.zeros((B, 10, N), dtype=np.float32)
+    raw[:, :2] = rng.uniform(-10, 10, (B, 2, N))
+    raw[:, 2] = rng.uniform(0, 20, (B, N))
+    raw[:, 3:7] = rng.integers(0, 65536, (B, 4, N))
+    raw[:, 7] = rng.integers(0, 32768, (B, N))
+    raw[:, 8:] = rng.integers(1, 6, (B, 2, N))
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    angle, flip, noise = draw_augmentation(B, N, cuda_device, g)
+    assert ((torch.rad2deg(angle).round() - torch.rad2deg(angle)).abs() < 1e-9).all() and noise.dtype == torch.float64
+    got = augment_rescale(torch.from_numpy(raw).to(cuda_device), 24.24, angle, flip, noise)
+    plain = augment_rescale(torch.from_numpy(raw).to(cuda_device), 24.24)
+    for b in range(B):
+        xyz_w, cloud_w = loader_port.load_transform(raw[b], 24.24, float(angle[b]), flip[b].cpu().numpy(), noise[b].cpu().numpy())
+        np.testing.assert_allclose(got["xyz"][b].cpu().numpy(), xyz_w, rtol=3e-7, atol=1e-6)
+        np.testing.assert_allclose(got["cloud"][b].cpu().numpy(), cloud_w, rtol=3e-7, atol=1e-7)
+        assert np.array_equal(got["cloud"][b, 7:].cpu().numpy(), cloud_w[7:]) and np.array_equal(got["xyz"][b, 2].cpu().numpy(), xyz_w[2])
+        xyz_p, cloud_p = loader_port.load_transform(raw[b], 24.24)
+        assert np.array_equal(plain["xyz"][b].cpu().numpy(), xyz_p) and np.array_equal(plain["cloud"][b].cpu().numpy(), cloud_p)
+
+
+def test_batched_evaluation_and_pseudo_labelling(cuda_device):
+    """sn2.drivers.evaluate_batched (B plots per launch, one synchronisation) returns the numbers of the reference's
+    batch_size = 1 loop (learning/test.py:38-76: meters are averages of per-plot losses), here recomputed plot by plot
+    through the drop-in API and the torch loss formulas, and against the CPU oracle; pseudo_label fills "coverages" for plots
+    with more than 2000 raw points (predict.py:104-111, inference/predict_utils.py:62-71)."""
+    from model.project_to_2d import project_to_plotwise_coverages
+    from oracle.pointnet2_port import project_to_plotwise_coverages_port
+    from sn2 import drivers, losses
+
+    N, P = 2048, 11
+    args, net, port = _make_models(N, cuda_device)
+    data = _plots(6, P, N)
+    g = torch.Generator().manual_seed(1)
+    cov_gt = torch.rand(P, 4, generator=g)
+    X = np.linspace(-30.0, 30.0, 5000)
+    a = np.abs(X)
+    Y = np.stack([np.exp(-a), 0.5 * np.exp(-0.5 * (a - 1.0) ** 2), 0.1 + 0.05 * a])
+    lut = losses.KdeLut(X, Y, cuda_device)
+    batches = [{"xyz": data["xyz"][i:i + 4], "cloud": data["cloud"][i:i + 4], "coverages": cov_gt[i:i + 4]} for i in range(0, P, 4)]
+    got, summaries = drivers.evaluate_batched(net, batches, args, lut)
+    assert len(summaries) == P
+    # the reference loop: one plot at a time
+    tot = {k: 0.0 for k in ("total_loss", "MAE_loss", "log_loss", "MAE_veg_b", "MAE_veg_moy", "MAE_veg_h")}
+    tot_o = dict(tot)
+    from scipy.interpolate import interp1d
+    f = [interp1d(X, Y[c]) for c in range(3)]
+    with torch.no_grad():
+        for i in range(P):
+            one = {"xyz": data["xyz"][i:i + 1], "cloud": data["cloud"][i:i + 1]}
+            cov, proba = net(one)
+            pl = project_to_plotwise_coverages(cov, one["cloud"], args)
+            pdf = lut.pdf(net.last_cloud_device, args.z_max)
+            gt = cov_gt[i:i + 1].to(cuda_device)
+            la, ll, le = losses.get_absolute_loss(pl, gt), losses.get_NLL_loss(proba, pdf)[0], losses.get_entropy_loss(proba)
+            st = losses.get_absolute_loss_by_strata(pl, gt)
+            for k, v in zip(tot, (la + args.m * ll + args.e * le, la, ll, st[0], st[1], st[2])):
+                tot[k] += float(v) / P
+            np.testing.assert_allclose(summaries[i][0], pl.cpu().numpy()[0], rtol=0, atol=0)
+            # CPU oracle, same plot
+            cov_o, proba_o = port(one)
+            pl_o = project_to_plotwise_coverages_port(cov_o, one["cloud"], args)
+            z = (one["cloud"][0, 2] * args.z_max).numpy().astype(np.float64)
+            pdf_o = torch.from_numpy(np.stack([fc(z) for fc in f], axis=1))
+            la, ll, le = losses.get_absolute_loss(pl_o, cov_gt[i:i + 1]), losses.get_NLL_loss(proba_o, pdf_o)[0], losses.get_entropy_loss(proba_o)
+            st = losses.get_absolute_loss_by_strata(pl_o, cov_gt[i:i + 1])
+            for k, v in zip(tot_o, (la + args.m * ll + args.e * le, la, ll, st[0], st[1], st[2])):
+                tot_o[k] += float(v) / P
+    for k in tot:
+        assert abs(got[k] - tot[k]) <= 1e-6 * abs(tot[k]) + 1e-7, (k, got[k], tot[k])
+        assert abs(got[k] - tot_o[k]) <= 1e-3 * abs(tot_o[k]) + 1e-5, (k, got[k], tot_o[k])
+    # pseudo-labelling
+    dataset = {f"PP{i:08d}": {"xyz": data["xyz"][i], "cloud": data["cloud"][i], "N_points_in_cloud": 1500 if i == 3 else 9000} for i in range(P)}
+    collate = lambda items: {"xyz": torch.stack([d["xyz"] for d in items]), "cloud": torch.stack([d["cloud"] for d in items])}  # noqa: E731
+    labelled = drivers.pseudo_label(net, dataset, collate, args, batch_size=4)
+    assert "PP00000003" not in labelled and len(labelled) == P - 1
+    with torch.no_grad():
+        cov, _ = net({"xyz": data["xyz"][5:6], "cloud": data["cloud"][5:6]})
+        want = project_to_plotwise_coverages(cov, data["cloud"][5:6], args).cpu().numpy()[0]
+    assert np.array_equal(labelled["PP00000005"]["coverages"], want)
