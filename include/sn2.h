@@ -73,7 +73,10 @@ int sn2_fps(const float *pos4, int B, int N, int M, const int *start, int *idx_o
  * bounding-box pruning (csrc/fps.cu); AUTO picks BUCKETED above 4096 points, BRUTE below. */
 enum { SN2_FPS_AUTO = 0, SN2_FPS_BRUTE = 1, SN2_FPS_BUCKETED = 2,
        SN2_FPS_BUCKETED_SPEC4 = 3 /* experimental: speculative 4-sample rounds, same indices, currently slower */,
-       SN2_FPS_CLUSTER4 = 4 /* the bucketed kernel on a 4-CTA cluster per plot (always used above 16384 points) */ };
+       SN2_FPS_CLUSTER4 = 4 /* the bucketed kernel on a 4-CTA cluster per plot (always used above 16384 points) */,
+       SN2_FPS_BUCKETED_ILP2 = 5 /* two active buckets of a warp updated per loop trip (interleaved TMEM / REDUX chains) */,
+       SN2_FPS_BUCKETED_NW16 = 6 /* 16 warps x 16 bucket slots instead of 8 x 32 */,
+       SN2_FPS_BUCKETED_NW16_ILP2 = 7 };
 int sn2_fps_algo(const float *pos4, int B, int N, int M, const int *start, int *idx_out,
                  float *pos4_out, int algo, void *stream);
 

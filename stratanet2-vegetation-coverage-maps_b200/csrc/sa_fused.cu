@@ -83,13 +83,8 @@ __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long da
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem_d), "l"(da),
                  "l"(db), "r"(UMMA_IDESC), "r"(acc), "r"(0), "r"(0), "r"(0), "r"(0));
 }
-constexpr int TC_PAD = 6144;                                  // an M=128 operand window around a 32-row region
-constexpr int TC_A_BYTES = TC_PAD + SF_WARPS * 8192 + 8192;   // per warp: 2 stages x (2 KB hi rows + 2 KB lo rows)
-constexpr int TC_SMEM = TC_A_BYTES + 2 * 1024 + 256;          // + W2 hi / lo tiles + mbarriers
-constexpr int TC_TMEM_COLS = SF_WARPS * 32;                   // 2 stages x 16 accumulator columns per warp
-
-template <int LEVEL, bool REDO, int DBG = 0, int TC = 0>  // TC: 0 SIMT, 1 tcgen05 3xTF32 (fp32-accurate), 2 tcgen05 plain TF32
-__global__ void __launch_bounds__(SF_WARPS * 32, REDO ? 1 : (LEVEL == 1 ? (TC ? 2 : 3) : 2))
+template <int LEVEL, bool REDO, int DBG = 0>
+__global__ void __launch_bounds__(SF_WARPS * 32, REDO ? 1 : (LEVEL == 1 ? 3 : 2))
 sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell_start,
                 const float4 *__restrict__ sorted, const float4 *__restrict__ qsorted,
                 const float *__restrict__ u, int N, int M, float r2, int K, int words,
@@ -106,42 +101,6 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
     unsigned *bm = reinterpret_cast<unsigned *>(sf_smem + SF_WARPS * RING * sizeof(int)) + (size_t)warp * words;  // REDO only
     const unsigned lt = (1u << lane) - 1u;
 
-    // ---- tensor-core state (TC): per-warp operand rows, W2 tiles, per-warp mbarrier, TMEM accumulators ----
-    static_assert(!TC || (LEVEL == 1 && !REDO), "the tcgen05 path covers the level-1 streaming kernel");
-    unsigned char *tc_base = sf_smem + SF_WARPS * RING * sizeof(int);  // 1024-byte aligned (ring = 8 KB)
-    unsigned char *a_st = tc_base + TC_PAD + warp * 8192;  // stage s: hi rows at a_st + s*4096, lo rows 2 KB after
-    float *b_hi = reinterpret_cast<float *>(tc_base + TC_A_BYTES), *b_lo = b_hi + 256;
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(tc_base + TC_A_BYTES + 2048);
-    __shared__ unsigned s_tmem;
-    unsigned tmem_d = 0, tc_parity = 0;  // tc_parity: bit s = phase parity of stage s's mbarrier
-    unsigned long long d_a0 = 0, d_bhi = 0, d_blo = 0;
-    if constexpr (TC) {
-        if (warp == 0) {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)),
-                         "r"(TC_TMEM_COLS));
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
-        }
-        if (lane < 2) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bars[2 * warp + lane])));
-        {   // W2 as the B operand [N = 16 (o) x K = 16 (k)], split into tf32 hi + lo (3xTF32: fp32-accurate product)
-            const int o = threadIdx.x >> 4, k = threadIdx.x & 15;
-            const float wv = W.l2.w[k][o];
-            const float hi = __uint_as_float(__float_as_uint(wv) & 0xffffe000u);
-            const int off = (o >> 3) * 128 + (k >> 2) * 32 + (o & 7) * 4 + (k & 3);  // in floats
-            b_hi[off] = TC == 1 ? hi : wv;
-            b_lo[off] = wv - hi;
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;\n");
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;\n");
-        __syncthreads();
-        asm volatile("tcgen05.fence::after_thread_sync;\n");
-        const int qd = warp & 3;  // TMEM lane quarter this warp can read = rows 32*qd.. of its M=128 tile
-        tmem_d = s_tmem + ((unsigned)(32 * qd) << 16) + (unsigned)(32 * warp);
-        d_a0 = umma_desc(smem_u32(a_st) - qd * 2048);  // stage s: +4096 B (= +256 in the address field); lo: +2048 B
-        d_bhi = umma_desc(smem_u32(b_hi));
-        d_blo = umma_desc(smem_u32(b_lo));
-    }
-
     // work items: streaming = one (plot, cell-ordered query) per warp; redo = entries of the overflow list
     long long item = REDO ? (long long)blockIdx.x * SF_WARPS + warp : 0;
     const long long n_items = REDO ? (long long)ovf[0] : 1;
@@ -154,7 +113,7 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
         } else {
             b = blockIdx.y;
             j = blockIdx.x * SF_WARPS + warp;
-            if (j >= M) break;  // (no early return: the TC variant frees tensor memory after the loop)
+            if (j >= M) break;
         }
         const float *hdr = grid_hdr + (size_t)b * SN2_GRID_HDR;
         const int *cs = cell_start + (size_t)b * (SN2_GRID_CELLS + 1);
@@ -217,99 +176,6 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
                 for (int o = 0; o < C; ++o) mx[o] = fmaxf(mx[o], h2[o]);
             }
         };
-
-        // Tensor-core form of one 32-edge batch, split in two halves so the MMA latency hides under the next
-        // batch's search + gather (two operand / accumulator stages per warp):
-        //   tc_issue  : layer 1 in registers, rows -> this warp's private operand region, 6 x tcgen05.mma
-        //               (128x16x8 TF32; 3xTF32 split A_hi B_hi + A_lo B_hi + A_hi B_lo keeps fp32 accuracy;
-        //               the rows of the other three lane quarters of the M=128 tile are don't-care), commit.
-        //   tc_consume: wait for that stage's mbarrier, tcgen05.ld the 32 rows x 16 columns, ReLU/BN/max.
-        auto tc_issue = [&](const int id, const int take, const int st) {
-            if constexpr (TC) {
-                float h1[C];
-#pragma unroll
-                for (int o = 0; o < C; ++o) h1[o] = 0.f;
-                if (lane < take) {
-                    const float *ur = ub + (size_t)id * C;
-#pragma unroll
-                    for (int g = 0; g < C / 4; ++g) {
-                        const float4 t4 = ldg4(ur + 4 * g);
-                        h1[4 * g] = t4.x + c[4 * g];
-                        h1[4 * g + 1] = t4.y + c[4 * g + 1];
-                        h1[4 * g + 2] = t4.z + c[4 * g + 2];
-                        h1[4 * g + 3] = t4.w + c[4 * g + 3];
-                    }
-                    relu_bn(W.l1, h1);
-                }
-                unsigned char *ah = a_st + st * 4096 + (lane >> 3) * 512 + (lane & 7) * 16;
-#pragma unroll
-                for (int kc = 0; kc < 4; ++kc) {
-                    float hi[4], lo[4];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        hi[t] = __uint_as_float(__float_as_uint(h1[4 * kc + t]) & 0xffffe000u);
-                        lo[t] = h1[4 * kc + t] - hi[t];
-                    }
-                    if (TC == 1) {
-                        *reinterpret_cast<float4 *>(ah + kc * 128) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<float4 *>(ah + 2048 + kc * 128) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                    } else {  // plain TF32: the tensor core truncates the low 13 mantissa bits itself
-                        *reinterpret_cast<float4 *>(ah + kc * 128) =
-                            make_float4(h1[4 * kc], h1[4 * kc + 1], h1[4 * kc + 2], h1[4 * kc + 3]);
-                    }
-                }
-                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-                __syncwarp();
-                if (lane == 0) {
-                    asm volatile("tcgen05.fence::after_thread_sync;\n");
-                    const unsigned dcol = s_tmem + (unsigned)(32 * warp + 16 * st);  // all 128 lanes, this stage's 16 columns
-                    const unsigned long long ahi = d_a0 + (unsigned long long)(st * 256), alo = ahi + 128;
-                    // K = 16 = two K=8 steps: +256 bytes (2 core matrices, +16 in the address field) on both operands
-                    umma_tf32(dcol, ahi, d_bhi, 0u);
-                    umma_tf32(dcol, ahi + 16, d_bhi + 16, 1u);
-                    if (TC == 1) {
-                        umma_tf32(dcol, alo, d_bhi, 1u);
-                        umma_tf32(dcol, alo + 16, d_bhi + 16, 1u);
-                        umma_tf32(dcol, ahi, d_blo, 1u);
-                        umma_tf32(dcol, ahi + 16, d_blo + 16, 1u);
-                    }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
-                                     smem_u32(&bars[2 * warp + st]))
-                                 : "memory");
-                }
-                __syncwarp();
-            }
-        };
-        auto tc_consume = [&](const int take, const int st) {
-            if constexpr (TC) {
-                unsigned done = 0;
-                for (int spin = 0; spin < (1 << 24) && !done; ++spin)
-                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                                 "selp.u32 %0, 1, 0, p;\n\t}\n"
-                                 : "=r"(done)
-                                 : "r"(smem_u32(&bars[2 * warp + st])), "r"((tc_parity >> st) & 1u)
-                                 : "memory");
-                if (!done) __trap();  // the MMA never completed: fail loudly instead of hanging the GPU
-                tc_parity ^= 1u << st;
-                asm volatile("tcgen05.fence::after_thread_sync;\n");
-                unsigned d[16];
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-                             : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]),
-                               "=r"(d[8]), "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15])
-                             : "r"(tmem_d + (unsigned)(16 * st)));
-                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;\n");
-                if (lane < take) {
-#pragma unroll
-                    for (int o = 0; o < C; ++o) {
-                        const float h2 = fmaf(fmaxf(__uint_as_float(d[o]) + W.l2.b[o], 0.f), W.l2.s[o], W.l2.t[o]);
-                        mx[o] = fmaxf(mx[o], h2);
-                    }
-                }
-                __syncwarp();
-            }
-        };
-        int tc_stage = 0, tc_pending = 0;  // tc_pending = rows of the batch in flight on stage tc_stage ^ 1 (0: none)
 
         if (REDO) {  // hit set as a bitmap over the plot's point indices
             for (int w = lane; w < words; w += 32) bm[w] = 0u;
@@ -391,12 +257,7 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
             head += take;
             cnt += take;
             __syncwarp();
-            if (TC) {
-                tc_issue(id, take, tc_stage);
-                if (tc_pending) tc_consume(tc_pending, tc_stage ^ 1);
-                tc_pending = take;
-                tc_stage ^= 1;
-            } else if (LEVEL == 2) {
+            if (LEVEL == 2) {
                 // lane = channel: one coalesced 128-byte read of u_j per neighbour, ids broadcast by shuffle
                 int t = 0;
                 for (; t + 4 <= take; t += 4) {
@@ -417,7 +278,6 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
             }
         }
 
-        if (TC && tc_pending) tc_consume(tc_pending, tc_stage ^ 1);
         const size_t row = (size_t)b * M + qloc;
         if (!REDO && cnt > K) {  // the cap binds: leave this centroid to the exact redo launch
             if (lane == 0) ovf[1 + atomicAdd(ovf, 1)] = b * M + j;
@@ -426,12 +286,11 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
         if constexpr (LEVEL == 1) {
 #pragma unroll
             for (int o = 0; o < C; ++o) mx[o] = cnt > 0 ? warp_max(mx[o]) : 0.f;
-            if constexpr (!TC) {  // streaming / redo kernels track the (sign-adjusted) pre-activation: finish it here
+            // the kernel tracks the (sign-adjusted) pre-activation: finish it here
 #pragma unroll
-                for (int o = 0; o < C; ++o) {
-                    const float sc = W.l2.s[o], a = sc < 0.f ? -mx[o] : mx[o];
-                    mx[o] = cnt > 0 ? fmaf(fmaxf(a, 0.f), sc, W.l2.t[o]) : 0.f;
-                }
+            for (int o = 0; o < C; ++o) {
+                const float sc = W.l2.s[o], a = sc < 0.f ? -mx[o] : mx[o];
+                mx[o] = cnt > 0 ? fmaf(fmaxf(a, 0.f), sc, W.l2.t[o]) : 0.f;
             }
             if (lane == 0) {
                 float4 *o4 = reinterpret_cast<float4 *>(out + row * C);
@@ -447,12 +306,279 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
             if (cnt_out) cnt_out[row] = cnt;
         }
     }
-    if constexpr (TC) {  // release tensor memory once every warp is done with it
-        asm volatile("tcgen05.fence::before_thread_sync;\n");
-        __syncthreads();
-        if (warp == 0)
-            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(s_tmem), "r"(TC_TMEM_COLS));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Level 1 with the second layer (the one dense per-edge contraction left: [E,16] x [16,16]) on the tensor cores.
+//
+// Four warps (one warpgroup; a CTA holds two) share ONE M = 128 accumulator tile: warp r of the group owns rows
+// 32r .. 32r+31 -- the TMEM lane quarter it is allowed to touch -- so every row of the tile is a real edge (the round-1
+// variant gave each warp a private M = 128 tile: 3/4 of the rows were padding and the tensor core spent its time
+// reading them from shared memory).  The A operand never passes through shared memory: each lane computes layer 1 of
+// its edge in registers (u_j + c_i, ReLU, BN) and writes the 16 values of its row straight into tensor memory
+// (tcgen05.st 32x32b.x16: lane = row, column = k); tcgen05.mma takes A from TMEM, B = W2^T (16 x 16, K-major,
+// no swizzle) from shared memory, D into TMEM.  The warps of a group work on different centroids but advance in
+// lock-step ROUNDS: produce a batch of <= 32 edges (search + ring as in the SIMT kernel), store the rows, meet at a
+// named barrier (bar.red.or also tells the group whether anybody has edges left), one thread issues the MMAs and
+// commits them to the stage's mbarrier, and the result is consumed one round later (two stages), so the MMA latency
+// (~300 cycles) hides under the next batch's search.  The per-edge epilogue is 16 fmax: bias, ReLU and BatchNorm are
+// applied once per centroid (monotone in the pre-activation; W2 columns with a negative BN scale are negated by the
+// launcher, as in the SIMT kernel).
+// MODE 1: 3xTF32 (A_hi B_hi + A_lo B_hi + A_hi B_lo, operands split into tf32 hi + lo): fp32-accurate, 6 MMAs / round.
+// MODE 2: TF32, operands rounded to nearest (cvt.rna): what torch 1.8 + cuBLAS did on the reference's Ampere GPUs.
+// MODE 3: operands rounded to BF16 precision (RNE) and multiplied on the same pipe -- bit-identical to a bf16 x bf16 ->
+//         fp32 MMA (products of bf16 values are exact in the tf32 datapath).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TC_RING = 256;
+template <int MODE> struct TcLayout {
+    static constexpr int A_COLS = MODE == 1 ? 32 : 16;         // A_hi (+ A_lo)
+    static constexpr int STAGE = A_COLS + 16;                  // + D
+    static constexpr int GROUP = 2 * STAGE;                    // two stages
+    static constexpr int COLS = MODE == 1 ? 256 : 128;         // allocation (power of two) for the CTA's two groups
+};
+
+__device__ __forceinline__ void umma_tf32_ts(unsigned tmem_d, unsigned tmem_a, unsigned long long db, unsigned acc)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a),
+                 "l"(db), "r"(UMMA_IDESC), "r"(acc), "r"(0), "r"(0), "r"(0), "r"(0));
+}
+__device__ __forceinline__ void tmem_st16(unsigned addr, const float (&v)[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(addr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                 "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                 "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+                 : "memory");
+}
+__device__ __forceinline__ float round_tf32(float x)
+{
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float round_bf16(float x)
+{
+    unsigned u = __float_as_uint(x);
+    u += 0x7fffu + ((u >> 16) & 1u);  // round to nearest even on the upper 16 bits (finite inputs)
+    return __uint_as_float(u & 0xffff0000u);
+}
+template <int MODE>
+__device__ __forceinline__ float tc_operand(float x)
+{
+    if (MODE == 2) return round_tf32(x);
+    if (MODE == 3) return round_bf16(x);
+    return x;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(SF_WARPS * 32, MODE == 1 ? 2 : 3)
+sa1_tc_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
+              const float4 *__restrict__ qsorted, const float *__restrict__ u, int N, int M, float r2, int K,
+              const __grid_constant__ W_SA1 W, float *__restrict__ out, int *__restrict__ cnt_out, int *__restrict__ ovf)
+{
+    using L = TcLayout<MODE>;
+    constexpr int C = SN2_C1, UNR = 4;
+    __shared__ int ring_all[SF_WARPS * TC_RING];
+    __shared__ __align__(1024) float b_tiles[2 * 256];      // W2^T hi | lo, canonical K-major no-swizzle layout
+    __shared__ __align__(8) unsigned long long bars[2 * 2];  // [group][stage]
+    __shared__ unsigned s_tmem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = warp >> 2, rq = warp & 3;
+    int *ring = ring_all + warp * TC_RING;
+    const unsigned lt = (1u << lane) - 1u;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "r"(L::COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
     }
+    if (threadIdx.x < 4) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bars[threadIdx.x])));
+    {   // B operand [N = 16 (o) x K = 16 (k)]: element (o, k) at (o/8)*128 + (k/4)*32 + (o%8)*4 + k%4 floats
+        const int o = threadIdx.x >> 4, k = threadIdx.x & 15;
+        const float wv = tc_operand<MODE>(W.l2.w[k][o]);
+        const float hi = __uint_as_float(__float_as_uint(wv) & 0xffffe000u);
+        const int off = (o >> 3) * 128 + (k >> 2) * 32 + (o & 7) * 4 + (k & 3);
+        b_tiles[off] = MODE == 1 ? hi : wv;
+        b_tiles[256 + off] = MODE == 1 ? wv - hi : 0.f;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n");
+    const unsigned tbase = s_tmem + (unsigned)(grp * L::GROUP);             // this group's columns, lane 0
+    const unsigned tmine = tbase + ((unsigned)(32 * rq) << 16);             // ... seen from this warp's lane quarter
+    const unsigned long long d_bhi = umma_desc(smem_u32(b_tiles)), d_blo = umma_desc(smem_u32(b_tiles + 256));
+    unsigned parity = 0;  // bit s: phase parity of this group's stage-s mbarrier
+
+    // ---- this warp's centroid (a warp past the last centroid still takes part in its group's rounds, with no edges) ----
+    const int b = blockIdx.y, j = blockIdx.x * SF_WARPS + warp;
+    const bool live = j < M;
+    const float *hdr = grid_hdr + (size_t)b * SN2_GRID_HDR;
+    const int *cs = cell_start + (size_t)b * (SN2_GRID_CELLS + 1);
+    const float4 *so = sorted + (size_t)b * N;
+    const float4 q = live ? __ldg(qsorted + (size_t)b * M + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int qloc = __float_as_int(q.w);
+    const float *ub = u + (size_t)b * N * C;
+    const float ox = hdr[0], oy = hdr[1], inv = hdr[2], oz = hdr[6], invz = hdr[7];
+    const int gx = __float_as_int(hdr[4]), gy = __float_as_int(hdr[5]), gz = __float_as_int(hdr[8]);
+    const int ix = cell_coord_c(q.x, ox, inv, gx), iy = cell_coord_c(q.y, oy, inv, gy), iz = cell_coord_c(q.z, oz, invz, gz);
+    const int x0 = max(ix - 1, 0), x1 = min(ix + 1, gx - 1), y0 = max(iy - 1, 0), y1 = min(iy + 1, gy - 1);
+    const int z0 = max(iz - 1, 0), z1 = min(iz + 1, gz - 1);
+    const int ny = y1 - y0 + 1, nrows = live ? ny * (z1 - z0 + 1) : 0;
+    auto row_of = [&](int t) { return ((z0 + t / ny) * gy + (y0 + t % ny)) * gx; };
+    float c[C], mx[C];
+#pragma unroll
+    for (int o = 0; o < C; ++o) {
+        c[o] = W.l1.b[o] - (W.l1.w[SN2_F0][o] * q.x + W.l1.w[SN2_F0 + 1][o] * q.y + W.l1.w[SN2_F0 + 2][o] * q.z);
+        mx[o] = -INFINITY;
+    }
+
+    auto consume = [&](const int take, const int st) {
+        unsigned done = 0;
+        for (int spin = 0; spin < (1 << 24) && !done; ++spin)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(done) : "r"(smem_u32(&bars[2 * grp + st])), "r"((parity >> st) & 1u) : "memory");
+        if (!done) __trap();  // the MMA never completed: fail loudly instead of hanging the GPU
+        parity ^= 1u << st;
+        asm volatile("tcgen05.fence::after_thread_sync;\n");
+        unsigned d[16];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                     : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]),
+                       "=r"(d[8]), "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15])
+                     : "r"(tmine + (unsigned)(st * L::STAGE + L::A_COLS)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n");
+        if (lane < take) {
+#pragma unroll
+            for (int o = 0; o < C; ++o) mx[o] = fmaxf(mx[o], __uint_as_float(d[o]));  // raw (sign-adjusted) pre-activation, bias later
+        }
+    };
+
+    int cnt = 0, head = 0, tail = 0, y = 0, base = 0, e = 0;
+    bool open_row = false, more = live;
+    int stage = 0, pending_take = 0;
+    bool pending = false;
+    while (true) {
+        // ---- produce: up to 32 edges of this warp's centroid ----
+        while (more && tail - head < 32) {
+            if (!open_row) {
+                if (y >= nrows) { more = false; break; }
+                base = __ldg(cs + row_of(y) + x0);
+                e = __ldg(cs + row_of(y) + x1 + 1);
+                open_row = true;
+            }
+            float4 vv[UNR];
+#pragma unroll
+            for (int t = 0; t < UNR; ++t) {
+                const int i = base + t * 32 + lane;
+                vv[t] = i < e ? __ldg(so + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int t = 0; t < UNR; ++t) {
+                if (base + t * 32 < e) {
+                    const float4 v = vv[t];
+                    const bool hit = (base + t * 32 + lane < e) && dist2(v.x, v.y, v.z, q.x, q.y, q.z) < r2;
+                    const unsigned bal = __ballot_sync(SN2_FULL, hit);
+                    if (hit) ring[(tail + __popc(bal & lt)) & (TC_RING - 1)] = __float_as_int(v.w);
+                    tail += __popc(bal);
+                }
+            }
+            base += 32 * UNR;
+            if (base >= e) { open_row = false; ++y; }
+            __syncwarp();
+        }
+        const int avail = tail - head, take = min(avail, 32);
+        const int id = take > 0 ? ring[(head + lane) & (TC_RING - 1)] : 0;
+        head += take;
+        cnt += take;
+        __syncwarp();
+        const bool more_after = more || (tail - head > 0);
+        // ---- layer 1 of my edge -> my row of the A tile, straight into tensor memory ----
+        float h1[C];
+#pragma unroll
+        for (int o = 0; o < C; ++o) h1[o] = 0.f;
+        if (lane < take) {
+            const float *ur = ub + (size_t)id * C;
+#pragma unroll
+            for (int g = 0; g < C / 4; ++g) {
+                const float4 t4 = ldg4(ur + 4 * g);
+                h1[4 * g] = t4.x + c[4 * g];
+                h1[4 * g + 1] = t4.y + c[4 * g + 1];
+                h1[4 * g + 2] = t4.z + c[4 * g + 2];
+                h1[4 * g + 3] = t4.w + c[4 * g + 3];
+            }
+            relu_bn(W.l1, h1);
+        }
+        const unsigned a_mine = tmine + (unsigned)(stage * L::STAGE);
+        if constexpr (MODE == 1) {
+            float lo[C];
+#pragma unroll
+            for (int o = 0; o < C; ++o) {
+                const float hi = __uint_as_float(__float_as_uint(h1[o]) & 0xffffe000u);
+                lo[o] = h1[o] - hi;
+                h1[o] = hi;
+            }
+            tmem_st16(a_mine, h1);
+            tmem_st16(a_mine + 16, lo);
+        } else {
+#pragma unroll
+            for (int o = 0; o < C; ++o) h1[o] = tc_operand<MODE>(h1[o]);
+            tmem_st16(a_mine, h1);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n");
+        // ---- rendezvous of the group: all 128 rows of this stage are in TMEM; does anybody have edges left? ----
+        unsigned any_more;
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, 128, q;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(any_more) : "r"((unsigned)more_after), "r"(1 + grp) : "memory");
+        if (rq == 0 && lane == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n");
+            const unsigned a_t = tbase + (unsigned)(stage * L::STAGE), d_t = a_t + (unsigned)L::A_COLS;
+            // K = 16 = two K = 8 steps: +8 columns of A, +256 bytes (= +16 in the descriptor's address field) of B
+            umma_tf32_ts(d_t, a_t, d_bhi, 0u);
+            umma_tf32_ts(d_t, a_t + 8, d_bhi + 16, 1u);
+            if constexpr (MODE == 1) {
+                umma_tf32_ts(d_t, a_t + 16, d_bhi, 1u);
+                umma_tf32_ts(d_t, a_t + 24, d_bhi + 16, 1u);
+                umma_tf32_ts(d_t, a_t, d_blo, 1u);
+                umma_tf32_ts(d_t, a_t + 8, d_blo + 16, 1u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bars[2 * grp + stage]))
+                         : "memory");
+        }
+        __syncwarp();
+        // ---- consume the previous round while this one is in the tensor core ----
+        if (pending) consume(pending_take, stage ^ 1);
+        pending = true;
+        pending_take = take;
+        stage ^= 1;
+        if (!any_more) break;
+    }
+    consume(pending_take, stage ^ 1);
+
+    if (live) {
+        const size_t row = (size_t)b * M + qloc;
+        if (cnt > K) {  // the cap binds: leave this centroid to the exact redo launch
+            if (lane == 0) ovf[1 + atomicAdd(ovf, 1)] = b * M + j;
+        } else {
+#pragma unroll
+            for (int o = 0; o < C; ++o) {
+                const float m = warp_max(mx[o]) + W.l2.b[o];  // bias of the (sign-adjusted) second layer, once per centroid
+                const float sc = W.l2.s[o], a = sc < 0.f ? -m : m;
+                mx[o] = cnt > 0 ? fmaf(fmaxf(a, 0.f), sc, W.l2.t[o]) : 0.f;
+            }
+            if (lane == 0) {
+                float4 *o4 = reinterpret_cast<float4 *>(out + row * C);
+#pragma unroll
+                for (int v = 0; v < C / 4; ++v) o4[v] = make_float4(mx[4 * v], mx[4 * v + 1], mx[4 * v + 2], mx[4 * v + 3]);
+                if (cnt_out) cnt_out[row] = cnt;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(s_tmem), "r"(L::COLS));
 }
 
 __global__ void zero_int_kernel(int *p) { *p = 0; }
@@ -494,14 +620,16 @@ static int launch_sa_fused(const float *grid_hdr, const int *cell_start, const f
         tc = 0;
     }
     if constexpr (LEVEL == 1) {
-        if (tc && !exact_only) {  // second layer on the tensor cores (tcgen05): 1 = 3xTF32, 2 = plain TF32
-            auto kern = tc == 1 ? sa_fused_kernel<1, false, 0, 1> : sa_fused_kernel<1, false, 0, 2>;
-            const size_t smem_tc = smem_ring + TC_SMEM;
-            SN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc), "sa_fused_tc attr");
-            kern<<<grid, SF_WARPS * 32, smem_tc, st>>>(grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4),
-                                                       reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, 0, w,
-                                                       out, cnt_out, ovf);
-            SN2_LAUNCH_CHECK("sa_fused_kernel<tc>");
+        if (tc && !exact_only) {  // second layer on the tensor cores (tcgen05): 1 = 3xTF32, 2 = TF32, 3 = BF16-precision operands
+            auto launch = [&](auto kern) {
+                kern<<<grid, SF_WARPS * 32, 0, st>>>(grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4),
+                                                     reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, ws, out, cnt_out,
+                                                     ovf);
+            };
+            if (tc == 1) launch(sa1_tc_kernel<1>);
+            else if (tc == 2) launch(sa1_tc_kernel<2>);
+            else launch(sa1_tc_kernel<3>);
+            SN2_LAUNCH_CHECK("sa1_tc_kernel");
         }
     }
     if (!(LEVEL == 1 && tc) && !exact_only) {
@@ -553,7 +681,7 @@ extern "C" int sn2_sa_fused_fwd(int level, const float *grid_hdr, const int *cel
     cudaStream_t st = (cudaStream_t)stream;
     if (level == 1)
         return sn2::launch_sa_fused<1>(grid_hdr, cell_start, sorted4, qsorted4, pos4, feat, u_scratch, ovf_scratch, B, N, M,
-                                       r2, K, w_host, nw, out, cnt_out, tensor_core == 2 ? 2 : (tensor_core ? 1 : 0), st);
+                                       r2, K, w_host, nw, out, cnt_out, (tensor_core >= 1 && tensor_core <= 3) ? tensor_core : 0, st);
     if (level == 2)
         return sn2::launch_sa_fused<2>(grid_hdr, cell_start, sorted4, qsorted4, pos4, feat, u_scratch, ovf_scratch, B, N, M,
                                        r2, K, w_host, nw, out, cnt_out, 0, st);

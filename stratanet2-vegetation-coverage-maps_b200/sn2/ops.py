@@ -66,6 +66,7 @@ def ingest(xyz: torch.Tensor, cloud: torch.Tensor):
 
 
 FPS_AUTO, FPS_BRUTE, FPS_BUCKETED, FPS_BUCKETED_SPEC4, FPS_CLUSTER4 = 0, 1, 2, 3, 4
+FPS_BUCKETED_ILP2, FPS_BUCKETED_NW16, FPS_BUCKETED_NW16_ILP2 = 5, 6, 7
 
 
 def fps_dense(pos4: torch.Tensor, B: int, N: int, M: int, start: torch.Tensor | None = None, algo: int = FPS_AUTO):

@@ -443,8 +443,16 @@ def test_sa_fused_equals_list_path(cuda_device, N, K, variant):
     assert torch.equal(cnt_tc, cnt)
     torch.testing.assert_close(x1_tc, x1_list, rtol=1e-4, atol=1e-5)
     # plain TF32 operands (what torch 1.8 + cuBLAS did on the reference's Ampere GPUs): stated looser bound
-    x1_tf32 = ops.sa_fused_fwd(1, pos0, feat0, pos1, B, N, M1, r1, K, W["sa1"], tensor_core=2)
+    x1_tf32, cnt_tf32 = ops.sa_fused_fwd(1, pos0, feat0, pos1, B, N, M1, r1, K, W["sa1"], want_counts=True, tensor_core=2)
+    assert torch.equal(cnt_tf32, cnt)
     torch.testing.assert_close(x1_tf32, x1_list, rtol=1e-2, atol=5e-3)
+    # BF16-precision operands (BASELINE config 5's "bf16 shared MLP"): 8 mantissa bits on both operands of the 16-term dot
+    # product -> stated bound: 2^-8 relative per operand, rtol 3e-2 / atol 2e-2 on the post-BatchNorm output
+    x1_bf16 = ops.sa_fused_fwd(1, pos0, feat0, pos1, B, N, M1, r1, K, W["sa1"], tensor_core=3)
+    torch.testing.assert_close(x1_bf16, x1_list, rtol=3e-2, atol=2e-2)
+    err = {m: float((x - x1_list).abs().max()) for m, x in (("3xtf32", x1_tc), ("tf32", x1_tf32), ("bf16", x1_bf16))}
+    print("SA1 tensor-core max abs error vs fp32 list path:", err)
+    assert err["3xtf32"] <= err["tf32"] <= err["bf16"] or err["bf16"] < 1e-3
     M2 = ops.m_of(M1, 0.25)
     _, pos2 = ops.fps_dense(pos1, B, M1, M2)
     rowptr2, col2 = ops.ball_query_dense(pos1, pos2, B, M1, M2, r2, K)

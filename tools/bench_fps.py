@@ -14,13 +14,13 @@ def t(fn, n=5):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n
 
-for B, N in ((64, 16384), (32, 16384), (16, 16384), (32, 10000), (1, 10000), (8, 8192), (64, 4096)):
+for B, N in ((64, 16384), (32, 10000), (1, 10000), (8, 8192), (64, 4096)):
     data = synth_batch(2, B, N)
     dev = torch.device("cuda")
     pos0, _ = ops.ingest(data["xyz"].to(dev), data["cloud"].to(dev))
     M = ops.m_of(N, 0.25)
     ref = None
-    for name, algo in (("brute", 1), ("bucket", 2), ("cluster4", 4)):
+    for name, algo in (("brute", 1), ("bucket", 2), ("ilp2", 5), ("nw16", 6), ("nw16+ilp2", 7)):
         ms = t(lambda: ops.fps_dense(pos0, B, N, M, None, algo))
         idx, _ = ops.fps_dense(pos0, B, N, M, None, algo)
         same = True if ref is None else bool(torch.equal(idx, ref))

@@ -25,7 +25,9 @@ M1 = ops.m_of(N, 0.25)
 _, pos1 = ops.fps_dense(pos0, B, N, M1)
 r = float(np.sqrt(2.0))
 print("grid build x2 :", t(lambda: (ops.build_grid(pos0, B, N, r), ops.build_grid(pos1, B, M1, r))))
-print("sa1 fused full:", t(lambda: ops.sa_fused_fwd(1, pos0, feat0, pos1, B, N, M1, r, 2000, W["sa1"])))
+grid0 = ops.build_grid(pos0, B, N, r)
+for name, tc in (("SIMT fp32", 0), ("tcgen05 3xTF32", 1), ("tcgen05 TF32", 2), ("tcgen05 BF16-precision", 3)):
+    print(f"sa1 fused, {name:24s}:", t(lambda: ops.sa_fused_fwd(1, pos0, feat0, pos1, B, N, M1, r, 2000, W["sa1"], tensor_core=tc, grid=grid0)))
 hdr, cs, sorted4 = ops.build_grid(pos0, B, N, r)
 _, _, qsorted4 = ops.build_grid(pos1, B, M1, r)
 lib = ctypes.CDLL(_lib.LIB_PATH)
