@@ -24,6 +24,7 @@
 // Results agree with the list path (sn2_ball_* + sn2_pointconv_fwd) to fp32 rounding (different
 // association of the first layer), and exactly in which edges participate, including when K binds.
 #include "mlp_common.cuh"
+#include <stdlib.h>
 
 namespace sn2 {
 
@@ -372,20 +373,27 @@ __device__ __forceinline__ float tc_operand(float x)
     return x;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(SF_WARPS * 32, MODE == 1 ? 2 : 3)
+// REDO = false: grid (M / 8, B), one centroid per warp (the streaming launch).  REDO = true: persistent launch over the
+// overflow list (centroids whose hit count exceeds the cap K): hits -> bitmap over the plot's point indices -> the first
+// K set bits in ascending index order (Appendix A2), exactly as the SIMT redo kernel, feeding the same rounds; a warp
+// walks through its items back to back (the last batch of item A is consumed in the round that stores the first batch
+// of item B, then A is finalised and the running max starts over).
+template <int MODE, bool REDO, int MINB = 2>
+__global__ void __launch_bounds__(SF_WARPS * 32, REDO ? 1 : MINB)
 sa1_tc_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
-              const float4 *__restrict__ qsorted, const float *__restrict__ u, int N, int M, float r2, int K,
+              const float4 *__restrict__ qsorted, const float *__restrict__ u, int N, int M, float r2, int K, int words,
               const __grid_constant__ W_SA1 W, float *__restrict__ out, int *__restrict__ cnt_out, int *__restrict__ ovf)
 {
     using L = TcLayout<MODE>;
     constexpr int C = SN2_C1, UNR = 4;
+    extern __shared__ __align__(16) unsigned char tc_dyn[];  // REDO: hit bitmaps [SF_WARPS][words]
     __shared__ int ring_all[SF_WARPS * TC_RING];
     __shared__ __align__(1024) float b_tiles[2 * 256];      // W2^T hi | lo, canonical K-major no-swizzle layout
     __shared__ __align__(8) unsigned long long bars[2 * 2];  // [group][stage]
     __shared__ unsigned s_tmem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = warp >> 2, rq = warp & 3;
     int *ring = ring_all + warp * TC_RING;
+    unsigned *bm = reinterpret_cast<unsigned *>(tc_dyn) + (size_t)warp * words;
     const unsigned lt = (1u << lane) - 1u;
 
     if (warp == 0) {
@@ -411,28 +419,31 @@ sa1_tc_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell_s
     const unsigned long long d_bhi = umma_desc(smem_u32(b_tiles)), d_blo = umma_desc(smem_u32(b_tiles + 256));
     unsigned parity = 0;  // bit s: phase parity of this group's stage-s mbarrier
 
-    // ---- this warp's centroid (a warp past the last centroid still takes part in its group's rounds, with no edges) ----
-    const int b = blockIdx.y, j = blockIdx.x * SF_WARPS + warp;
-    const bool live = j < M;
-    const float *hdr = grid_hdr + (size_t)b * SN2_GRID_HDR;
-    const int *cs = cell_start + (size_t)b * (SN2_GRID_CELLS + 1);
-    const float4 *so = sorted + (size_t)b * N;
-    const float4 q = live ? __ldg(qsorted + (size_t)b * M + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const int qloc = __float_as_int(q.w);
-    const float *ub = u + (size_t)b * N * C;
-    const float ox = hdr[0], oy = hdr[1], inv = hdr[2], oz = hdr[6], invz = hdr[7];
-    const int gx = __float_as_int(hdr[4]), gy = __float_as_int(hdr[5]), gz = __float_as_int(hdr[8]);
-    const int ix = cell_coord_c(q.x, ox, inv, gx), iy = cell_coord_c(q.y, oy, inv, gy), iz = cell_coord_c(q.z, oz, invz, gz);
-    const int x0 = max(ix - 1, 0), x1 = min(ix + 1, gx - 1), y0 = max(iy - 1, 0), y1 = min(iy + 1, gy - 1);
-    const int z0 = max(iz - 1, 0), z1 = min(iz + 1, gz - 1);
-    const int ny = y1 - y0 + 1, nrows = live ? ny * (z1 - z0 + 1) : 0;
-    auto row_of = [&](int t) { return ((z0 + t / ny) * gy + (y0 + t % ny)) * gx; };
+    // ---- work items of this warp ----
+    long long item = REDO ? (long long)blockIdx.x * SF_WARPS + warp : 0;
+    const long long item_step = REDO ? (long long)gridDim.x * SF_WARPS : 1;
+    const long long n_items = REDO ? (long long)ovf[0] : ((int)(blockIdx.x * SF_WARPS + warp) < M ? 1 : 0);
+
+    // current item
+    bool have = false, more = false, open_row = false;
+    int b = 0, j = 0, qloc = 0, x0 = 0, x1 = 0, y0 = 0, z0 = 0, ny = 1, nrows = 0, gx = 1, gy = 1;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int *cs = cell_start;
+    const float4 *so = sorted;
+    const float *ub = u;
+    int cnt = 0, head = 0, tail = 0, y = 0, base = 0, e = 0;
+    int emitted = 0, wblk = 0;
+    unsigned wmask = 0u, wword = 0u;
     float c[C], mx[C];
 #pragma unroll
-    for (int o = 0; o < C; ++o) {
-        c[o] = W.l1.b[o] - (W.l1.w[SN2_F0][o] * q.x + W.l1.w[SN2_F0 + 1][o] * q.y + W.l1.w[SN2_F0 + 2][o] * q.z);
-        mx[o] = -INFINITY;
-    }
+    for (int o = 0; o < C; ++o) { c[o] = 0.f; mx[o] = -INFINITY; }
+    auto row_of = [&](int t) { return ((z0 + t / ny) * gy + (y0 + t % ny)) * gx; };
+
+    // batch in flight (stored last round, consumed this round)
+    bool pending = false, p_last = false;
+    int p_take = 0, p_cnt = 0, p_code = 0;
+    long long p_row = 0;
+    int stage = 0;
 
     auto consume = [&](const int take, const int st) {
         unsigned done = 0;
@@ -454,46 +465,135 @@ sa1_tc_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell_s
             for (int o = 0; o < C; ++o) mx[o] = fmaxf(mx[o], __uint_as_float(d[o]));  // raw (sign-adjusted) pre-activation, bias later
         }
     };
+    // the item whose last batch has just been consumed: bias / ReLU / BatchNorm once, write the row, start the max over
+    auto finalize = [&]() {
+        if (!REDO && p_cnt > K) {  // the cap binds: leave this centroid to the exact redo launch
+            if (lane == 0) ovf[1 + atomicAdd(ovf, 1)] = p_code;
+        } else {
+            float r[C];
+#pragma unroll
+            for (int o = 0; o < C; ++o) {
+                const float m = warp_max(mx[o]) + W.l2.b[o];  // bias of the (sign-adjusted) second layer, once per centroid
+                const float sc = W.l2.s[o], a = sc < 0.f ? -m : m;
+                r[o] = p_cnt > 0 ? fmaf(fmaxf(a, 0.f), sc, W.l2.t[o]) : 0.f;
+            }
+            if (lane == 0) {
+                float4 *o4 = reinterpret_cast<float4 *>(out + p_row * C);
+#pragma unroll
+                for (int v = 0; v < C / 4; ++v) o4[v] = make_float4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+                if (cnt_out) cnt_out[p_row] = p_cnt;
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < C; ++o) mx[o] = -INFINITY;
+    };
 
-    int cnt = 0, head = 0, tail = 0, y = 0, base = 0, e = 0;
-    bool open_row = false, more = live;
-    int stage = 0, pending_take = 0;
-    bool pending = false;
     while (true) {
-        // ---- produce: up to 32 edges of this warp's centroid ----
-        while (more && tail - head < 32) {
-            if (!open_row) {
-                if (y >= nrows) { more = false; break; }
-                base = __ldg(cs + row_of(y) + x0);
-                e = __ldg(cs + row_of(y) + x1 + 1);
-                open_row = true;
+        // ---- next item of this warp ----
+        if (!have && item < n_items) {
+            if (REDO) {
+                const int code = ovf[1 + item];
+                b = code / M;
+                j = code - b * M;
+            } else {
+                b = blockIdx.y;
+                j = blockIdx.x * SF_WARPS + warp;
             }
-            float4 vv[UNR];
+            item += item_step;
+            const float *hdr = grid_hdr + (size_t)b * SN2_GRID_HDR;
+            cs = cell_start + (size_t)b * (SN2_GRID_CELLS + 1);
+            so = sorted + (size_t)b * N;
+            q = __ldg(qsorted + (size_t)b * M + j);
+            qloc = __float_as_int(q.w);
+            ub = u + (size_t)b * N * C;
+            const float ox = hdr[0], oy = hdr[1], inv = hdr[2], oz = hdr[6], invz = hdr[7];
+            gx = __float_as_int(hdr[4]);
+            gy = __float_as_int(hdr[5]);
+            const int gz = __float_as_int(hdr[8]);
+            const int ix = cell_coord_c(q.x, ox, inv, gx), iy = cell_coord_c(q.y, oy, inv, gy), iz = cell_coord_c(q.z, oz, invz, gz);
+            x0 = max(ix - 1, 0); x1 = min(ix + 1, gx - 1);
+            y0 = max(iy - 1, 0);
+            const int y1 = min(iy + 1, gy - 1);
+            z0 = max(iz - 1, 0);
+            const int z1 = min(iz + 1, gz - 1);
+            ny = y1 - y0 + 1;
+            nrows = ny * (z1 - z0 + 1);
 #pragma unroll
-            for (int t = 0; t < UNR; ++t) {
-                const int i = base + t * 32 + lane;
-                vv[t] = i < e ? __ldg(so + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int t = 0; t < UNR; ++t) {
-                if (base + t * 32 < e) {
-                    const float4 v = vv[t];
-                    const bool hit = (base + t * 32 + lane < e) && dist2(v.x, v.y, v.z, q.x, q.y, q.z) < r2;
-                    const unsigned bal = __ballot_sync(SN2_FULL, hit);
-                    if (hit) ring[(tail + __popc(bal & lt)) & (TC_RING - 1)] = __float_as_int(v.w);
-                    tail += __popc(bal);
+            for (int o = 0; o < C; ++o)
+                c[o] = W.l1.b[o] - (W.l1.w[SN2_F0][o] * q.x + W.l1.w[SN2_F0 + 1][o] * q.y + W.l1.w[SN2_F0 + 2][o] * q.z);
+            have = true; more = true; open_row = false;
+            cnt = 0; head = 0; tail = 0; y = 0; emitted = 0; wblk = 0; wmask = 0u;
+            if (REDO) {  // hit set as a bitmap over the plot's point indices
+                for (int w = lane; w < words; w += 32) bm[w] = 0u;
+                __syncwarp();
+                for (int t = 0; t < nrows; ++t) {
+                    const int s2 = __ldg(cs + row_of(t) + x0), e2 = __ldg(cs + row_of(t) + x1 + 1);
+                    for (int i = s2 + lane; i < e2; i += 32) {
+                        const float4 v = __ldg(so + i);
+                        if (dist2(v.x, v.y, v.z, q.x, q.y, q.z) < r2) {
+                            const int id = __float_as_int(v.w);
+                            atomicOr(&bm[id >> 5], 1u << (id & 31));
+                        }
+                    }
                 }
+                __syncwarp();
             }
-            base += 32 * UNR;
-            if (base >= e) { open_row = false; ++y; }
+        }
+        // ---- produce: up to 32 edges of the current item ----
+        while (have && more && tail - head < 32) {
+            if (!REDO) {
+                if (!open_row) {
+                    if (y >= nrows) { more = false; break; }
+                    base = __ldg(cs + row_of(y) + x0);
+                    e = __ldg(cs + row_of(y) + x1 + 1);
+                    open_row = true;
+                }
+                float4 vv[UNR];
+#pragma unroll
+                for (int t = 0; t < UNR; ++t) {
+                    const int i = base + t * 32 + lane;
+                    vv[t] = i < e ? __ldg(so + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int t = 0; t < UNR; ++t) {
+                    if (base + t * 32 < e) {
+                        const float4 v = vv[t];
+                        const bool hit = (base + t * 32 + lane < e) && dist2(v.x, v.y, v.z, q.x, q.y, q.z) < r2;
+                        const unsigned bal = __ballot_sync(SN2_FULL, hit);
+                        if (hit) ring[(tail + __popc(bal & lt)) & (TC_RING - 1)] = __float_as_int(v.w);
+                        tail += __popc(bal);
+                    }
+                }
+                base += 32 * UNR;
+                if (base >= e) { open_row = false; ++y; }
+            } else {
+                // first K set bits of the hit bitmap in ascending point index (same walk as the SIMT redo kernel)
+                if (!wmask) {
+                    if (emitted >= K || wblk >= words) { more = false; break; }
+                    wword = wblk + lane < words ? bm[wblk + lane] : 0u;
+                    wmask = __ballot_sync(SN2_FULL, wword != 0u);
+                    if (!wmask) { wblk += 32; continue; }
+                }
+                const int wl = __ffs(wmask) - 1;
+                wmask &= wmask - 1;
+                const unsigned bits = __shfl_sync(SN2_FULL, wword, wl);
+                const int rk = __popc(bits & lt);
+                if (((bits >> lane) & 1u) && emitted + rk < K) ring[(tail + rk) & (TC_RING - 1)] = ((wblk + wl) << 5) + lane;
+                const int n = min(__popc(bits), K - emitted);
+                tail += n;
+                emitted += n;
+                if (!wmask) wblk += 32;
+                if (emitted >= K) more = false;
+            }
             __syncwarp();
         }
-        const int avail = tail - head, take = min(avail, 32);
+        const int avail = tail - head, take = have ? min(avail, 32) : 0;
         const int id = take > 0 ? ring[(head + lane) & (TC_RING - 1)] : 0;
         head += take;
         cnt += take;
         __syncwarp();
-        const bool more_after = more || (tail - head > 0);
+        const bool last = have && !more && tail == head;              // this batch ends the current item
+        const bool more_after = (have && !last) || item < n_items;
         // ---- layer 1 of my edge -> my row of the A tile, straight into tensor memory ----
         float h1[C];
 #pragma unroll
@@ -549,32 +649,25 @@ sa1_tc_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell_s
         }
         __syncwarp();
         // ---- consume the previous round while this one is in the tensor core ----
-        if (pending) consume(pending_take, stage ^ 1);
+        if (pending) {
+            consume(p_take, stage ^ 1);
+            if (p_last) finalize();
+        }
         pending = true;
-        pending_take = take;
+        p_take = take;
+        p_last = last;
+        if (last) {
+            p_cnt = cnt;
+            p_code = b * M + j;
+            p_row = (long long)b * M + qloc;
+            have = false;
+        }
         stage ^= 1;
         if (!any_more) break;
     }
-    consume(pending_take, stage ^ 1);
-
-    if (live) {
-        const size_t row = (size_t)b * M + qloc;
-        if (cnt > K) {  // the cap binds: leave this centroid to the exact redo launch
-            if (lane == 0) ovf[1 + atomicAdd(ovf, 1)] = b * M + j;
-        } else {
-#pragma unroll
-            for (int o = 0; o < C; ++o) {
-                const float m = warp_max(mx[o]) + W.l2.b[o];  // bias of the (sign-adjusted) second layer, once per centroid
-                const float sc = W.l2.s[o], a = sc < 0.f ? -m : m;
-                mx[o] = cnt > 0 ? fmaf(fmaxf(a, 0.f), sc, W.l2.t[o]) : 0.f;
-            }
-            if (lane == 0) {
-                float4 *o4 = reinterpret_cast<float4 *>(out + row * C);
-#pragma unroll
-                for (int v = 0; v < C / 4; ++v) o4[v] = make_float4(mx[4 * v], mx[4 * v + 1], mx[4 * v + 2], mx[4 * v + 3]);
-                if (cnt_out) cnt_out[row] = cnt;
-            }
-        }
+    if (pending) {
+        consume(p_take, stage ^ 1);
+        if (p_last) finalize();
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n");
     __syncthreads();
@@ -615,24 +708,36 @@ static int launch_sa_fused(const float *grid_hdr, const int *cell_start, const f
     const size_t smem_ring = (size_t)SF_WARPS * 256 * sizeof(int);
     dim3 grid((M + SF_WARPS - 1) / SF_WARPS, B);
     const bool exact_only = K < 256 && K < N;
-    if (exact_only) {
-        all_overflow_kernel<<<(B * M + 255) / 256, 256, 0, st>>>(ovf, B * M);
-        tc = 0;
-    }
+    if (exact_only) all_overflow_kernel<<<(B * M + 255) / 256, 256, 0, st>>>(ovf, B * M);
+    const size_t smem_bm = (size_t)SF_WARPS * words * sizeof(unsigned);
     if constexpr (LEVEL == 1) {
-        if (tc && !exact_only) {  // second layer on the tensor cores (tcgen05): 1 = 3xTF32, 2 = TF32, 3 = BF16-precision operands
-            auto launch = [&](auto kern) {
-                kern<<<grid, SF_WARPS * 32, 0, st>>>(grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4),
-                                                     reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, ws, out, cnt_out,
-                                                     ovf);
+        if (tc) {  // second layer on the tensor cores (tcgen05): 1 = 3xTF32, 2 = TF32, 3 = BF16-precision operands
+            if (K < N && smem_bm + 12 * 1024 > 200 * 1024) return SN2_EUNSUPPORTED;
+            auto run = [&](auto stream_kern, auto redo_kern) -> int {
+                if (!exact_only) {
+                    stream_kern<<<grid, SF_WARPS * 32, 0, st>>>(grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4),
+                                                                reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, 0, ws, out,
+                                                                cnt_out, ovf);
+                    SN2_LAUNCH_CHECK("sa1_tc_kernel");
+                }
+                if (K < N) {  // the cap can bind: exact redo of the overflow list on the same tensor-core path
+                    SN2_CUDA_TRY(cudaFuncSetAttribute(redo_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bm), "sa1_tc redo attr");
+                    redo_kern<<<148, SF_WARPS * 32, smem_bm, st>>>(grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4),
+                                                                   reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, words, ws,
+                                                                   out, cnt_out, ovf);
+                    SN2_LAUNCH_CHECK("sa1_tc_kernel<redo>");
+                }
+                return SN2_OK;
             };
-            if (tc == 1) launch(sa1_tc_kernel<1>);
-            else if (tc == 2) launch(sa1_tc_kernel<2>);
-            else launch(sa1_tc_kernel<3>);
-            SN2_LAUNCH_CHECK("sa1_tc_kernel");
+            // CTAs per SM of the streaming launch: 2 (<= 128 registers, no spills; default) or 3 (80 registers, TF32 / BF16 modes
+            // only: their 128 TMEM columns allow it) -- a tuning switch, read once
+            static const int minb = [] { const char *e = getenv("SN2_TC_MINB"); return e && atoi(e) == 3 ? 3 : 2; }();
+            if (tc == 1) return run(sa1_tc_kernel<1, false, 2>, sa1_tc_kernel<1, true>);
+            if (tc == 2) return minb == 3 ? run(sa1_tc_kernel<2, false, 3>, sa1_tc_kernel<2, true>) : run(sa1_tc_kernel<2, false, 2>, sa1_tc_kernel<2, true>);
+            return minb == 3 ? run(sa1_tc_kernel<3, false, 3>, sa1_tc_kernel<3, true>) : run(sa1_tc_kernel<3, false, 2>, sa1_tc_kernel<3, true>);
         }
     }
-    if (!(LEVEL == 1 && tc) && !exact_only) {
+    if (!exact_only) {
         auto kern = sa_fused_kernel<LEVEL, false>;
         kern<<<grid, SF_WARPS * 32, smem_ring, st>>>(grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4),
                                                      reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, 0, ws,
@@ -640,7 +745,7 @@ static int launch_sa_fused(const float *grid_hdr, const int *cell_start, const f
         SN2_LAUNCH_CHECK("sa_fused_kernel");
     }
     if (K < N) {  // the cap can bind: exact redo of the overflow list (exits at once when the list is empty)
-        const size_t smem = smem_ring + (size_t)SF_WARPS * words * sizeof(unsigned);
+        const size_t smem = smem_ring + smem_bm;
         if (smem > 200 * 1024) return SN2_EUNSUPPORTED;
         auto kern = sa_fused_kernel<LEVEL, true>;
         SN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sa_fused attr");
