@@ -1444,3 +1444,51 @@ def test_batched_evaluation_and_pseudo_labelling(cuda_device):
         cov, _ = net({"xyz": data["xyz"][5:6], "cloud": data["cloud"][5:6]})
         want = project_to_plotwise_coverages(cov, data["cloud"][5:6], args).cpu().numpy()[0]
     assert np.array_equal(labelled["PP00000005"]["coverages"], want)
+
+
+def test_graphed_step_follows_lr_scheduler_without_recapture(cuda_device):
+    """The reference steps StepLR(step_size=1, gamma=0.985) after every epoch (learning/train.py:180-185, 111-113).  With
+    FusedAdam the learning rate is a device scalar, so ONE captured graph follows the schedule: parameters after 6 steps
+    (3 'epochs' of 2 steps) equal the eager loop's; with torch.optim.Adam the rate is baked in and recapture() is needed."""
+    import copy
+
+    from model.project_to_2d import project_to_plotwise_coverages
+    from sn2.optim import FusedAdam
+    from sn2.pipeline import GraphedTrainStep
+
+    N = 2048
+    args, net, _ = _make_models(N, cuda_device)
+    net.train()
+    twin = copy.deepcopy(net)
+    batch = _plots(4, 3, N)
+    batch["gt"] = torch.rand(3, 4, generator=torch.Generator().manual_seed(2))
+
+    def make(model):
+        opt = FusedAdam(model.parameters(), lr=1e-2, weight_decay=1e-3)
+        sch = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=0.5)
+
+        def step(b):
+            opt.zero_grad()
+            cov, proba = model(b)
+            pw = project_to_plotwise_coverages(cov, model.last_cloud_device, args)
+            loss = ((pw - b["gt"].to(pw.device)) ** 2).mean() + 0.01 * (proba ** 2).mean()
+            loss.backward()
+            opt.step()
+            return loss.detach()
+        return opt, sch, step
+
+    opt_e, sch_e, step_e = make(net)
+    opt_g, sch_g, step_g = make(twin)
+    gstep = GraphedTrainStep(twin, step_g, opt_g)
+    for epoch in range(3):
+        for _ in range(2):
+            step_e(batch)
+            gstep(batch)
+        sch_e.step()
+        sch_g.step()
+    assert gstep.captures == 1 and abs(float(opt_g.lr_dev) - 1e-2 * 0.25) < 1e-9   # the rate used by the last two steps
+    assert int(opt_g.step_dev) == int(opt_e.step_dev) == 6
+    for (k, v), (_, v2) in zip(net.state_dict().items(), twin.state_dict().items()):
+        if v.is_floating_point():
+            diff = (v2 - v).abs()
+            assert float((diff > 2e-3 + 2e-3 * v.abs()).float().mean()) < 5e-3, k
