@@ -316,11 +316,20 @@ extract_plots_kernel(ExtractArgs a)
                     const int jy = cy0 + jr;
                     const int rs = __ldg(a.cell_start + jy * g.nx + max(ix - 1, cx0)), re = __ldg(a.cell_start + jy * g.nx + min(ix + 1, cx1) + 1);
                     const int bit_r = row_bit0[jr] + (rs - row_start[jr]);
-                    for (int kk = rs; kk < re; ++kk) {
-                        const int bb = bit_r + (kk - rs);
-                        if (!((inbits[bb >> 5] >> (bb & 31)) & 1u)) continue;                 // not in this plot (uniform branch)
-                        const float4 q = __ldg(a.sorted4 + kk);                                // uniform address: broadcast
-                        if (mine && q.z < m && within_f64(p.x, p.y, q.x, q.y, zr2f, zr2)) m = q.z;
+                    // 32 candidates per step: one coalesced float4 load per lane, then the in-disk ones are handed round by
+                    // shuffle (a per-candidate broadcast load was latency bound: the 196 KB of shared memory leave ~30 KB of L1)
+                    for (int kb = rs; kb < re; kb += 32) {
+                        const int kk = kb + lane, bb = bit_r + (kk - rs);
+                        const bool cin = kk < re && ((inbits[bb >> 5] >> (bb & 31)) & 1u);
+                        float4 q = make_float4(0.f, 0.f, INFINITY, 0.f);
+                        if (cin) q = __ldg(a.sorted4 + kk);
+                        unsigned cm = __ballot_sync(SN2_FULL, cin);
+                        while (cm) {  // warp-uniform
+                            const int t = __ffs(cm) - 1;
+                            cm &= cm - 1;
+                            const float qx = __shfl_sync(SN2_FULL, q.x, t), qy = __shfl_sync(SN2_FULL, q.y, t), qz = __shfl_sync(SN2_FULL, q.z, t);
+                            if (mine && qz < m && within_f64(p.x, p.y, qx, qy, zr2f, zr2)) m = qz;
+                        }
                     }
                 }
                 if (mine) {  // position of this point in the plot's ascending index list

@@ -382,7 +382,7 @@ template <int MODE, bool REDO, int MINB = 2>
 __global__ void __launch_bounds__(SF_WARPS * 32, REDO ? 1 : MINB)
 sa1_tc_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
               const float4 *__restrict__ qsorted, const float *__restrict__ u, int N, int M, float r2, int K, int words,
-              const __grid_constant__ W_SA1 W, float *__restrict__ out, int *__restrict__ cnt_out, int *__restrict__ ovf)
+              const __grid_constant__ W_SA1 W, float *__restrict__ out, int *__restrict__ cnt_out, int *__restrict__ ovf, int B)
 {
     using L = TcLayout<MODE>;
     constexpr int C = SN2_C1, UNR = 4;
@@ -420,9 +420,19 @@ sa1_tc_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell_s
     unsigned parity = 0;  // bit s: phase parity of this group's stage-s mbarrier
 
     // ---- work items of this warp ----
+    // REDO: entries of the overflow list, strided over all warps of the grid.  Streaming: the CTA owns a contiguous chunk of
+    // the (plot, cell-ordered centroid) sequence and its warps pull the next centroid from a shared counter, so a warp that
+    // finishes a small neighbourhood (median 15 edges, p90 260) keeps feeding rows into its group's rounds instead of idling
+    // until the largest neighbourhood of the group is done.
+    __shared__ int s_next;
+    const long long total = (long long)B * M;
+    const long long chunk = (total + gridDim.x - 1) / gridDim.x;
+    const long long q_end = REDO ? 0 : min(total, (long long)(blockIdx.x + 1) * chunk);
+    if (!REDO && threadIdx.x == 0) s_next = (int)min(total, (long long)blockIdx.x * chunk);
     long long item = REDO ? (long long)blockIdx.x * SF_WARPS + warp : 0;
-    const long long item_step = REDO ? (long long)gridDim.x * SF_WARPS : 1;
-    const long long n_items = REDO ? (long long)ovf[0] : ((int)(blockIdx.x * SF_WARPS + warp) < M ? 1 : 0);
+    const long long item_step = REDO ? (long long)gridDim.x * SF_WARPS : 0;
+    const long long n_items = REDO ? (long long)ovf[0] : 0;
+    __syncthreads();
 
     // current item
     bool have = false, more = false, open_row = false;
@@ -490,16 +500,21 @@ sa1_tc_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell_s
 
     while (true) {
         // ---- next item of this warp ----
-        if (!have && item < n_items) {
+        long long code_next = -1;
+        if (!have) {
             if (REDO) {
-                const int code = ovf[1 + item];
-                b = code / M;
-                j = code - b * M;
-            } else {
-                b = blockIdx.y;
-                j = blockIdx.x * SF_WARPS + warp;
+                if (item < n_items) code_next = ovf[1 + item];
+                item += item_step;
+            } else if (*reinterpret_cast<volatile int *>(&s_next) < q_end) {
+                int t = 0;
+                if (lane == 0) t = atomicAdd(&s_next, 1);
+                t = __shfl_sync(SN2_FULL, t, 0);
+                if (t < q_end) code_next = t;
             }
-            item += item_step;
+        }
+        if (code_next >= 0) {
+            b = (int)(code_next / M);
+            j = (int)(code_next - (long long)b * M);
             const float *hdr = grid_hdr + (size_t)b * SN2_GRID_HDR;
             cs = cell_start + (size_t)b * (SN2_GRID_CELLS + 1);
             so = sorted + (size_t)b * N;
@@ -593,7 +608,7 @@ sa1_tc_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell_s
         cnt += take;
         __syncwarp();
         const bool last = have && !more && tail == head;              // this batch ends the current item
-        const bool more_after = (have && !last) || item < n_items;
+        const bool more_after = (have && !last) || (REDO ? item < n_items : *reinterpret_cast<volatile int *>(&s_next) < q_end);
         // ---- layer 1 of my edge -> my row of the A tile, straight into tensor memory ----
         float h1[C];
 #pragma unroll
@@ -715,16 +730,18 @@ static int launch_sa_fused(const float *grid_hdr, const int *cell_start, const f
             if (K < N && smem_bm + 12 * 1024 > 200 * 1024) return SN2_EUNSUPPORTED;
             auto run = [&](auto stream_kern, auto redo_kern) -> int {
                 if (!exact_only) {
-                    stream_kern<<<grid, SF_WARPS * 32, 0, st>>>(grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4),
-                                                                reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, 0, ws, out,
-                                                                cnt_out, ovf);
+                    const long long ncta = ((long long)B * M + SF_WARPS * 4 - 1) / (SF_WARPS * 4);  // >= 4 centroids per warp
+                    const unsigned qgrid = (unsigned)min(ncta, (long long)148 * 8);  // 1-D work queue over all (plot, centroid) pairs
+                    stream_kern<<<qgrid, SF_WARPS * 32, 0, st>>>(grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4),
+                                                                 reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, 0, ws, out,
+                                                                 cnt_out, ovf, B);
                     SN2_LAUNCH_CHECK("sa1_tc_kernel");
                 }
                 if (K < N) {  // the cap can bind: exact redo of the overflow list on the same tensor-core path
                     SN2_CUDA_TRY(cudaFuncSetAttribute(redo_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bm), "sa1_tc redo attr");
                     redo_kern<<<148, SF_WARPS * 32, smem_bm, st>>>(grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4),
                                                                    reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, words, ws,
-                                                                   out, cnt_out, ovf);
+                                                                   out, cnt_out, ovf, B);
                     SN2_LAUNCH_CHECK("sa1_tc_kernel<redo>");
                 }
                 return SN2_OK;
