@@ -1488,7 +1488,10 @@ def test_graphed_step_follows_lr_scheduler_without_recapture(cuda_device):
         sch_g.step()
     assert gstep.captures == 1 and abs(float(opt_g.lr_dev) - 1e-2 * 0.25) < 1e-9   # the rate used by the last two steps
     assert int(opt_g.step_dev) == int(opt_e.step_dev) == 6
+    # Adam's normalised update turns the ~1e-7 atomics noise of near-zero gradients into O(lr) differences on a handful of
+    # weights; the rates add up to 3.5e-2 over the six steps, a baked-in rate would add up to 6e-2
     for (k, v), (_, v2) in zip(net.state_dict().items(), twin.state_dict().items()):
         if v.is_floating_point():
             diff = (v2 - v).abs()
-            assert float((diff > 2e-3 + 2e-3 * v.abs()).float().mean()) < 5e-3, k
+            assert float((diff > 7e-3 + 2e-3 * v.abs()).float().mean()) < 2e-2, k
+            assert float(diff.mean()) < 2e-3, (k, float(diff.mean()))
