@@ -19,7 +19,7 @@ net.sa1_module.max_num_neighbors = K
 net.sn2_tensor_core = tc
 data = {k: v.to(dev) for k, v in synth_batch(5 if K < 2000 else 2, B, N).items()}
 with torch.no_grad():
-    for _ in range(2):
+    for _ in range(1 if os.environ.get("SN2_NCU_ONE") == "1" else 2):
         cov, proba, g, cloud_d = forward_eval(net, data["xyz"], data["cloud"], dev, K)
         ops.project_plotwise(cloud_d, cov, args.diam_pix)
         ops.project_rasters(cloud_d, cov, "point_major", args.diam_pix, args.diam_meters)

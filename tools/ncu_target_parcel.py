@@ -14,7 +14,7 @@ side = float(sys.argv[1])
 dev = torch.device("cuda", 0)
 args, net = bench.make_model(10000, 0)
 cloud = bench.synthetic_parcel(dev, side=side)
-for _ in range(2):
+for _ in range(1 if os.environ.get("SN2_NCU_ONE") == "1" else 2):
     parcel = ParcelCloud(cloud, dev)
     centers = plot_centers_reference(parcel.x_min, parcel.x_max, parcel.y_min, parcel.y_max, args)
     ex = extract_plots(parcel, centers, args)
