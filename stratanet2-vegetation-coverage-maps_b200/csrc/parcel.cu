@@ -323,7 +323,10 @@ extract_plots_kernel(ExtractArgs a)
                         const bool cin = kk < re && ((inbits[bb >> 5] >> (bb & 31)) & 1u);
                         float4 q = make_float4(0.f, 0.f, INFINITY, 0.f);
                         if (cin) q = __ldg(a.sorted4 + kk);
-                        unsigned cm = __ballot_sync(SN2_FULL, cin);
+                        // a candidate can only lower somebody's minimum if it lies below the LARGEST current minimum of the
+                        // warp's points: once every lane has met a ground return most candidates drop out here
+                        const float mtop = warp_max(mine ? m : -INFINITY);
+                        unsigned cm = __ballot_sync(SN2_FULL, cin && q.z < mtop);
                         while (cm) {  // warp-uniform
                             const int t = __ffs(cm) - 1;
                             cm &= cm - 1;
@@ -499,12 +502,24 @@ hardveg_threshold_kernel(const unsigned *__restrict__ hist, const double *__rest
     __shared__ double best_d[32];
     __shared__ int best_i[32];
     const int tid = threadIdx.x;
-    if (tid == 0) {
-        unsigned acc = 0;
-        suffix[HV_BINS] = 0;
-        for (int k = HV_BINS; k >= 1; --k) {  // suffix[i] = sum_{k > i} hist[k], i in [0, HV_BINS)
-            acc += hist[k];
-            suffix[k - 1] = acc;
+    {   // suffix[i] = sum_{k > i} hist[k], i in [0, HV_BINS): per-thread chunks of 10, block scan of the chunk totals
+        constexpr int CH = (HV_BINS + 1 + 1023) / 1024;
+        __shared__ unsigned tot[1024];
+        const int k0 = tid * CH;
+        unsigned mine = 0;
+        for (int k = k0; k < min(k0 + CH, HV_BINS + 1); ++k) mine += hist[k];
+        tot[tid] = mine;
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1) {  // inclusive suffix scan of tot (sum over threads >= tid)
+            const unsigned v = tid + d < 1024 ? tot[tid + d] : 0u;
+            __syncthreads();
+            tot[tid] += v;
+            __syncthreads();
+        }
+        unsigned acc = tid + 1 < 1024 ? tot[tid + 1] : 0u;  // everything in later chunks
+        for (int k = min(k0 + CH, HV_BINS + 1) - 1; k >= k0; --k) {
+            acc += hist[k];                    // acc = sum_{k' >= k} hist[k']
+            if (k >= 1) suffix[k - 1] = acc;
         }
     }
     __syncthreads();
