@@ -57,7 +57,8 @@ const char *sn2_last_cuda_error(void);
 
 /* ---- a0-a2: input layout.  Replaces get_long_form + column drop (model/point_net2.py:107-118,
  * 155-158).  xyz (B,3,N), cloud (B,F,N) fp32 -> pos4 [B*N] float4, feat [B*N, F-2] row-major.
- * F must be 10 (n_input_feats, config.py:101). */
+ * F must be 10 (n_input_feats, config.py:101).  Either input (with its output) may be NULL: positions and features
+ * can be ingested by separate launches, so that FPS starts as soon as xyz has arrived while cloud is still in flight. */
 int sn2_ingest(const float *xyz, const float *cloud, int B, int N, int F, float *pos4, float *feat,
                void *stream);
 

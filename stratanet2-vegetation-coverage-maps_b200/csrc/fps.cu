@@ -21,8 +21,11 @@ __global__ void ingest_kernel(const float *__restrict__ xyz, const float *__rest
     if (i >= total) return;
     int b = (int)(i / N);
     int n = (int)(i - (long long)b * N);
-    const float *px = xyz + (size_t)b * 3 * N + n;
-    pos4[i] = make_float4(__ldg(px), __ldg(px + N), __ldg(px + 2 * (size_t)N), 0.f);
+    if (xyz) {  // positions and features may be ingested by separate launches (the positions' copy lands first)
+        const float *px = xyz + (size_t)b * 3 * N + n;
+        pos4[i] = make_float4(__ldg(px), __ldg(px + N), __ldg(px + 2 * (size_t)N), 0.f);
+    }
+    if (!cloud) return;
     const float *pc = cloud + (size_t)b * F * N + n;
     float v[SN2_F0];
 #pragma unroll
@@ -672,8 +675,8 @@ extern "C" int sn2_fps_max_points(void) { return 65536; }
 extern "C" int sn2_ingest(const float *xyz, const float *cloud, int B, int N, int F, float *pos4, float *feat,
                           void *stream)
 {
-    if (!xyz || !cloud || !pos4 || !feat || B <= 0 || N <= 0) return SN2_EINVAL;
-    if (F != SN2_F0 + 2) return SN2_EUNSUPPORTED;
+    if ((!xyz && !cloud) || (xyz && !pos4) || (cloud && !feat) || B <= 0 || N <= 0) return SN2_EINVAL;
+    if (cloud && F != SN2_F0 + 2) return SN2_EUNSUPPORTED;
     long long total = (long long)B * N;
     int threads = 256;
     long long blocks = (total + threads - 1) / threads;

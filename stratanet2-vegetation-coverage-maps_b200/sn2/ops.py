@@ -65,6 +65,26 @@ def ingest(xyz: torch.Tensor, cloud: torch.Tensor):
     return pos4, feat
 
 
+def ingest_pos(xyz: torch.Tensor):
+    """(B,3,N) device fp32 -> pos4 (B*N,4): the half of `ingest` that FPS / the grids need."""
+    lib = _lib.load()
+    B, _, N = xyz.shape
+    pos4 = torch.empty((B * N, 4), dtype=torch.float32, device=xyz.device)
+    check(lib.sn2_ingest(dptr(xyz, torch.float32), None, B, N, 0, dptr(pos4), None, stream_ptr()), "sn2_ingest")
+    _count(1)
+    return pos4
+
+
+def ingest_feat(cloud: torch.Tensor):
+    """(B,10,N) device fp32 -> feat (B*N,8) (x, y dropped)."""
+    lib = _lib.load()
+    B, F, N = cloud.shape
+    feat = torch.empty((B * N, F - 2), dtype=torch.float32, device=cloud.device)
+    check(lib.sn2_ingest(None, dptr(cloud, torch.float32), B, N, F, None, dptr(feat), stream_ptr()), "sn2_ingest")
+    _count(1)
+    return feat
+
+
 FPS_AUTO, FPS_BRUTE, FPS_BUCKETED, FPS_BUCKETED_SPEC4, FPS_CLUSTER4 = 0, 1, 2, 3, 4
 FPS_BUCKETED_ILP2, FPS_BUCKETED_NW16, FPS_BUCKETED_NW16_ILP2 = 5, 6, 7
 

@@ -140,16 +140,35 @@ def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_
     M2 = ops.m_of(M1, sa2.ratio)
     if head is not main:
         fork(head)
+    # The head of the dependency chain needs the POSITIONS only (12 B / point): xyz is copied and ingested first, FPS level 1
+    # starts, and the 3.3x larger `cloud` copy + its ingest run on side stream B underneath it (ordered after the xyz copy
+    # so that the two host-to-device copies do not share the link).
+    split = os.environ.get("SN2_SPLIT_INGEST", "1") == "1"
     with torch.cuda.stream(head):
         xyz_d = xyz.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
-        cloud_d = cloud.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
-        with T.stage("ingest"):
-            pos0, feat0 = ops.ingest(xyz_d, cloud_d)
+        xyz_here = torch.cuda.Event()
+        xyz_here.record(head)
+        if split:
+            with T.stage("ingest"):
+                pos0 = ops.ingest_pos(xyz_d)
+        else:
+            cloud_d = cloud.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+            with T.stage("ingest"):
+                pos0, feat0 = ops.ingest(xyz_d, cloud_d)
         grid0 = ops.build_grid(pos0, B, N, sa1.r)  # cell order of the raw points: SA1's search grid AND knn1's query order
         with T.stage("fps1"):
             idx1, pos1 = ops.fps_dense(pos0, B, N, M1)
+    if split:
+        with torch.cuda.stream(side_b):
+            side_b.wait_event(xyz_here)  # after the xyz copy (and, through it, after everything queued on main before this call)
+            cloud_d = cloud.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+            with T.stage("ingest_feat"):
+                feat0 = ops.ingest_feat(cloud_d)
+            feat_here = torch.cuda.Event()
+            feat_here.record(side_b)
+        keep.extend((cloud_d, feat0))
     if head is not main:
-        join(head, xyz_d, cloud_d, pos0, feat0, idx1, pos1, *grid0)
+        join(head, xyz_d, pos0, idx1, pos1, *grid0)
     # The plot-level dependency graph (reference :131-139) has three independent branches after fps1:
     # sa1 (needs all SMs), fps2 -> knn2 (a 64-CTA latency chain, then a small search) and knn1.
     # They run on separate streams so the serial FPS chain of level 2 hides under the SA1 kernel.
@@ -163,6 +182,8 @@ def forward_eval(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_
     with torch.cuda.stream(side_b):
         with T.stage("knn1"):
             nbr1, w1 = ops.knn3_dense(pos1, pos0, B, M1, N, qsorted4=grid0[2])
+    if split:  # SA1 (and everything after it on main) needs the features, produced on side stream B before knn1
+        main.wait_event(feat_here)
     rowptr1 = col1 = rowptr2 = col2 = None
     if trace is not None:  # neighbour lists only materialised for parity tests / backward
         rowptr1, col1 = ops.ball_query_dense(pos0, pos1, B, N, M1, sa1.r, max_num_neighbors)
