@@ -602,11 +602,26 @@ def run_parcel(opts, cfg):
         ms_e2e = timed(mine_host, True, reps)
         clocks = sampler.stop()
         last = one_pass(mine, False)
-    t = torch.tensor([ms_res, ms_e2e], dtype=torch.float64, device=dev)
+    # the one collective of the pass, timed on its own: NCCL all-reduce of the [7,H,W] float64 fusion accumulators
+    ar_ms = None
+    if world > 1:
+        acc = torch.zeros((7, info["H"], info["W"]), dtype=torch.float64, device=dev)
+        for _ in range(3):
+            dist.all_reduce(acc)
+        barrier()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for _ in range(10):
+            dist.all_reduce(acc)
+        eb.record()
+        torch.cuda.synchronize()
+        ar_ms = ea.elapsed_time(eb) / 10
+    t = torch.tensor([ms_res, ms_e2e, ar_ms or 0.0], dtype=torch.float64, device=dev)
     nvalid = torch.tensor([info["plots_valid"]], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(nvalid)
+        ar_ms = float(t[2])
     ms_res, ms_e2e = float(t[0]), float(t[1])
     covered = float((~torch.isnan(last[4])).float().mean())
     out = {
@@ -618,7 +633,8 @@ def run_parcel(opts, cfg):
                    "mosaic": [5, info["H"], info["W"]], "mosaic_covered_fraction": covered,
                    "hard_medium_vegetation_threshold": float(info["threshold"]),
                    "l2": "inputs larger than L2 (a 1.4 GB cloud; ~100 distinct 33 MB plot batches per pass)",
-                   "parallelism": f"plot centres in contiguous blocks (x stripes) x{world}, one all-reduce of the [7,{info['H']},{info['W']}] f64 accumulators"},
+                   "parallelism": f"plot centres in contiguous blocks (x stripes) x{world}, one all-reduce of the [7,{info['H']},{info['W']}] f64 accumulators",
+                   "allreduce_ms": ar_ms, "allreduce_bytes": int(7 * info["H"] * info["W"] * 8)},
         "points_per_s": Ptot / (ms_res / 1e3),
         "e2e": {"value": C / (ms_e2e / 1e3), "unit": "plots/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(mine_host.numel() * 4), "d2h_bytes_per_step": int(5 * info["H"] * info["W"] * 8),
