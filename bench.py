@@ -889,11 +889,11 @@ def run_infer(opts, cfg, cpu_baseline=True):
     }
     hbm_peak, peak_src = peaks()
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic_cfg2.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_ncu_traffic_cfg2.json")
     if opts.config == 2 and os.path.exists(tpath):
         tj = json.load(open(tpath))
-        traffic = {"fps1": tj.get("fps_bucket_kernel<8, 32, 0, 1, 1>"), "fps2": tj.get("fps_kernel<512, 8, 1>"),
-                   "fp1_head": tj.get("fp1_head_kernel")}.get(dom)
+        traffic = {"fps1": tj.get("fps_bucket_kernel<8, 32, 0, 1, 1, 2>"), "fps2": tj.get("fps_kernel<512, 8, 1>"),
+                   "sa1_fused": tj.get("sa_fused_kernel<1, 0, 0>"), "fp1_head": tj.get("fp1_head_kernel")}.get(dom)
     roof = None
     if dom in alg_bytes:
         ach = alg_bytes[dom] * B / (per_step[dom] / 1e3) / 1e9
