@@ -100,6 +100,9 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int *ring = reinterpret_cast<int *>(sf_smem) + warp * RING;
     unsigned *bm = reinterpret_cast<unsigned *>(sf_smem + SF_WARPS * RING * sizeof(int)) + (size_t)warp * words;  // REDO only
+    // streaming only: per-warp table of the <= 9 candidate rows of the current centroid: [k] = inclusive prefix of the row
+    // lengths (flat candidate index space), [16 + k] = offset from a flat index inside row k to its position in `sorted`
+    int *rtab = reinterpret_cast<int *>(sf_smem + SF_WARPS * RING * sizeof(int)) + warp * 32;
     const unsigned lt = (1u << lane) - 1u;
 
     // work items: streaming = one (plot, cell-ordered query) per warp; redo = entries of the overflow list
@@ -197,38 +200,63 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
         // ---- producer / consumer loop with ONE call site of the message MLP (keeps the loop in I-cache) ----
         int cnt = 0;
         int head = 0, tail = 0;          // warp-uniform ring cursors
-        int y = 0, base = 0, e = 0;      // streaming iterator: current (layer, cell row) and candidate range
-        bool open_row = false;
+        // streaming iterator over the FLATTENED candidate space: the rows of a 3 x 3 x 3 cell block are short (18 candidates
+        // on average, six of nine nearly empty), so walking them one by one left the 32-lane tests 44 % full and paid two
+        // dependent cell_start loads, an integer division and ~100 instructions of loop control per row (ncu source page:
+        // 37 % of the kernel's instructions).  Here lanes 0..8 fetch their row's range in parallel once, a prefix sum
+        // turns the rows into one index space, and every 32-lane step maps flat index -> (row, position) with a
+        // 9-entry table in shared memory.
+        int f0 = 0, ftotal = 0;
+        if (!REDO) {
+            int rs_ = 0, len_ = 0;
+            if (lane < nrows) {
+                const int rb = row_of(lane);
+                rs_ = __ldg(cs + rb + x0);
+                len_ = __ldg(cs + rb + x1 + 1) - rs_;
+            }
+            int pre_ = len_;
+#pragma unroll
+            for (int d = 1; d < 16; d <<= 1) {
+                const int t_ = __shfl_up_sync(SN2_FULL, pre_, d);
+                if (lane >= d) pre_ += t_;
+            }
+            if (lane < 16) {
+                rtab[lane] = pre_;                 // lanes >= nrows: the total (their rows are empty)
+                rtab[16 + lane] = rs_ - (pre_ - len_);
+            }
+            ftotal = __shfl_sync(SN2_FULL, pre_, 15);
+            __syncwarp();
+        }
         int emitted = 0, wblk = 0;       // redo iterator: set bits emitted so far, next 32-word block of the bitmap
         unsigned wmask = 0u, wword = 0u; //   non-empty words left in the current block, this lane's word of the block
         bool more = true;
         while (true) {
             while (more && tail - head < 32) {
                 if (!REDO) {
-                    if (!open_row) {
-                        if (y >= nrows) { more = false; break; }
-                        base = __ldg(cs + row_of(y) + x0);
-                        e = __ldg(cs + row_of(y) + x1 + 1);
-                        open_row = true;
-                    }
+                    if (f0 >= ftotal) { more = false; break; }
                     float4 vv[UNR];
 #pragma unroll
                     for (int t = 0; t < UNR; ++t) {
-                        const int i = base + t * 32 + lane;
-                        vv[t] = i < e ? __ldg(so + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int f = f0 + t * 32 + lane;
+                        vv[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (f < ftotal) {
+                            int r = 0;
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) r += rtab[k] <= f;   // rows 0..8: r = number of rows that end at or before f
+                            vv[t] = __ldg(so + f + rtab[16 + r]);
+                        }
                     }
 #pragma unroll
                     for (int t = 0; t < UNR; ++t) {
-                        if (base + t * 32 < e) {  // warp-uniform: short runs (3-D cells) cost one sub-batch, not UNR
+                        if (f0 + t * 32 < ftotal) {  // warp-uniform
                             const float4 v = vv[t];
-                            const bool hit = (base + t * 32 + lane < e) && dist2(v.x, v.y, v.z, q.x, q.y, q.z) < r2;
+                            const bool hit = (f0 + t * 32 + lane < ftotal) && dist2(v.x, v.y, v.z, q.x, q.y, q.z) < r2;
                             const unsigned bal = __ballot_sync(SN2_FULL, hit);
                             if (hit) ring[(tail + __popc(bal & lt)) & (RING - 1)] = __float_as_int(v.w);
                             tail += __popc(bal);
                         }
                     }
-                    base += 32 * UNR;
-                    if (base >= e) { open_row = false; ++y; }
+                    f0 += 32 * UNR;
                 } else {
                     // first K set bits of the hit bitmap in ascending point index: 32-word blocks, empty words
                     // skipped by ballot, one word (<= 32 ids) per step, every lane places its own bit by popc rank
@@ -721,6 +749,7 @@ static int launch_sa_fused(const float *grid_hdr, const int *cell_start, const f
     SN2_LAUNCH_CHECK("sa_pre_kernel");
     const int words = (N + 31) / 32;
     const size_t smem_ring = (size_t)SF_WARPS * 256 * sizeof(int);
+    const size_t smem_stream = smem_ring + (size_t)SF_WARPS * 32 * sizeof(int);  // + the per-warp row tables
     dim3 grid((M + SF_WARPS - 1) / SF_WARPS, B);
     const bool exact_only = K < 256 && K < N;
     if (exact_only) all_overflow_kernel<<<(B * M + 255) / 256, 256, 0, st>>>(ovf, B * M);
@@ -756,9 +785,9 @@ static int launch_sa_fused(const float *grid_hdr, const int *cell_start, const f
     }
     if (!exact_only) {
         auto kern = sa_fused_kernel<LEVEL, false>;
-        kern<<<grid, SF_WARPS * 32, smem_ring, st>>>(grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4),
-                                                     reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, 0, ws,
-                                                     out, cnt_out, ovf);
+        kern<<<grid, SF_WARPS * 32, smem_stream, st>>>(grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4),
+                                                       reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, 0, ws,
+                                                       out, cnt_out, ovf);
         SN2_LAUNCH_CHECK("sa_fused_kernel");
     }
     if (K < N) {  // the cap can bind: exact redo of the overflow list (exits at once when the list is empty)
@@ -785,7 +814,7 @@ extern "C" int sn2_debug_sa_search_only(const float *grid_hdr, const int *cell_s
     W_SA1 w;
     if (int rc = load_weights(w, w_host, nw)) return rc;
     dim3 grid((M + SF_WARPS - 1) / SF_WARPS, B);
-    sa_fused_kernel<1, false, 1><<<grid, SF_WARPS * 32, SF_WARPS * 256 * sizeof(int), (cudaStream_t)stream>>>(
+    sa_fused_kernel<1, false, 1><<<grid, SF_WARPS * 32, SF_WARPS * (256 + 32) * sizeof(int), (cudaStream_t)stream>>>(
         grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4), reinterpret_cast<const float4 *>(qsorted4), u, N, M,
         r2, K, 0, w, out, cnt_out, ovf);
     SN2_LAUNCH_CHECK("sa_fused_kernel<dbg>");
