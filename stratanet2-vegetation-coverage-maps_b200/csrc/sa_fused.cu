@@ -416,11 +416,13 @@ sa1_tc_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell_s
     constexpr int C = SN2_C1, UNR = 4;
     extern __shared__ __align__(16) unsigned char tc_dyn[];  // REDO: hit bitmaps [SF_WARPS][words]
     __shared__ int ring_all[SF_WARPS * TC_RING];
+    __shared__ int rtab_all[SF_WARPS * 32];                 // per warp: flattened candidate rows (see sa_fused_kernel)
     __shared__ __align__(1024) float b_tiles[2 * 256];      // W2^T hi | lo, canonical K-major no-swizzle layout
     __shared__ __align__(8) unsigned long long bars[2 * 2];  // [group][stage]
     __shared__ unsigned s_tmem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = warp >> 2, rq = warp & 3;
     int *ring = ring_all + warp * TC_RING;
+    int *rtab = rtab_all + warp * 32;
     unsigned *bm = reinterpret_cast<unsigned *>(tc_dyn) + (size_t)warp * words;
     const unsigned lt = (1u << lane) - 1u;
 
@@ -463,13 +465,13 @@ sa1_tc_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell_s
     __syncthreads();
 
     // current item
-    bool have = false, more = false, open_row = false;
+    bool have = false, more = false;
     int b = 0, j = 0, qloc = 0, x0 = 0, x1 = 0, y0 = 0, z0 = 0, ny = 1, nrows = 0, gx = 1, gy = 1;
     float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
     const int *cs = cell_start;
     const float4 *so = sorted;
     const float *ub = u;
-    int cnt = 0, head = 0, tail = 0, y = 0, base = 0, e = 0;
+    int cnt = 0, head = 0, tail = 0, f0 = 0, ftotal = 0;
     int emitted = 0, wblk = 0;
     unsigned wmask = 0u, wword = 0u;
     float c[C], mx[C];
@@ -564,8 +566,29 @@ sa1_tc_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell_s
 #pragma unroll
             for (int o = 0; o < C; ++o)
                 c[o] = W.l1.b[o] - (W.l1.w[SN2_F0][o] * q.x + W.l1.w[SN2_F0 + 1][o] * q.y + W.l1.w[SN2_F0 + 2][o] * q.z);
-            have = true; more = true; open_row = false;
-            cnt = 0; head = 0; tail = 0; y = 0; emitted = 0; wblk = 0; wmask = 0u;
+            have = true; more = true;
+            cnt = 0; head = 0; tail = 0; f0 = 0; emitted = 0; wblk = 0; wmask = 0u;
+            if (!REDO) {  // rows of the 3 x 3 x 3 block -> one flat candidate index space
+                int rs_ = 0, len_ = 0;
+                if (lane < nrows) {
+                    const int rb = row_of(lane);
+                    rs_ = __ldg(cs + rb + x0);
+                    len_ = __ldg(cs + rb + x1 + 1) - rs_;
+                }
+                int pre_ = len_;
+#pragma unroll
+                for (int d = 1; d < 16; d <<= 1) {
+                    const int t_ = __shfl_up_sync(SN2_FULL, pre_, d);
+                    if (lane >= d) pre_ += t_;
+                }
+                __syncwarp();
+                if (lane < 16) {
+                    rtab[lane] = pre_;
+                    rtab[16 + lane] = rs_ - (pre_ - len_);
+                }
+                ftotal = __shfl_sync(SN2_FULL, pre_, 15);
+                __syncwarp();
+            }
             if (REDO) {  // hit set as a bitmap over the plot's point indices
                 for (int w = lane; w < words; w += 32) bm[w] = 0u;
                 __syncwarp();
@@ -585,30 +608,30 @@ sa1_tc_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell_s
         // ---- produce: up to 32 edges of the current item ----
         while (have && more && tail - head < 32) {
             if (!REDO) {
-                if (!open_row) {
-                    if (y >= nrows) { more = false; break; }
-                    base = __ldg(cs + row_of(y) + x0);
-                    e = __ldg(cs + row_of(y) + x1 + 1);
-                    open_row = true;
-                }
+                if (f0 >= ftotal) { more = false; break; }
                 float4 vv[UNR];
 #pragma unroll
                 for (int t = 0; t < UNR; ++t) {
-                    const int i = base + t * 32 + lane;
-                    vv[t] = i < e ? __ldg(so + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int f = f0 + t * 32 + lane;
+                    vv[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (f < ftotal) {
+                        int r = 0;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) r += rtab[k] <= f;
+                        vv[t] = __ldg(so + f + rtab[16 + r]);
+                    }
                 }
 #pragma unroll
                 for (int t = 0; t < UNR; ++t) {
-                    if (base + t * 32 < e) {
+                    if (f0 + t * 32 < ftotal) {
                         const float4 v = vv[t];
-                        const bool hit = (base + t * 32 + lane < e) && dist2(v.x, v.y, v.z, q.x, q.y, q.z) < r2;
+                        const bool hit = (f0 + t * 32 + lane < ftotal) && dist2(v.x, v.y, v.z, q.x, q.y, q.z) < r2;
                         const unsigned bal = __ballot_sync(SN2_FULL, hit);
                         if (hit) ring[(tail + __popc(bal & lt)) & (TC_RING - 1)] = __float_as_int(v.w);
                         tail += __popc(bal);
                     }
                 }
-                base += 32 * UNR;
-                if (base >= e) { open_row = false; ++y; }
+                f0 += 32 * UNR;
             } else {
                 // first K set bits of the hit bitmap in ascending point index (same walk as the SIMT redo kernel)
                 if (!wmask) {
