@@ -84,6 +84,30 @@ __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long da
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem_d), "l"(da),
                  "l"(db), "r"(UMMA_IDESC), "r"(acc), "r"(0), "r"(0), "r"(0), "r"(0));
 }
+// Packed fp32 FMA (Blackwell FFMA2): two IEEE fmas per issue slot, bit-identical to two FFMAs.  The level-1 kernel is
+// bound by instruction issue (ncu: issue active 79 %, FMA pipe 37 %), so its 16 x 16 second layer was tried as 128 FFMA2
+// with the weight pairs read from shared memory (64 LDS.128 per 32 edges) instead of 256 FFMA + 64 uniform constant
+// loads.  Measured SLOWER (SA1 at config 2: 1.13 ms vs 0.92 ms, results identical): FFMA2 takes register pairs only, and
+// the broadcast LDS.128 stream plus the pair moves cost more than the issue slots they free.  Kept as a compile-time
+// switch for re-measurement; the product build uses 0.
+#ifndef SN2_SA1_FFMA2
+#define SN2_SA1_FFMA2 0
+#endif
+typedef unsigned long long u64_t;
+__device__ __forceinline__ u64_t pack_f32x2(float a, float b)
+{
+    u64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ u64_t fma_f32x2(u64_t a, u64_t b, u64_t c)
+{
+    u64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(u64_t v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+
 template <int LEVEL, bool REDO, int DBG = 0>
 __global__ void __launch_bounds__(SF_WARPS * 32, REDO ? 1 : (LEVEL == 1 ? 3 : 2))
 sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell_start,
@@ -104,6 +128,13 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
     // lengths (flat candidate index space), [16 + k] = offset from a flat index inside row k to its position in `sorted`
     int *rtab = reinterpret_cast<int *>(sf_smem + SF_WARPS * RING * sizeof(int)) + warp * 32;
     const unsigned lt = (1u << lane) - 1u;
+    // level 1: second-layer weights [k][o] + bias as fp32 pairs for the packed FMA
+    __shared__ __align__(16) float s_w2[(LEVEL == 1 && SN2_SA1_FFMA2) ? SN2_C1 * SN2_C1 + SN2_C1 : 4];
+    if constexpr (LEVEL == 1 && SN2_SA1_FFMA2) {
+        for (int i = threadIdx.x; i < SN2_C1 * SN2_C1 + SN2_C1; i += SF_WARPS * 32)
+            s_w2[i] = i < SN2_C1 * SN2_C1 ? W.l2.w[i / SN2_C1][i % SN2_C1] : W.l2.b[i - SN2_C1 * SN2_C1];
+        __syncthreads();
+    }
 
     // work items: streaming = one (plot, cell-ordered query) per warp; redo = entries of the overflow list
     long long item = REDO ? (long long)blockIdx.x * SF_WARPS + warp : 0;
@@ -167,11 +198,37 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
                     h1[4 * g + 2] = t4.z + c[4 * g + 2];
                     h1[4 * g + 3] = t4.w + c[4 * g + 3];
                 }
-                relu_bn(W.l1, h1);
-                float h2[SN2_C1];
-                acc_init(W.l2, h2);
+                // layer 1's BatchNorm affine is folded into layer 2 by the launcher: W2' = diag(s1) W2, b2' = b2 + t1 W2
 #pragma unroll
-                for (int k = 0; k < SN2_C1; ++k) acc_step<0>(W.l2, h1[k], h2, k);
+                for (int k = 0; k < C; ++k) h1[k] = fmaxf(h1[k], 0.f);
+                float h2[SN2_C1];
+                if constexpr (SN2_SA1_FFMA2) {
+                    u64_t a2[SN2_C1 / 2];
+                    const ulonglong2 *bw = reinterpret_cast<const ulonglong2 *>(s_w2 + SN2_C1 * SN2_C1);
+#pragma unroll
+                    for (int g = 0; g < SN2_C1 / 4; ++g) {
+                        const ulonglong2 b2 = bw[g];
+                        a2[2 * g] = b2.x;
+                        a2[2 * g + 1] = b2.y;
+                    }
+#pragma unroll
+                    for (int k = 0; k < SN2_C1; ++k) {
+                        const u64_t hk = pack_f32x2(h1[k], h1[k]);
+                        const ulonglong2 *wr = reinterpret_cast<const ulonglong2 *>(s_w2 + SN2_C1 * k);
+#pragma unroll
+                        for (int g = 0; g < SN2_C1 / 4; ++g) {
+                            const ulonglong2 w2 = wr[g];
+                            a2[2 * g] = fma_f32x2(hk, w2.x, a2[2 * g]);
+                            a2[2 * g + 1] = fma_f32x2(hk, w2.y, a2[2 * g + 1]);
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < SN2_C1 / 2; ++g) unpack_f32x2(a2[g], h2[2 * g], h2[2 * g + 1]);
+                } else {
+                    acc_init(W.l2, h2);
+#pragma unroll
+                    for (int k = 0; k < SN2_C1; ++k) acc_step<0>(W.l2, h1[k], h2, k);
+                }
                 // No ReLU / BatchNorm per edge: f(a) = fma(max(a, 0), s, t) is monotone in the pre-activation a, so
                 // max_j f(a_j) = f(max_j a_j) for s >= 0 and f(min_j a_j) for s < 0.  The launcher negates the
                 // second-layer weights and bias of the s < 0 channels (fma is odd: the accumulators come out exactly
@@ -207,12 +264,30 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
         // turns the rows into one index space, and every 32-lane step maps flat index -> (row, position) with a
         // 9-entry table in shared memory.
         int f0 = 0, ftotal = 0;
+        int mypre = 0x7fffffff, myoff = 0;  // lane k < (non-empty rows): inclusive end of row k in flat space, flat -> `sorted` offset
         if (!REDO) {
             int rs_ = 0, len_ = 0;
             if (lane < nrows) {
-                const int rb = row_of(lane);
-                rs_ = __ldg(cs + rb + x0);
-                len_ = __ldg(cs + rb + x1 + 1) - rs_;
+                // Row (cy, cz) trimmed to the cells the search sphere can reach: lower bounds dy, dz on the distance from the
+                // centroid to the row's slab, chord half-width w = sqrt(r2 - dy^2 - dz^2) along x.  Conservative (margins
+                // cover the rounding of the cell arithmetic), so the hit set is unchanged; one lane per row, in parallel.
+                const int tz = lane / ny, ty = lane - tz * ny;
+                const int cy = y0 + ty, cz = z0 + tz;
+                const float csx = hdr[3], csz = hdr[9];
+                const float ey = 1e-4f * csx + 1e-6f * (fabsf(q.y) + fabsf(oy) + csx * gy);
+                const float ez = 1e-4f * csz + 1e-6f * (fabsf(q.z) + fabsf(oz) + csz * gz);
+                float dy = cy > iy ? (oy + cy * csx) - q.y : (cy < iy ? q.y - (oy + (cy + 1) * csx) : 0.f);
+                float dz = cz > iz ? (oz + cz * csz) - q.z : (cz < iz ? q.z - (oz + (cz + 1) * csz) : 0.f);
+                dy = fmaxf(dy - ey, 0.f);
+                dz = fmaxf(dz - ez, 0.f);
+                const float rem = r2 * 1.00001f - dy * dy - dz * dz;
+                if (rem > 0.f) {
+                    const float w = sqrtf(rem) * 1.00001f + 1e-4f * csx + 1e-6f * (fabsf(q.x) + fabsf(ox) + csx * gx);
+                    const int xa = max(x0, cell_coord_c(q.x - w, ox, inv, gx)), xb = min(x1, cell_coord_c(q.x + w, ox, inv, gx));
+                    const int rb = (cz * gy + cy) * gx;
+                    rs_ = __ldg(cs + rb + xa);
+                    len_ = __ldg(cs + rb + xb + 1) - rs_;
+                }
             }
             int pre_ = len_;
 #pragma unroll
@@ -220,11 +295,20 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
                 const int t_ = __shfl_up_sync(SN2_FULL, pre_, d);
                 if (lane >= d) pre_ += t_;
             }
-            if (lane < 16) {
-                rtab[lane] = pre_;                 // lanes >= nrows: the total (their rows are empty)
-                rtab[16 + lane] = rs_ - (pre_ - len_);
+            ftotal = __shfl_sync(SN2_FULL, pre_, 15);  // lanes >= nrows carry the total (their rows are empty)
+            // drop the empty rows: the ends of the remaining ones are strictly increasing, so a 32-candidate step can mark
+            // them as distinct bits (below)
+            const unsigned ne = __ballot_sync(SN2_FULL, len_ > 0);
+            if (len_ > 0) {
+                const int slot = __popc(ne & lt);
+                rtab[slot] = pre_;
+                rtab[16 + slot] = rs_ - (pre_ - len_);
             }
-            ftotal = __shfl_sync(SN2_FULL, pre_, 15);
+            __syncwarp();
+            if (lane < __popc(ne)) {
+                mypre = rtab[lane];
+                myoff = rtab[16 + lane];
+            }
             __syncwarp();
         }
         int emitted = 0, wblk = 0;       // redo iterator: set bits emitted so far, next 32-word block of the bitmap
@@ -237,14 +321,17 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
                     float4 vv[UNR];
 #pragma unroll
                     for (int t = 0; t < UNR; ++t) {
-                        const int f = f0 + t * 32 + lane;
+                        // flat index -> row: r = number of rows that end at or before f = (rows ended before this step) +
+                        // (row ends inside the step at or before this lane); lane k holds the end of row k
+                        const int fb = f0 + t * 32, f = fb + lane;
                         vv[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (f < ftotal) {
-                            int r = 0;
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) r += rtab[k] <= f;   // rows 0..8: r = number of rows that end at or before f
-                            vv[t] = __ldg(so + f + rtab[16 + r]);
-                        }
+                        if (fb >= ftotal) continue;  // warp-uniform
+                        const int pe = mypre - fb;
+                        const unsigned done = __ballot_sync(SN2_FULL, pe <= 0);
+                        const unsigned ends = __reduce_or_sync(SN2_FULL, (unsigned)(pe - 1) < 31u ? 1u << pe : 0u);
+                        const int r = __popc(done) + __popc(ends & ((2u << lane) - 1u));
+                        const int off = __shfl_sync(SN2_FULL, myoff, r);
+                        if (f < ftotal) vv[t] = __ldg(so + f + off);
                     }
 #pragma unroll
                     for (int t = 0; t < UNR; ++t) {
@@ -313,19 +400,45 @@ sa_fused_kernel(const float *__restrict__ grid_hdr, const int *__restrict__ cell
             continue;
         }
         if constexpr (LEVEL == 1) {
+            // max over the 32 lanes of all 16 channels by a transposing butterfly: every exchange halves the channels a
+            // lane still carries (8 + 4 + 2 + 1 + 1 shuffles instead of 16 x 5); lanes 2c and 2c + 1 end up with channel c
+            static_assert(C == 16, "butterfly below is written for 16 channels");
+            float v8[8], v4[4], v2[2];
+            {
+                const bool hi = lane & 16;
 #pragma unroll
-            for (int o = 0; o < C; ++o) mx[o] = cnt > 0 ? warp_max(mx[o]) : 0.f;
-            // the kernel tracks the (sign-adjusted) pre-activation: finish it here
-#pragma unroll
-            for (int o = 0; o < C; ++o) {
-                const float sc = W.l2.s[o], a = sc < 0.f ? -mx[o] : mx[o];
-                mx[o] = cnt > 0 ? fmaf(fmaxf(a, 0.f), sc, W.l2.t[o]) : 0.f;
+                for (int i = 0; i < 8; ++i) {
+                    const float snd = hi ? mx[i] : mx[i + 8], keep = hi ? mx[i + 8] : mx[i];
+                    v8[i] = fmaxf(keep, __shfl_xor_sync(SN2_FULL, snd, 16));
+                }
             }
-            if (lane == 0) {
-                float4 *o4 = reinterpret_cast<float4 *>(out + row * C);
+            {
+                const bool hi = lane & 8;
 #pragma unroll
-                for (int v = 0; v < C / 4; ++v) o4[v] = make_float4(mx[4 * v], mx[4 * v + 1], mx[4 * v + 2], mx[4 * v + 3]);
+                for (int i = 0; i < 4; ++i) {
+                    const float snd = hi ? v8[i] : v8[i + 4], keep = hi ? v8[i + 4] : v8[i];
+                    v4[i] = fmaxf(keep, __shfl_xor_sync(SN2_FULL, snd, 8));
+                }
             }
+            {
+                const bool hi = lane & 4;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float snd = hi ? v4[i] : v4[i + 2], keep = hi ? v4[i + 2] : v4[i];
+                    v2[i] = fmaxf(keep, __shfl_xor_sync(SN2_FULL, snd, 4));
+                }
+            }
+            float v1;
+            {
+                const bool hi = lane & 2;
+                const float snd = hi ? v2[0] : v2[1], keep = hi ? v2[1] : v2[0];
+                v1 = fmaxf(keep, __shfl_xor_sync(SN2_FULL, snd, 2));
+            }
+            v1 = fmaxf(v1, __shfl_xor_sync(SN2_FULL, v1, 1));
+            // the kernel tracks the (sign-adjusted) pre-activation: finish it here (lane pair = channel)
+            const int ch = lane >> 1;
+            const float sc = W.l2.s[ch], a = sc < 0.f ? -v1 : v1;
+            if (!(lane & 1)) out[row * C + ch] = cnt > 0 ? fmaf(fmaxf(a, 0.f), sc, W.l2.t[ch]) : 0.f;
         } else {
             // out = max_j f(u_j) = f(max u) if s >= 0 else f(min u): f is monotone in u (lane = channel)
             const float sc = W.l1.s[lane], sel = sc >= 0.f ? mx[0] : mn[0];
@@ -756,13 +869,23 @@ static int launch_sa_fused(const float *grid_hdr, const int *cell_start, const f
 {
     typename SAEdge<LEVEL>::W w;
     if (int rc = load_weights(w, w_host, nw)) return rc;
-    typename SAEdge<LEVEL>::W ws = w;  // SIMT kernels of level 1: second layer negated where the BatchNorm scale is negative
+    typename SAEdge<LEVEL>::W ws = w;  // kernels of level 1: second layer negated where the BatchNorm scale is negative
+    typename SAEdge<LEVEL>::W wf = w;  // SIMT kernel of level 1: additionally layer 1's BatchNorm affine folded into layer 2
     if constexpr (LEVEL == 1) {
         for (int o = 0; o < SN2_C1; ++o) {
             if (ws.l2.s[o] < 0.f) {
                 ws.l2.b[o] = -ws.l2.b[o];
                 for (int k = 0; k < SN2_C1; ++k) ws.l2.w[k][o] = -ws.l2.w[k][o];
             }
+        }
+        wf = ws;
+        for (int o = 0; o < SN2_C1; ++o) {
+            double bacc = ws.l2.b[o];
+            for (int k = 0; k < SN2_C1; ++k) {
+                bacc += (double)ws.l1.t[k] * (double)ws.l2.w[k][o];
+                wf.l2.w[k][o] = ws.l1.s[k] * ws.l2.w[k][o];
+            }
+            wf.l2.b[o] = (float)bacc;
         }
     }
     const long long P = (long long)B * N;
@@ -809,7 +932,7 @@ static int launch_sa_fused(const float *grid_hdr, const int *cell_start, const f
     if (!exact_only) {
         auto kern = sa_fused_kernel<LEVEL, false>;
         kern<<<grid, SF_WARPS * 32, smem_stream, st>>>(grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4),
-                                                       reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, 0, ws,
+                                                       reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, 0, wf,
                                                        out, cnt_out, ovf);
         SN2_LAUNCH_CHECK("sa_fused_kernel");
     }
@@ -820,7 +943,7 @@ static int launch_sa_fused(const float *grid_hdr, const int *cell_start, const f
         SN2_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sa_fused attr");
         kern<<<148 * 2, SF_WARPS * 32, smem, st>>>(grid_hdr, cell_start, reinterpret_cast<const float4 *>(sorted4),
                                                    reinterpret_cast<const float4 *>(qsorted4), u_scratch, N, M, r2, K, words,
-                                                   ws, out, cnt_out, ovf);
+                                                   wf, out, cnt_out, ovf);
         SN2_LAUNCH_CHECK("sa_fused_kernel<redo>");
     }
     return SN2_OK;
