@@ -282,6 +282,47 @@ int sn2_pointwise_loss_bwd(const float *proba, const double *pdf, const double *
 int sn2_kde_lut(const float *cloud, int B, int F, int N, float z_max, const double *X, const double *Y, int K, double *pdf,
                 void *stream);
 
+/* ---- train-mode SA1 block without materialised messages, csrc/train_sa.cu ------------------------------------------
+ * Replaces, under model.train(), model/point_net2.py:21-29 for sa1 (PointConv(local_nn = MLP([11,16,16])), aggr = max):
+ * the message MLP is RECOMPUTED from a per-point table in every sweep over the CSR neighbour lists (rowptr [M+1], col
+ * [>= E] global point indices, live edge count = rowptr[M]) instead of writing [E,11] / [E,16] / [E,16] arrays.  LIVE
+ * parameter tensors (device): W1 [16,11], b1 [16], W2 [16,16], b2 [16], gamma2 [16].  Statistics and backward sums are
+ * raw fp64 sums as in the lrb_* entry points; the caller runs sn2_bn_finalize[_sync] / sn2_bn_param_grad /
+ * sn2_bn_bwd_sync between the calls (SyncBatchNorm: same collectives as the materialising path).  queue: device int32
+ * scratch, the cursor of a sweep's work queue (reset by the call itself).
+ *   sn2_sa1t_pre      u [P,16] = W1[:, :8] feat + W1[:, 8:] pos
+ *   sn2_sa1t_stats1   stats1 [33] fp64 = {sum a1, sum a1^2, E}, a1 = relu(u[col] + b1 - W1p q)              -> ss1
+ *   sn2_sa1t_stats2   stats2 [33] of a2 = relu(W2 BN1(a1) + b2); key / arg [M,16]: arg-max edge of sign(gamma2) * a2
+ *                     (first edge on ties, -1 for an empty row)                                             -> ss2
+ *   sn2_sa1t_finish   x1 [M,16] = BN2(a2[arg]) (0 for an empty row), amax [M,16] = a2[arg]
+ *   sn2_sa1t_bwd_sums sums2 [32] fp64 = {sum dx1, sum dx1 * amax}
+ *   sn2_sa1t_bwd_w2   dW2 [16,16], db2 [16] and sums1 [32] fp64 (BatchNorm 1's raw backward sums); partial
+ *                     [sn2_sa1t_blocks(), sn2_sa1t_partials()] scratch
+ *   sn2_sa1t_bwd_in   du [P,16] (zeroed here, vector atomics) = sum over the edges of a point of dz1, dc [M,16] = row sums
+ *   sn2_sa1t_bwd_w1   dW1 [16,11], db1 [16] from du, dc (same scratch); the gradient of the point features, when needed,
+ *                     is du W1[:, :8] (a plain GEMM of the caller). */
+int sn2_sa1t_partials(void);
+int sn2_sa1t_blocks(void);
+int sn2_sa1t_pre(const float *feat, const float *pos4, long long P, const float *W1, float *u, void *stream);
+int sn2_sa1t_stats1(const float *u, const float *qpos4, const int *rowptr, const int *col, int M, const float *W1,
+                    const float *b1, double *stats1, int *queue, void *stream);
+int sn2_sa1t_stats2(const float *u, const float *qpos4, const int *rowptr, const int *col, int M, const float *W1,
+                    const float *b1, const float *W2, const float *b2, const float *ss1, const float *gamma2, double *stats2,
+                    float *key, int *arg, int *queue, void *stream);
+int sn2_sa1t_finish(const float *key, const int *arg, const float *gamma2, const float *ss2, int M, float *x1, float *amax,
+                    void *stream);
+int sn2_sa1t_bwd_sums(const float *dout, const float *amax, const int *arg, int M, double *sums2, void *stream);
+int sn2_sa1t_bwd_w2(const float *u, const float *qpos4, const int *rowptr, const int *col, int M, const float *W1,
+                    const float *b1, const float *W2, const float *b2, const float *gamma2, const float *ss1, const float *ss2,
+                    const double *stats2, const double *sums2, const float *dout, const int *arg, float *partial, float *dW2,
+                    float *db2, double *sums1, int *queue, void *stream);
+int sn2_sa1t_bwd_in(const float *u, const float *qpos4, const int *rowptr, const int *col, long long P, int M, const float *W1,
+                    const float *b1, const float *W2, const float *b2, const float *gamma2, const float *ss1, const float *ss2,
+                    const double *stats1, const double *stats2, const double *sums1, const double *sums2, const float *dout,
+                    const int *arg, float *du, float *dc, int *queue, void *stream);
+int sn2_sa1t_bwd_w1(const float *du, const float *dc, const float *feat, const float *pos4, const float *qpos4, long long P,
+                    int M, float *partial, float *dW1, float *db1, void *stream);
+
 /* ---- peer-memory collectives for data-parallel training, csrc/comm.cu ----------------------------
  * The reference has no distributed code; these stand where a DistributedDataParallel / SyncBatchNorm wrapper around
  * learning/train.py:52-66 would call NCCL.  One region per rank (the ONLY device memory this library allocates),

@@ -61,6 +61,16 @@ SIGNATURES = {
     "sn2_lrb_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp],
     "sn2_head_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp],
     "sn2_head_bwd_partials": [],
+    "sn2_sa1t_partials": [],
+    "sn2_sa1t_blocks": [],
+    "sn2_sa1t_pre": [_vp, _vp, _ll, _vp, _vp, _vp],
+    "sn2_sa1t_stats1": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp],
+    "sn2_sa1t_stats2": [_vp, _vp, _vp, _vp, _i] + [_vp] * 11,
+    "sn2_sa1t_finish": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "sn2_sa1t_bwd_sums": [_vp, _vp, _vp, _i, _vp, _vp],
+    "sn2_sa1t_bwd_w2": [_vp, _vp, _vp, _vp, _i] + [_vp] * 17,
+    "sn2_sa1t_bwd_in": [_vp, _vp, _vp, _vp, _ll, _i] + [_vp] * 17,
+    "sn2_sa1t_bwd_w1": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _vp, _vp, _vp, _vp],
     "sn2_head_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp],
     "sn2_pointwise_loss_fwd": [_vp, _vp, _ll, _vp, _vp, _vp],
     "sn2_pointwise_loss_bwd": [_vp, _vp, _vp, _ll, _vp, _vp],

@@ -286,6 +286,125 @@ class LinReluBN(torch.autograd.Function):
         return dx, dW, db, dgb[0], dgb[1], None, None, None, None
 
 
+def _bn_stats_to_ss(lib, bn, stats, gamma, beta, Co, st):
+    """Raw fp64 sums (+ count) -> ss = scale | shift | mean | invstd with running-stat update, as LinReluBN does it:
+    plain BatchNorm1d, SyncBatchNorm over the peer communicator (summed inside the kernel), or over NCCL."""
+    ss = torch.empty(4 * Co, dtype=torch.float32, device=stats.device)
+    track = bn.track_running_stats and bn.running_mean is not None
+    rm, rv = (dptr(bn.running_mean), dptr(bn.running_var)) if track else (None, None)
+    nbt = dptr(bn.num_batches_tracked, torch.int64) if track and bn.num_batches_tracked is not None else None
+    gp, btp = dptr(_c(gamma), torch.float32), dptr(_c(beta), torch.float32)
+    group = _sync_group(bn)
+    peer = _comm.get_comm(group) if group is not None else None
+    if peer is not None:
+        check(lib.sn2_bn_finalize_sync(peer.handle, dptr(stats), gp, btp, float(bn.eps), float(bn.momentum), rm, rv, nbt,
+                                       dptr(ss), Co, st), "sn2_bn_finalize_sync")
+    else:
+        if group is not None:
+            torch.distributed.all_reduce(stats, group=group)
+        check(lib.sn2_bn_finalize(dptr(stats), gp, btp, float(bn.eps), float(bn.momentum), rm, rv, nbt, dptr(ss), Co, st),
+              "sn2_bn_finalize")
+    return ss, group, peer
+
+
+def _bn_bwd_sums(lib, sums, ss, Co, group, peer, st):
+    """This rank's raw backward sums -> (dgamma, dbeta); afterwards `sums` holds the sums over all ranks."""
+    dgb = torch.empty((2, Co), dtype=torch.float32, device=sums.device)
+    dgp, dbp = ctypes.c_void_p(dgb.data_ptr()), ctypes.c_void_p(dgb.data_ptr() + 4 * Co)
+    if peer is not None:
+        check(lib.sn2_bn_bwd_sync(peer.handle, dptr(sums), dptr(ss), Co, dgp, dbp, st), "sn2_bn_bwd_sync")
+    else:
+        check(lib.sn2_bn_param_grad(dptr(sums), dptr(ss), Co, dgp, dbp, st), "sn2_bn_param_grad")
+        if group is not None:
+            torch.distributed.all_reduce(sums, group=group)
+    return dgb[0], dgb[1]
+
+
+class SA1Recompute(torch.autograd.Function):
+    """The whole train-mode sa1 block -- PointConv message, MLP([11,16,16]) = 2 x (Linear -> ReLU -> BatchNorm1d with
+    batch statistics), max aggregation (reference model/point_net2.py:21-29, :45-53) -- without materialising any
+    per-edge array: every sweep recomputes the messages from a per-point table (csrc/train_sa.cu).  Same statistics
+    protocol as LinReluBN (running statistics, num_batches_tracked, SyncBatchNorm)."""
+
+    @staticmethod
+    def supported(seq, feat) -> bool:
+        blocks = list(seq)
+        if len(blocks) != 2 or feat.shape[1] != 8 or feat.dtype != torch.float32:
+            return False
+        for blk, shape in zip(blocks, ((16, 11), (16, 16))):
+            layers = list(blk)
+            if len(layers) != 3 or not isinstance(layers[0], torch.nn.Linear) or not isinstance(layers[1], torch.nn.ReLU):
+                return False
+            lin, bn = layers[0], layers[2]
+            if not isinstance(bn, (torch.nn.BatchNorm1d, torch.nn.SyncBatchNorm)):
+                return False
+            if not (bn.training and bn.affine and bn.momentum is not None and lin.bias is not None
+                    and tuple(lin.weight.shape) == shape):
+                return False
+        return True
+
+    @staticmethod
+    def forward(ctx, feat, pos4, qpos4, rowptr, col, W1, b1, g1, bt1, W2, b2, g2, bt2, bn1, bn2):
+        lib = _lib.load()
+        feat, W1, b1, W2, b2, g2 = _c(feat), _c(W1), _c(b1), _c(W2), _c(b2), _c(g2)
+        P, M, dev, st = feat.shape[0], qpos4.shape[0], feat.device, stream_ptr()
+        f32 = torch.float32
+        u = torch.empty((P, 16), dtype=f32, device=dev)
+        stats1 = torch.empty(33, dtype=torch.float64, device=dev)
+        stats2 = torch.empty(33, dtype=torch.float64, device=dev)
+        key = torch.empty((M, 16), dtype=f32, device=dev)
+        arg = torch.empty((M, 16), dtype=torch.int32, device=dev)
+        x1 = torch.empty((M, 16), dtype=f32, device=dev)
+        amax = torch.empty((M, 16), dtype=f32, device=dev)
+        queue = torch.empty(4, dtype=torch.int32, device=dev)  # work-queue cursors: each sweep resets its own
+        rp, cp, qp = dptr(rowptr, torch.int32), dptr(col, torch.int32), dptr(qpos4)
+        check(lib.sn2_sa1t_pre(dptr(feat, f32), dptr(pos4), P, dptr(W1, f32), dptr(u), st), "sn2_sa1t_pre")
+        check(lib.sn2_sa1t_stats1(dptr(u), qp, rp, cp, M, dptr(W1), dptr(b1, f32), dptr(stats1), dptr(queue), st), "sn2_sa1t_stats1")
+        ss1, group1, peer1 = _bn_stats_to_ss(lib, bn1, stats1, g1, bt1, 16, st)
+        check(lib.sn2_sa1t_stats2(dptr(u), qp, rp, cp, M, dptr(W1), dptr(b1), dptr(W2, f32), dptr(b2, f32), dptr(ss1),
+                                  dptr(g2, f32), dptr(stats2), dptr(key), dptr(arg), dptr(queue), st), "sn2_sa1t_stats2")
+        ss2, group2, peer2 = _bn_stats_to_ss(lib, bn2, stats2, g2, bt2, 16, st)
+        check(lib.sn2_sa1t_finish(dptr(key), dptr(arg), dptr(g2), dptr(ss2), M, dptr(x1), dptr(amax), st), "sn2_sa1t_finish")
+        ops._count(8)
+        ctx.save_for_backward(feat, pos4, qpos4, rowptr, col, W1, b1, W2, b2, g2, u, ss1, ss2, stats1, stats2, arg, amax)
+        ctx.sync = (group1, peer1, group2, peer2)
+        return x1
+
+    @staticmethod
+    def backward(ctx, dx1):
+        lib = _lib.load()
+        feat, pos4, qpos4, rowptr, col, W1, b1, W2, b2, g2, u, ss1, ss2, stats1, stats2, arg, amax = ctx.saved_tensors
+        group1, peer1, group2, peer2 = ctx.sync
+        P, M, dev, st = feat.shape[0], qpos4.shape[0], feat.device, stream_ptr()
+        f32 = torch.float32
+        dx1 = _c(dx1)
+        if dx1.data_ptr() % 16:
+            dx1 = dx1.clone()
+        sums1 = torch.empty(32, dtype=torch.float64, device=dev)
+        sums2 = torch.empty(32, dtype=torch.float64, device=dev)
+        partial = torch.empty((int(lib.sn2_sa1t_blocks()), int(lib.sn2_sa1t_partials())), dtype=f32, device=dev)
+        dW1, db1 = torch.empty_like(W1), torch.empty_like(b1)
+        dW2, db2 = torch.empty_like(W2), torch.empty_like(b2)
+        du = torch.empty((P, 16), dtype=f32, device=dev)
+        dc = torch.empty((M, 16), dtype=f32, device=dev)
+        queue = torch.empty(4, dtype=torch.int32, device=dev)
+        rp, cp, qp = dptr(rowptr, torch.int32), dptr(col, torch.int32), dptr(qpos4)
+        check(lib.sn2_sa1t_bwd_sums(dptr(dx1, f32), dptr(amax), dptr(arg), M, dptr(sums2), st), "sn2_sa1t_bwd_sums")
+        dg2, dbt2 = _bn_bwd_sums(lib, sums2, ss2, 16, group2, peer2, st)
+        check(lib.sn2_sa1t_bwd_w2(dptr(u), qp, rp, cp, M, dptr(W1), dptr(b1), dptr(W2), dptr(b2), dptr(g2), dptr(ss1), dptr(ss2),
+                                  dptr(stats2), dptr(sums2), dptr(dx1), dptr(arg), dptr(partial), dptr(dW2), dptr(db2),
+                                  dptr(sums1), dptr(queue), st), "sn2_sa1t_bwd_w2")
+        dg1, dbt1 = _bn_bwd_sums(lib, sums1, ss1, 16, group1, peer1, st)
+        check(lib.sn2_sa1t_bwd_in(dptr(u), qp, rp, cp, P, M, dptr(W1), dptr(b1), dptr(W2), dptr(b2), dptr(g2), dptr(ss1),
+                                  dptr(ss2), dptr(stats1), dptr(stats2), dptr(sums1), dptr(sums2), dptr(dx1), dptr(arg),
+                                  dptr(du), dptr(dc), dptr(queue), st), "sn2_sa1t_bwd_in")
+        check(lib.sn2_sa1t_bwd_w1(dptr(du), dptr(dc), dptr(feat), dptr(pos4), qp, P, M, dptr(partial), dptr(dW1), dptr(db1), st),
+              "sn2_sa1t_bwd_w1")
+        ops._count(9)
+        dfeat = du @ W1[:, :8] if ctx.needs_input_grad[0] else None
+        return dfeat, None, None, None, None, dW1, db1, dg1, dbt1, dW2, db2, dg2, dbt2, None, None
+
+
 class Head(torch.autograd.Function):
     """relu(lin1) -> lin2 -> softmax(4) x sigmoid(1) of reference model/point_net2.py:141-153 (dropout p = 0) in one
     kernel each way; the backward recomputes the head from its input row, nothing else is saved.

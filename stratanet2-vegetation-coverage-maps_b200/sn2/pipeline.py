@@ -388,7 +388,7 @@ def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num
     backward).  `structure`: a TrainStructure prepared ahead of time (StructurePrefetcher)."""
     import torch.nn.functional as F
 
-    from .autograd_ops import EdgeMsg, Head, Interp3, InterpPlot, SegmentMax, run_mlp, tall_linear
+    from .autograd_ops import EdgeMsg, Head, Interp3, InterpPlot, SA1Recompute, SegmentMax, run_mlp, tall_linear
 
     invalidate_packed(model)  # running statistics are about to change behind torch's back
     S = structure if structure is not None else TrainStructure(model, xyz, cloud, device, max_num_neighbors, timer)
@@ -401,8 +401,14 @@ def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num
     rows1, rows2 = getattr(S, "rows1", None), getattr(S, "rows2", None)  # device edge counts of fixed-capacity lists
 
     # the last BatchNorm of each message MLP is applied inside the max aggregation (no pass of its own)
-    y1, ss1 = run_mlp(sa1.conv.local_nn, EdgeMsg.apply(feat0, pos0, pos1, rowptr1, col1, rows1), rows1, defer_last=True)
-    x1, _ = SegmentMax.apply(y1, rowptr1, ss1)
+    if os.environ.get("SN2_SA_RECOMPUTE", "1") == "1" and SA1Recompute.supported(sa1.conv.local_nn, feat0):
+        # no per-edge array is written: every sweep recomputes the messages (csrc/train_sa.cu)
+        (l1, _, n1), (l2, _, n2) = list(sa1.conv.local_nn[0]), list(sa1.conv.local_nn[1])
+        x1 = SA1Recompute.apply(feat0, pos0, pos1, rowptr1, col1, l1.weight, l1.bias, n1.weight, n1.bias,
+                                l2.weight, l2.bias, n2.weight, n2.bias, n1, n2)
+    else:
+        y1, ss1 = run_mlp(sa1.conv.local_nn, EdgeMsg.apply(feat0, pos0, pos1, rowptr1, col1, rows1), rows1, defer_last=True)
+        x1, _ = SegmentMax.apply(y1, rowptr1, ss1)
     y2, ss2 = run_mlp(sa2.conv.local_nn, EdgeMsg.apply(x1, pos1, pos2, rowptr2, col2, rows2), rows2, defer_last=True)
     x2, _ = SegmentMax.apply(y2, rowptr2, ss2)
     y3, ss3 = run_mlp(model.sa3_module.nn, torch.cat([x2, pos2[:, :3]], dim=1), defer_last=True)

@@ -945,6 +945,84 @@ def test_deferred_batchnorm_matches_materialised(cuda_device, monkeypatch):
         torch.testing.assert_close(s1[k], s0[k], rtol=1e-5, atol=1e-6, msg=lambda m_, k=k: f"{k}: {m_}")
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("negative_gamma", [False, True])
+def test_sa1_recompute_block_matches_materialised_and_fp64(cuda_device, negative_gamma):
+    """SA1Recompute (csrc/train_sa.cu: the train-mode sa1 block with every message recomputed per sweep) against (a) the
+    materialising path EdgeMsg -> LinReluBN x2 -> SegmentMax on the same inputs and (b) a float64 torch restatement of
+    reference model/point_net2.py:21-29 + :45-53: output, gradients of all eight parameter tensors and of the point
+    features, running statistics.  Ragged rows (1 .. 90 edges, one empty row), negative BatchNorm scales."""
+    import copy
+
+    from model.point_net2 import MLP
+    from sn2.autograd_ops import EdgeMsg, SA1Recompute, SegmentMax, run_mlp
+
+    g = torch.Generator().manual_seed(5 + int(negative_gamma))
+    P, Q = 6000, 1500
+    deg = torch.randint(1, 91, (Q,), generator=g)
+    deg[7] = 0
+    rowptr = torch.zeros(Q + 1, dtype=torch.int64)
+    rowptr[1:] = torch.cumsum(deg, 0)
+    E = int(rowptr[-1])
+    col = torch.randint(0, P, (E,), generator=g)
+    feat = torch.randn(P, 8, generator=g)
+    pos = torch.cat([torch.randn(P, 3, generator=g), torch.zeros(P, 1)], 1)
+    qpos = torch.cat([torch.randn(Q, 3, generator=g), torch.zeros(Q, 1)], 1)
+    dout = torch.randn(Q, 16, generator=g)
+    mlp = MLP([11, 16, 16]).train()
+    with torch.no_grad():
+        for blk in mlp:
+            gam = torch.randn(16, generator=g) * 0.7 + 0.3 if negative_gamma else torch.rand(16, generator=g) + 0.5
+            blk[2].weight.copy_(gam)
+            blk[2].bias.copy_(torch.randn(16, generator=g) * 0.2)
+
+    # (b) float64 restatement on the CPU
+    m64 = copy.deepcopy(mlp).double()
+    f64 = feat.double().requires_grad_(True)
+    row = torch.repeat_interleave(torch.arange(Q), deg)
+    msg = torch.cat([f64[col], pos[col, :3].double() - qpos[row, :3].double()], 1)
+    y = m64(msg)
+    ref = torch.zeros(Q, 16, dtype=torch.float64)
+    for i in range(Q):
+        if deg[i] > 0:
+            ref[i] = y[rowptr[i]:rowptr[i + 1]].max(0).values
+    ref.backward(dout.double())
+    ref_grads = [p_.grad.clone() for p_ in m64.parameters()]
+
+    dev = cuda_device
+    rp, cl = rowptr.to(torch.int32).to(dev), col.to(torch.int32).to(dev)
+    pos_d, qpos_d, dout_d = pos.to(dev), qpos.to(dev), dout.to(dev)
+    results = []
+    for recompute in (False, True):
+        m = copy.deepcopy(mlp).to(dev)
+        fd = feat.to(dev).requires_grad_(True)
+        if recompute:
+            assert SA1Recompute.supported(m, fd)
+            (l1, _, n1), (l2, _, n2) = list(m[0]), list(m[1])
+            out = SA1Recompute.apply(fd, pos_d, qpos_d, rp, cl, l1.weight, l1.bias, n1.weight, n1.bias,
+                                     l2.weight, l2.bias, n2.weight, n2.bias, n1, n2)
+        else:
+            yy, ss = run_mlp(m, EdgeMsg.apply(fd, pos_d, qpos_d, rp, cl), defer_last=True)
+            out, _ = SegmentMax.apply(yy, rp, ss)
+        out.backward(dout_d)
+        results.append((out.detach().cpu(), [p_.grad.cpu() for p_ in m.parameters()], fd.grad.cpu(),
+                        {k: v.cpu() for k, v in m.state_dict().items()}))
+    (o0, g0, df0, s0), (o1, g1, df1, s1) = results
+    assert torch.all(o1[7] == 0)
+    for o in (o0, o1):
+        torch.testing.assert_close(o.double(), ref.detach(), rtol=1e-4, atol=1e-5)
+    names = [n for n, _ in mlp.named_parameters()]
+    for n, a0, a1, r in zip(names, g0, g1, ref_grads):
+        scale = float(r.abs().max()) + 1e-12
+        e0, e1 = float((a0.double() - r).abs().max()) / scale, float((a1.double() - r).abs().max()) / scale
+        assert e1 < 2e-4, f"{n}: recompute path {e1:.2e} of the fp64 gradient's max-norm (materialising path {e0:.2e})"
+    scale = float(f64.grad.abs().max())
+    assert float((df1.double() - f64.grad).abs().max()) / scale < 2e-4
+    assert float((df0.double() - f64.grad).abs().max()) / scale < 2e-4
+    for k in s0:
+        torch.testing.assert_close(s1[k], s0[k], rtol=1e-5, atol=1e-6, msg=lambda m_, k=k: f"{k}: {m_}")
+
+
 def test_structure_prefetcher_matches_plain_loop(cuda_device):
     """StructurePrefetcher (structural stage of batch i+1 on a side stream) yields the same forward results and
     gradients as the plain loop, batch by batch."""
