@@ -40,7 +40,7 @@ constexpr int TS_NP2 = TC * (TC + 1);  // [o][k] partial of G, column TC = db2
 constexpr int TS_LD = 20;           // row stride of the per-warp tiles (conflict-free float4 rows)
 constexpr int TS_CHUNK = 8;         // centroids a warp pulls from the work queue at a time
 
-struct TsW {                         // shared-memory image of the parameters and BatchNorm coefficients
+struct __align__(16) TsW {                         // shared-memory image of the parameters and BatchNorm coefficients
     float w1p[3][TC];                // [k][o] = W1[o][TF + k]
     float b1[TC];
     float w2f[TC][TC];               // [k][o] = W2[o][k] * s1[k]   (BatchNorm 1 folded into layer 2)
@@ -313,13 +313,7 @@ sa1t_sweep_kernel(const TsArgs a)
 #pragma unroll
             for (int k = 0; k < TC; ++k) {
 #pragma unroll
-                for (int g = 0; g < TC / 4; ++g) {
-                    const float4 wv = *reinterpret_cast<const float4 *>(&S.w2f[k][4 * g]);
-                    a2[4 * g] = fmaf(a1[k], wv.x, a2[4 * g]);
-                    a2[4 * g + 1] = fmaf(a1[k], wv.y, a2[4 * g + 1]);
-                    a2[4 * g + 2] = fmaf(a1[k], wv.z, a2[4 * g + 2]);
-                    a2[4 * g + 3] = fmaf(a1[k], wv.w, a2[4 * g + 3]);
-                }
+                for (int o = 0; o < TC; ++o) a2[o] = fmaf(a1[k], S.w2f[k][o], a2[o]);
             }
 #pragma unroll
             for (int o = 0; o < TC; ++o) a2[o] = fmaxf(a2[o], 0.f);
@@ -382,13 +376,7 @@ sa1t_sweep_kernel(const TsArgs a)
 #pragma unroll
                 for (int o = 0; o < TC; ++o) {
 #pragma unroll
-                    for (int g = 0; g < TC / 4; ++g) {
-                        const float4 wv = *reinterpret_cast<const float4 *>(&S.w2t[o][4 * g]);
-                        dh1[4 * g] = fmaf(dz2[o], wv.x, dh1[4 * g]);
-                        dh1[4 * g + 1] = fmaf(dz2[o], wv.y, dh1[4 * g + 1]);
-                        dh1[4 * g + 2] = fmaf(dz2[o], wv.z, dh1[4 * g + 2]);
-                        dh1[4 * g + 3] = fmaf(dz2[o], wv.w, dh1[4 * g + 3]);
-                    }
+                    for (int k = 0; k < TC; ++k) dh1[k] = fmaf(dz2[o], S.w2t[o][k], dh1[k]);
                 }
 #pragma unroll
                 for (int k = 0; k < TC; ++k) {
