@@ -323,6 +323,25 @@ int sn2_sa1t_bwd_in(const float *u, const float *qpos4, const int *rowptr, const
 int sn2_sa1t_bwd_w1(const float *du, const float *dc, const float *feat, const float *pos4, const float *qpos4, long long P,
                     int M, float *partial, float *dW1, float *db1, void *stream);
 
+/* sa2 (PointConv(local_nn = MLP([19,32])), one block), same scheme with lane = channel: LIVE W [32,19], b [32], gamma [32].
+ *   sn2_sa2t_pre      u [P,32] = W[:, :16] x + W[:, 16:] pos
+ *   sn2_sa2t_fwd      stats [65] fp64 of a = relu(u[col] + b - Wp q); key / arg [M,32]                       -> ss
+ *   sn2_sa2t_finish   x2 [M,32] = BN(a[arg]), amax [M,32]
+ *   sn2_sa2t_bwd_sums sums [64] fp64 = {sum dx2, sum dx2 * amax}
+ *   sn2_sa2t_bwd      du [P,32] (zeroed here) += relu'(a) BN'(dz) over the edges of a point, dc [M,32] = row sums
+ *   sn2_sa2t_bwd_w    dW [32,19], db [32] (partial as above); the gradient of x is du W[:, :16] (caller's GEMM) */
+int sn2_sa2t_pre(const float *x, const float *pos4, long long P, const float *W, float *u, void *stream);
+int sn2_sa2t_fwd(const float *u, const float *qpos4, const int *rowptr, const int *col, int M, const float *W, const float *b,
+                 const float *gamma, double *stats, float *key, int *arg, int *queue, void *stream);
+int sn2_sa2t_finish(const float *key, const int *arg, const float *gamma, const float *ss, int M, float *x2, float *amax,
+                    void *stream);
+int sn2_sa2t_bwd_sums(const float *dout, const float *amax, const int *arg, int M, double *sums, void *stream);
+int sn2_sa2t_bwd(const float *u, const float *qpos4, const int *rowptr, const int *col, long long P, int M, const float *W,
+                 const float *b, const float *gamma, const float *ss, const double *stats, const double *sums, const float *dout,
+                 const int *arg, float *du, float *dc, int *queue, void *stream);
+int sn2_sa2t_bwd_w(const float *du, const float *dc, const float *x, const float *pos4, const float *qpos4, long long P, int M,
+                   float *partial, float *dW, float *db, void *stream);
+
 /* ---- peer-memory collectives for data-parallel training, csrc/comm.cu ----------------------------
  * The reference has no distributed code; these stand where a DistributedDataParallel / SyncBatchNorm wrapper around
  * learning/train.py:52-66 would call NCCL.  One region per rank (the ONLY device memory this library allocates),

@@ -71,10 +71,11 @@ struct TsArgs {
 };
 
 // dy = mask * (cA * dz + cB * y + cC): BatchNorm backward from the raw sums S1 = sum dz, S2 = sum dz * y (train_mlp.cu)
+template <int C = TC>
 __device__ __forceinline__ void bn_bwd_coeff(const float *ss, const double *sums, double n, int o, float &cA, float &cB, float &cC)
 {
-    const float sc = ss[o], mean = ss[2 * TC + o], inv = ss[3 * TC + o];
-    const double S1 = sums[o], S2 = sums[TC + o];
+    const float sc = ss[o], mean = ss[2 * C + o], inv = ss[3 * C + o];
+    const double S1 = sums[o], S2 = sums[C + o];
     const float m1 = (float)(S1 / n);
     const float m2 = (float)((double)inv * (S2 - (double)mean * S1) / n);
     const float kb = -inv * m2;
@@ -139,25 +140,33 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// u_j = W1x x_j + W1p p_j
+// u_j = W1x x_j + W1p p_j   (CF point features -> CO channels; W [CO][CF + 3])
+template <int CF, int CO>
 __global__ void __launch_bounds__(256)
-sa1t_pre_kernel(const float *__restrict__ feat, const float4 *__restrict__ pos, long long P, const float *__restrict__ W1,
+sa_t_pre_kernel(const float *__restrict__ feat, const float4 *__restrict__ pos, long long P, const float *__restrict__ W1,
                 float *__restrict__ u)
 {
-    __shared__ __align__(16) float w[TK1][TC];  // [k][o]
-    for (int i = threadIdx.x; i < TK1 * TC; i += 256) w[i / TC][i % TC] = __ldg(W1 + (i % TC) * TK1 + i / TC);
+    constexpr int CK = CF + 3;
+    __shared__ __align__(16) float w[CK][CO];  // [k][o]
+    for (int i = threadIdx.x; i < CK * CO; i += 256) w[i / CO][i % CO] = __ldg(W1 + (i % CO) * CK + i / CO);
     __syncthreads();
     const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
     if (p >= P) return;
-    const float4 f0 = ldg4(feat + p * TF), f1 = ldg4(feat + p * TF + 4), pp = __ldg(pos + p);
-    const float in[TK1] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, pp.x, pp.y, pp.z};
-    float acc[TC];
+    float in[CK];
 #pragma unroll
-    for (int o = 0; o < TC; ++o) acc[o] = 0.f;
+    for (int g = 0; g < CF / 4; ++g) {
+        const float4 f = ldg4(feat + p * CF + 4 * g);
+        in[4 * g] = f.x; in[4 * g + 1] = f.y; in[4 * g + 2] = f.z; in[4 * g + 3] = f.w;
+    }
+    const float4 pp = __ldg(pos + p);
+    in[CF] = pp.x; in[CF + 1] = pp.y; in[CF + 2] = pp.z;
+    float acc[CO];
 #pragma unroll
-    for (int k = 0; k < TK1; ++k) {
+    for (int o = 0; o < CO; ++o) acc[o] = 0.f;
 #pragma unroll
-        for (int g = 0; g < TC / 4; ++g) {
+    for (int k = 0; k < CK; ++k) {
+#pragma unroll
+        for (int g = 0; g < CO / 4; ++g) {
             const float4 wv = *reinterpret_cast<const float4 *>(&w[k][4 * g]);
             acc[4 * g] = fmaf(in[k], wv.x, acc[4 * g]);
             acc[4 * g + 1] = fmaf(in[k], wv.y, acc[4 * g + 1]);
@@ -165,18 +174,18 @@ sa1t_pre_kernel(const float *__restrict__ feat, const float4 *__restrict__ pos, 
             acc[4 * g + 3] = fmaf(in[k], wv.w, acc[4 * g + 3]);
         }
     }
-    float4 *o4 = reinterpret_cast<float4 *>(u + p * TC);
+    float4 *o4 = reinterpret_cast<float4 *>(u + p * CO);
 #pragma unroll
-    for (int g = 0; g < TC / 4; ++g) o4[g] = make_float4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
+    for (int g = 0; g < CO / 4; ++g) o4[g] = make_float4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
 }
 
 // zero the sums, count = live edge count = rowptr[M]
-__global__ void sa1t_stats_init_kernel(double *stats, const int *__restrict__ rowptr, int M, int *queue)
+__global__ void sa1t_stats_init_kernel(double *stats, const int *__restrict__ rowptr, int M, int *queue, int C)
 {
     const int t = threadIdx.x;
-    if (t == 2 * TC + 1) *queue = 0;
-    if (t < 2 * TC) stats[t] = 0.0;
-    if (t == 2 * TC) stats[2 * TC] = (double)__ldg(rowptr + M);
+    if (t == 2 * C + 1) *queue = 0;
+    if (t < 2 * C) stats[t] = 0.0;
+    if (t == 2 * C) stats[2 * C] = (double)__ldg(rowptr + M);
 }
 
 // The sweeps read the parameters as constant-bank operands (uniform loads / direct FFMA operands), like the eval kernel:
@@ -434,48 +443,52 @@ sa1t_sweep_kernel(const TsArgs a)
     }
 }
 
-// x1 = BN2(a2[arg]) = key * sgn2 * s2 + t2 (0 for a centroid without neighbours); amax = a2[arg]
+// x = BN(a[arg]) = key * sgn * s + t (0 for a centroid without neighbours); amax = a[arg]
+template <int C>
 __global__ void __launch_bounds__(256)
-sa1t_finish_kernel(const float *__restrict__ key, const int *__restrict__ arg, const float *__restrict__ gamma2,
-                   const float *__restrict__ ss2, long long n, float *__restrict__ x1, float *__restrict__ amax)
+sa_t_finish_kernel(const float *__restrict__ key, const int *__restrict__ arg, const float *__restrict__ gamma,
+                   const float *__restrict__ ss, long long n, float *__restrict__ x, float *__restrict__ amax)
 {
     const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
     if (t >= n) return;
-    const int o = (int)(t % TC);
+    const int o = (int)(t % C);
     const bool any = __ldg(arg + t) >= 0;
-    const float av = any ? (__ldg(gamma2 + o) < 0.f ? -__ldg(key + t) : __ldg(key + t)) : 0.f;
+    const float av = any ? (__ldg(gamma + o) < 0.f ? -__ldg(key + t) : __ldg(key + t)) : 0.f;
     amax[t] = av;
-    x1[t] = any ? fmaf(av, __ldg(ss2 + o), __ldg(ss2 + TC + o)) : 0.f;
+    x[t] = any ? fmaf(av, __ldg(ss + o), __ldg(ss + C + o)) : 0.f;
 }
 
-// B0: sums[o] = sum_i dout[i][o], sums[16 + o] = sum_i dout[i][o] * amax[i][o] over the centroids that have an arg-max edge
+// B0: sums[o] = sum_i dout[i][o], sums[C + o] = sum_i dout[i][o] * amax[i][o] over the centroids that have an arg-max edge
+template <int C>
 __global__ void __launch_bounds__(256)
-sa1t_bwd_sums_kernel(const float *__restrict__ dout, const float *__restrict__ amax, const int *__restrict__ arg, long long M,
+sa_t_bwd_sums_kernel(const float *__restrict__ dout, const float *__restrict__ amax, const int *__restrict__ arg, long long M,
                      double *__restrict__ sums)
 {
-    __shared__ double red[2 * TC];
-    if (threadIdx.x < 2 * TC) red[threadIdx.x] = 0.0;
+    static_assert(C == 16 || C == 32, "channel <-> lane mapping below");
+    __shared__ double red[2 * C];
+    if (threadIdx.x < 2 * C) red[threadIdx.x] = 0.0;
     __syncthreads();
-    // thread = (row slot, channel): 16 rows per 256 threads and step
-    const int o = threadIdx.x % TC;
+    // thread = (row slot, channel): 256 / C rows per step
+    const int o = threadIdx.x % C;
     double s1 = 0.0, s2 = 0.0;
-    for (long long i = (long long)blockIdx.x * (256 / TC) + threadIdx.x / TC; i < M; i += (long long)gridDim.x * (256 / TC)) {
-        const long long t = i * TC + o;
+    for (long long i = (long long)blockIdx.x * (256 / C) + threadIdx.x / C; i < M; i += (long long)gridDim.x * (256 / C)) {
+        const long long t = i * C + o;
         if (__ldg(arg + t) >= 0) {
             const float d = __ldg(dout + t);
             s1 += (double)d;
             s2 += (double)d * (double)__ldg(amax + t);
         }
     }
-    // lanes l and l + 16 hold the same channel
-    s1 += __shfl_xor_sync(SN2_FULL, s1, 16);
-    s2 += __shfl_xor_sync(SN2_FULL, s2, 16);
-    if ((threadIdx.x & 31) < TC) {
+    if constexpr (C == 16) {  // lanes l and l + 16 hold the same channel
+        s1 += __shfl_xor_sync(SN2_FULL, s1, 16);
+        s2 += __shfl_xor_sync(SN2_FULL, s2, 16);
+    }
+    if ((threadIdx.x & 31) < C) {
         atomicAdd(red + o, s1);
-        atomicAdd(red + TC + o, s2);
+        atomicAdd(red + C + o, s2);
     }
     __syncthreads();
-    if (threadIdx.x < 2 * TC) atomicAdd(sums + threadIdx.x, red[threadIdx.x]);
+    if (threadIdx.x < 2 * C) atomicAdd(sums + threadIdx.x, red[threadIdx.x]);
 }
 
 // CTA partials of B1 -> dW2 = G diag(s1) + db2 t1^T, db2, and BatchNorm 1's raw backward sums T1 = W2^T db2,
@@ -505,16 +518,18 @@ sa1t_w2_finish_kernel(const float *__restrict__ partial, int nblk, const float *
     }
 }
 
-// W1: dW1[o][k] = sum_j du[j][o] in_j[k] - sum_i dc[i][o] q_i[k - 8] (k >= 8), db1[o] = sum_j du[j][o]; CTA partials
-// in the [o][k | db] layout of lrb_wgrad_reduce.  thread = (o, k), k = 11 stands for the bias (in = 1).
-constexpr int W1_T = TC * (TK1 + 1), W1_TILE = 64;
-__global__ void __launch_bounds__(W1_T)
-sa1t_w1_kernel(const float *__restrict__ du, const float *__restrict__ dc, const float *__restrict__ feat,
+// W1: dW1[o][k] = sum_j du[j][o] in_j[k] - sum_i dc[i][o] q_i[k - CF] (k >= CF), db1[o] = sum_j du[j][o]; CTA partials
+// in the [o][k | db] layout of lrb_wgrad_reduce.  thread = (o, k), k = CF + 3 stands for the bias (in = 1).
+constexpr int W1_TILE = 64;
+template <int CO, int CF>
+__global__ void __launch_bounds__(CO * (CF + 4))
+sa_t_w1_kernel(const float *__restrict__ du, const float *__restrict__ dc, const float *__restrict__ feat,
                const float4 *__restrict__ pos, const float4 *__restrict__ qpos, long long P, long long M, float *__restrict__ partial)
 {
-    __shared__ float sd[W1_TILE][TC + 1];
-    __shared__ float sx[W1_TILE][TK1 + 2];
-    const int t = threadIdx.x, o = t / (TK1 + 1), k = t - o * (TK1 + 1);
+    constexpr int CK = CF + 3, T = CO * (CK + 1);
+    __shared__ float sd[W1_TILE][CO + 1];
+    __shared__ float sx[W1_TILE][CK + 2];
+    const int t = threadIdx.x, o = t / (CK + 1), k = t - o * (CK + 1);
     float acc = 0.f;
     const long long ntp = (P + W1_TILE - 1) / W1_TILE, ntq = (M + W1_TILE - 1) / W1_TILE;
     for (long long tl = blockIdx.x; tl < ntp + ntq; tl += gridDim.x) {
@@ -522,21 +537,21 @@ sa1t_w1_kernel(const float *__restrict__ du, const float *__restrict__ dc, const
         const long long base = (pts ? tl : tl - ntp) * W1_TILE, lim = pts ? P : M;
         const float *d = pts ? du : dc;
         __syncthreads();
-        for (int x = t; x < W1_TILE * TC; x += W1_T) {
-            const int r = x / TC, cc = x - r * TC;
-            sd[r][cc] = base + r < lim ? __ldg(d + (base + r) * TC + cc) : 0.f;
+        for (int x = t; x < W1_TILE * CO; x += T) {
+            const int r = x / CO, cc = x - r * CO;
+            sd[r][cc] = base + r < lim ? __ldg(d + (base + r) * CO + cc) : 0.f;
         }
-        for (int x = t; x < W1_TILE * (TK1 + 1); x += W1_T) {
-            const int r = x / (TK1 + 1), cc = x - r * (TK1 + 1);
+        for (int x = t; x < W1_TILE * (CK + 1); x += T) {
+            const int r = x / (CK + 1), cc = x - r * (CK + 1);
             float v = 0.f;
             if (base + r < lim) {
                 if (pts) {
-                    if (cc < TF) v = __ldg(feat + (base + r) * TF + cc);
-                    else if (cc < TK1) { const float4 pp = __ldg(pos + base + r); v = cc == TF ? pp.x : (cc == TF + 1 ? pp.y : pp.z); }
+                    if (cc < CF) v = __ldg(feat + (base + r) * CF + cc);
+                    else if (cc < CK) { const float4 pp = __ldg(pos + base + r); v = cc == CF ? pp.x : (cc == CF + 1 ? pp.y : pp.z); }
                     else v = 1.f;
-                } else if (cc >= TF && cc < TK1) {
+                } else if (cc >= CF && cc < CK) {
                     const float4 qq = __ldg(qpos + base + r);
-                    v = -(cc == TF ? qq.x : (cc == TF + 1 ? qq.y : qq.z));
+                    v = -(cc == CF ? qq.x : (cc == CF + 1 ? qq.y : qq.z));
                 }
             }
             sx[r][cc] = v;
@@ -545,22 +560,145 @@ sa1t_w1_kernel(const float *__restrict__ du, const float *__restrict__ dc, const
 #pragma unroll 8
         for (int r = 0; r < W1_TILE; ++r) acc = fmaf(sd[r][o], sx[r][k], acc);
     }
-    partial[(size_t)blockIdx.x * W1_T + t] = acc;
+    partial[(size_t)blockIdx.x * T + t] = acc;
 }
 
+template <int CO, int CF>
 __global__ void __launch_bounds__(256)
-sa1t_w1_reduce_kernel(const float *__restrict__ partial, int nblk, float *__restrict__ dW1, float *__restrict__ db1)
+sa_t_w1_reduce_kernel(const float *__restrict__ partial, int nblk, float *__restrict__ dW1, float *__restrict__ db1)
 {
+    constexpr int CK = CF + 3, T = CO * (CK + 1);
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (t >= W1_T) return;
+    if (t >= T) return;
     float s = 0.f;
-    for (int b = lane; b < nblk; b += 32) s += __ldg(partial + (size_t)b * W1_T + t);
+    for (int b = lane; b < nblk; b += 32) s += __ldg(partial + (size_t)b * T + t);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(SN2_FULL, s, d);
     if (lane == 0) {
-        const int o = t / (TK1 + 1), k = t - o * (TK1 + 1);
-        if (k < TK1) dW1[o * TK1 + k] = s;
+        const int o = t / (CK + 1), k = t - o * (CK + 1);
+        if (k < CK) dW1[o * CK + k] = s;
         else db1[o] = s;
+    }
+}
+
+template <int CO, int CF>
+int launch_w1(const float *du, const float *dc, const float *feat, const float *pos4, const float *qpos4, long long P, long long M,
+              float *partial, float *dW, float *db, cudaStream_t st)
+{
+    constexpr int T = CO * (CF + 4);
+    const int grid = 148 * 6;
+    sa_t_w1_kernel<CO, CF><<<grid, T, 0, st>>>(du, dc, feat, reinterpret_cast<const float4 *>(pos4), reinterpret_cast<const float4 *>(qpos4), P, M,
+                                              partial);
+    SN2_LAUNCH_CHECK("sa_t_w1_kernel");
+    sa_t_w1_reduce_kernel<CO, CF><<<(T * 32 + 255) / 256, 256, 0, st>>>(partial, grid, dW, db);
+    SN2_LAUNCH_CHECK("sa_t_w1_reduce_kernel");
+    return SN2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sa2: PointConv(local_nn = MLP([19, 32])), ONE block: a = relu(u_j + c_i), x2 = max_e BN(a).  lane = channel (32): a
+// neighbour's u row is one coalesced 128-byte read, the running statistics / arg-max / row sums are per-lane scalars and
+// nothing is reduced across lanes.  MODE 0: forward sweep (sum a, sum a^2, arg-max edge of sign(gamma) * a);
+// MODE 1: backward sweep (dz1 = relu'(a) BN'(dz): du[col] += dz1, dc_i = row sum).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int T2C = 32, T2F = 16, T2K = T2F + 3;
+constexpr int T2_CHUNK = 2;  // few, long rows (20 000 centroids x ~100 edges at config 3): small chunks balance the warps
+struct Ts2Args {
+    const float *u;
+    const float4 *qpos;
+    const int *rowptr, *col;
+    int M;
+    const float *W, *b, *gamma, *ss;   // live parameters [32][19], [32], [32]; ss [4*32]
+    const double *stats, *sums;
+    const float *dout;
+    const int *arg;
+    double *stats_out;
+    float *key;
+    int *arg_out;
+    float *du, *dc;
+    int *queue;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(TS_T)
+sa2t_sweep_kernel(const Ts2Args a)
+{
+    __shared__ double red[2 * T2C];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 2 * T2C) red[tid] = 0.0;
+    __syncthreads();
+    const float w0 = __ldg(a.W + lane * T2K + T2F), w1 = __ldg(a.W + lane * T2K + T2F + 1), w2 = __ldg(a.W + lane * T2K + T2F + 2);
+    const float bb = __ldg(a.b + lane);
+    const float sgn = __ldg(a.gamma + lane) < 0.f ? -1.f : 1.f;
+    float cA = 0.f, cB = 0.f, cC = 0.f;
+    if constexpr (MODE == 1) bn_bwd_coeff<T2C>(a.ss, a.sums, a.stats[2 * T2C], lane, cA, cB, cC);
+    double sad = 0.0, sqd = 0.0;
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(a.queue, T2_CHUNK);
+        base = __shfl_sync(SN2_FULL, base, 0);
+        if (base >= a.M) break;
+        const int rp_l = (lane <= T2_CHUNK && base + lane <= a.M) ? __ldg(a.rowptr + base + lane) : 0;
+        const float4 q_l = (lane < T2_CHUNK && base + lane < a.M) ? __ldg(a.qpos + base + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float sa = 0.f, sq = 0.f;
+        for (int ci = 0; ci < T2_CHUNK && base + ci < a.M; ++ci) {
+            const int i = base + ci;
+            const int s = __shfl_sync(SN2_FULL, rp_l, ci), e = __shfl_sync(SN2_FULL, rp_l, ci + 1);
+            const float qx = __shfl_sync(SN2_FULL, q_l.x, ci), qy = __shfl_sync(SN2_FULL, q_l.y, ci), qz = __shfl_sync(SN2_FULL, q_l.z, ci);
+            const float c = bb - (w0 * qx + w1 * qy + w2 * qz);
+            float best = -INFINITY, dcs = 0.f, dl = 0.f;
+            int beste = 0x7fffffff, argl = -1;
+            if constexpr (MODE == 1) {
+                argl = __ldg(a.arg + (size_t)i * T2C + lane);
+                dl = __ldg(a.dout + (size_t)i * T2C + lane);
+            }
+            auto edge = [&](int p, float v, int j) {
+                const float av = fmaxf(v + c, 0.f);
+                if constexpr (MODE == 0) {
+                    sa += av;
+                    sq = fmaf(av, av, sq);
+                    const float kv = sgn * av;
+                    if (kv > best) { best = kv; beste = j; }  // ascending j: the first edge stays on ties
+                } else {
+                    const float dz = argl == j ? dl : 0.f;
+                    const float da = av > 0.f ? fmaf(cA, dz, fmaf(cB, av, cC)) : 0.f;
+                    atomicAdd(a.du + (size_t)p * T2C + lane, da);
+                    dcs += da;
+                }
+            };
+            for (int j0 = s; j0 < e; j0 += 32) {
+                const int idl = j0 + lane < e ? __ldg(a.col + j0 + lane) : 0;
+                const int take = min(32, e - j0);
+                // 16 neighbour rows in flight per warp: the loop is a chain of L2 round trips otherwise
+                constexpr int UN = 16;
+                for (int t = 0; t < take; t += UN) {
+                    int pp[UN];
+                    float vv[UN];
+#pragma unroll
+                    for (int k = 0; k < UN; ++k) {
+                        pp[k] = __shfl_sync(SN2_FULL, idl, (t + k) & 31);
+                        vv[k] = t + k < take ? __ldg(a.u + (size_t)pp[k] * T2C + lane) : 0.f;  // warp-uniform predicate
+                    }
+#pragma unroll
+                    for (int k = 0; k < UN; ++k)
+                        if (t + k < take) edge(pp[k], vv[k], j0 + t + k);
+                }
+            }
+            if constexpr (MODE == 0) {
+                a.key[(size_t)i * T2C + lane] = best;
+                a.arg_out[(size_t)i * T2C + lane] = e > s ? beste : -1;
+            } else {
+                a.dc[(size_t)i * T2C + lane] = dcs;
+            }
+        }
+        sad += (double)sa;
+        sqd += (double)sq;
+    }
+    if constexpr (MODE == 0) {
+        atomicAdd(red + lane, sad);
+        atomicAdd(red + T2C + lane, sqd);
+        __syncthreads();
+        if (tid < 2 * T2C) atomicAdd(a.stats_out + tid, red[tid]);
     }
 }
 
@@ -584,14 +722,14 @@ int launch_sweep(const TsArgs &a, int grid, cudaStream_t st)
 
 using namespace sn2;
 
-extern "C" int sn2_sa1t_partials(void) { return TS_NP2 > W1_T ? TS_NP2 : W1_T; }
+extern "C" int sn2_sa1t_partials(void) { return T2C * (T2K + 1); }  // the largest CTA partial: sa2's [32][19 | db]
 extern "C" int sn2_sa1t_blocks(void) { return 148 * 6; }
 
 extern "C" int sn2_sa1t_pre(const float *feat, const float *pos4, long long P, const float *W1, float *u, void *stream)
 {
     if (!feat || !pos4 || !W1 || !u || P <= 0) return SN2_EINVAL;
-    sa1t_pre_kernel<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(feat, reinterpret_cast<const float4 *>(pos4), P, W1, u);
-    SN2_LAUNCH_CHECK("sa1t_pre_kernel");
+    sa_t_pre_kernel<TF, TC><<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(feat, reinterpret_cast<const float4 *>(pos4), P, W1, u);
+    SN2_LAUNCH_CHECK("sa_t_pre_kernel");
     return SN2_OK;
 }
 
@@ -600,7 +738,7 @@ extern "C" int sn2_sa1t_stats1(const float *u, const float *qpos4, const int *ro
 {
     if (!u || !qpos4 || !rowptr || !col || !W1 || !b1 || !stats1 || !queue || M <= 0) return SN2_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    sa1t_stats_init_kernel<<<1, 64, 0, st>>>(stats1, rowptr, M, queue);
+    sa1t_stats_init_kernel<<<1, 128, 0, st>>>(stats1, rowptr, M, queue, TC);
     TsArgs a = {};
     a.u = u; a.qpos = reinterpret_cast<const float4 *>(qpos4); a.rowptr = rowptr; a.col = col; a.M = M;
     a.W1 = W1; a.b1 = b1; a.stats_out = stats1; a.queue = queue;
@@ -614,7 +752,7 @@ extern "C" int sn2_sa1t_stats2(const float *u, const float *qpos4, const int *ro
     if (!u || !qpos4 || !rowptr || !col || !W1 || !b1 || !W2 || !b2 || !ss1 || !gamma2 || !stats2 || !key || !arg || !queue || M <= 0)
         return SN2_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    sa1t_stats_init_kernel<<<1, 64, 0, st>>>(stats2, rowptr, M, queue);
+    sa1t_stats_init_kernel<<<1, 128, 0, st>>>(stats2, rowptr, M, queue, TC);
     TsArgs a = {};
     a.u = u; a.qpos = reinterpret_cast<const float4 *>(qpos4); a.rowptr = rowptr; a.col = col; a.M = M;
     a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.ss1 = ss1; a.gamma2 = gamma2; a.stats_out = stats2; a.key = key; a.arg_out = arg; a.queue = queue;
@@ -626,7 +764,7 @@ extern "C" int sn2_sa1t_finish(const float *key, const int *arg, const float *ga
 {
     if (!key || !arg || !gamma2 || !ss2 || !x1 || !amax || M <= 0) return SN2_EINVAL;
     const long long n = (long long)M * TC;
-    sa1t_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(key, arg, gamma2, ss2, n, x1, amax);
+    sa_t_finish_kernel<TC><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(key, arg, gamma2, ss2, n, x1, amax);
     SN2_LAUNCH_CHECK("sa1t_finish_kernel");
     return SN2_OK;
 }
@@ -636,7 +774,7 @@ extern "C" int sn2_sa1t_bwd_sums(const float *dout, const float *amax, const int
     if (!dout || !amax || !arg || !sums2 || M <= 0) return SN2_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     SN2_CUDA_TRY(cudaMemsetAsync(sums2, 0, 2 * TC * sizeof(double), st), "sa1t sums2 memset");
-    sa1t_bwd_sums_kernel<<<148, 256, 0, st>>>(dout, amax, arg, M, sums2);
+    sa_t_bwd_sums_kernel<TC><<<148, 256, 0, st>>>(dout, amax, arg, M, sums2);
     SN2_LAUNCH_CHECK("sa1t_bwd_sums_kernel");
     return SN2_OK;
 }
@@ -686,11 +824,74 @@ extern "C" int sn2_sa1t_bwd_w1(const float *du, const float *dc, const float *fe
 {
     if (!du || !dc || !feat || !pos4 || !qpos4 || !partial || !dW1 || !db1 || P <= 0 || M <= 0) return SN2_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = 148 * 6;
-    sa1t_w1_kernel<<<grid, W1_T, 0, st>>>(du, dc, feat, reinterpret_cast<const float4 *>(pos4), reinterpret_cast<const float4 *>(qpos4), P,
-                                         (long long)M, partial);
-    SN2_LAUNCH_CHECK("sa1t_w1_kernel");
-    sa1t_w1_reduce_kernel<<<(W1_T * 32 + 255) / 256, 256, 0, st>>>(partial, grid, dW1, db1);
-    SN2_LAUNCH_CHECK("sa1t_w1_reduce_kernel");
+    return launch_w1<TC, TF>(du, dc, feat, pos4, qpos4, P, (long long)M, partial, dW1, db1, st);
+}
+
+// ---- sa2 -------------------------------------------------------------------------------------------------------
+extern "C" int sn2_sa2t_pre(const float *x, const float *pos4, long long P, const float *W, float *u, void *stream)
+{
+    if (!x || !pos4 || !W || !u || P <= 0) return SN2_EINVAL;
+    sa_t_pre_kernel<T2F, T2C><<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<const float4 *>(pos4), P, W, u);
+    SN2_LAUNCH_CHECK("sa_t_pre_kernel<2>");
     return SN2_OK;
+}
+
+extern "C" int sn2_sa2t_fwd(const float *u, const float *qpos4, const int *rowptr, const int *col, int M, const float *W,
+                            const float *b, const float *gamma, double *stats, float *key, int *arg, int *queue, void *stream)
+{
+    if (!u || !qpos4 || !rowptr || !col || !W || !b || !gamma || !stats || !key || !arg || !queue || M <= 0) return SN2_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    sa1t_stats_init_kernel<<<1, 128, 0, st>>>(stats, rowptr, M, queue, T2C);
+    Ts2Args a = {};
+    a.u = u; a.qpos = reinterpret_cast<const float4 *>(qpos4); a.rowptr = rowptr; a.col = col; a.M = M;
+    a.W = W; a.b = b; a.gamma = gamma; a.stats_out = stats; a.key = key; a.arg_out = arg; a.queue = queue;
+    sa2t_sweep_kernel<0><<<sweep_grid(M, 6), TS_T, 0, st>>>(a);
+    SN2_LAUNCH_CHECK("sa2t_sweep_kernel<fwd>");
+    return SN2_OK;
+}
+
+extern "C" int sn2_sa2t_finish(const float *key, const int *arg, const float *gamma, const float *ss, int M, float *x2, float *amax,
+                               void *stream)
+{
+    if (!key || !arg || !gamma || !ss || !x2 || !amax || M <= 0) return SN2_EINVAL;
+    const long long n = (long long)M * T2C;
+    sa_t_finish_kernel<T2C><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(key, arg, gamma, ss, n, x2, amax);
+    SN2_LAUNCH_CHECK("sa_t_finish_kernel<2>");
+    return SN2_OK;
+}
+
+extern "C" int sn2_sa2t_bwd_sums(const float *dout, const float *amax, const int *arg, int M, double *sums, void *stream)
+{
+    if (!dout || !amax || !arg || !sums || M <= 0) return SN2_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    SN2_CUDA_TRY(cudaMemsetAsync(sums, 0, 2 * T2C * sizeof(double), st), "sa2t sums memset");
+    sa_t_bwd_sums_kernel<T2C><<<148, 256, 0, st>>>(dout, amax, arg, M, sums);
+    SN2_LAUNCH_CHECK("sa_t_bwd_sums_kernel<2>");
+    return SN2_OK;
+}
+
+extern "C" int sn2_sa2t_bwd(const float *u, const float *qpos4, const int *rowptr, const int *col, long long P, int M,
+                            const float *W, const float *b, const float *gamma, const float *ss, const double *stats,
+                            const double *sums, const float *dout, const int *arg, float *du, float *dc, int *queue, void *stream)
+{
+    if (!u || !qpos4 || !rowptr || !col || !W || !b || !gamma || !ss || !stats || !sums || !dout || !arg || !du || !dc || !queue ||
+        M <= 0 || P <= 0)
+        return SN2_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    SN2_CUDA_TRY(cudaMemsetAsync(du, 0, (size_t)P * T2C * sizeof(float), st), "sa2t du memset");
+    SN2_CUDA_TRY(cudaMemsetAsync(queue, 0, sizeof(int), st), "sa2t queue memset");
+    Ts2Args a = {};
+    a.u = u; a.qpos = reinterpret_cast<const float4 *>(qpos4); a.rowptr = rowptr; a.col = col; a.M = M;
+    a.W = W; a.b = b; a.gamma = gamma; a.ss = ss; a.stats = stats; a.sums = sums; a.dout = dout; a.arg = arg; a.du = du; a.dc = dc;
+    a.queue = queue;
+    sa2t_sweep_kernel<1><<<sweep_grid(M, 6), TS_T, 0, st>>>(a);
+    SN2_LAUNCH_CHECK("sa2t_sweep_kernel<bwd>");
+    return SN2_OK;
+}
+
+extern "C" int sn2_sa2t_bwd_w(const float *du, const float *dc, const float *x, const float *pos4, const float *qpos4, long long P,
+                              int M, float *partial, float *dW, float *db, void *stream)
+{
+    if (!du || !dc || !x || !pos4 || !qpos4 || !partial || !dW || !db || P <= 0 || M <= 0) return SN2_EINVAL;
+    return launch_w1<T2C, T2F>(du, dc, x, pos4, qpos4, P, (long long)M, partial, dW, db, (cudaStream_t)stream);
 }

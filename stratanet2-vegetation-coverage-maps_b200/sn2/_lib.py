@@ -70,6 +70,12 @@ SIGNATURES = {
     "sn2_sa1t_bwd_sums": [_vp, _vp, _vp, _i, _vp, _vp],
     "sn2_sa1t_bwd_w2": [_vp, _vp, _vp, _vp, _i] + [_vp] * 17,
     "sn2_sa1t_bwd_in": [_vp, _vp, _vp, _vp, _ll, _i] + [_vp] * 17,
+    "sn2_sa2t_pre": [_vp, _vp, _ll, _vp, _vp, _vp],
+    "sn2_sa2t_fwd": [_vp, _vp, _vp, _vp, _i] + [_vp] * 8,
+    "sn2_sa2t_finish": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "sn2_sa2t_bwd_sums": [_vp, _vp, _vp, _i, _vp, _vp],
+    "sn2_sa2t_bwd": [_vp, _vp, _vp, _vp, _ll, _i] + [_vp] * 12,
+    "sn2_sa2t_bwd_w": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _vp, _vp, _vp, _vp],
     "sn2_sa1t_bwd_w1": [_vp, _vp, _vp, _vp, _vp, _ll, _i, _vp, _vp, _vp, _vp],
     "sn2_head_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp],
     "sn2_pointwise_loss_fwd": [_vp, _vp, _ll, _vp, _vp, _vp],

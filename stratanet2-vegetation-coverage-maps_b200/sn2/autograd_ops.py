@@ -405,6 +405,74 @@ class SA1Recompute(torch.autograd.Function):
         return dfeat, None, None, None, None, dW1, db1, dg1, dbt1, dW2, db2, dg2, dbt2, None, None
 
 
+class SA2Recompute(torch.autograd.Function):
+    """The train-mode sa2 block -- PointConv message, MLP([19,32]) = Linear -> ReLU -> BatchNorm1d with batch
+    statistics, max aggregation -- without per-edge arrays (csrc/train_sa.cu, lane = channel); see SA1Recompute."""
+
+    @staticmethod
+    def supported(seq, x) -> bool:
+        blocks = list(seq)
+        if len(blocks) != 1 or x.shape[1] != 16 or x.dtype != torch.float32:
+            return False
+        layers = list(blocks[0])
+        if len(layers) != 3 or not isinstance(layers[0], torch.nn.Linear) or not isinstance(layers[1], torch.nn.ReLU):
+            return False
+        lin, bn = layers[0], layers[2]
+        if not isinstance(bn, (torch.nn.BatchNorm1d, torch.nn.SyncBatchNorm)):
+            return False
+        return bool(bn.training and bn.affine and bn.momentum is not None and lin.bias is not None
+                    and tuple(lin.weight.shape) == (32, 19))
+
+    @staticmethod
+    def forward(ctx, x, pos4, qpos4, rowptr, col, W, b, g, bt, bn):
+        lib = _lib.load()
+        x, W, b, g = _c(x), _c(W), _c(b), _c(g)
+        P, M, dev, st = x.shape[0], qpos4.shape[0], x.device, stream_ptr()
+        f32 = torch.float32
+        u = torch.empty((P, 32), dtype=f32, device=dev)
+        stats = torch.empty(65, dtype=torch.float64, device=dev)
+        key = torch.empty((M, 32), dtype=f32, device=dev)
+        arg = torch.empty((M, 32), dtype=torch.int32, device=dev)
+        x2 = torch.empty((M, 32), dtype=f32, device=dev)
+        amax = torch.empty((M, 32), dtype=f32, device=dev)
+        queue = torch.empty(4, dtype=torch.int32, device=dev)
+        rp, cp, qp = dptr(rowptr, torch.int32), dptr(col, torch.int32), dptr(qpos4)
+        check(lib.sn2_sa2t_pre(dptr(x, f32), dptr(pos4), P, dptr(W, f32), dptr(u), st), "sn2_sa2t_pre")
+        check(lib.sn2_sa2t_fwd(dptr(u), qp, rp, cp, M, dptr(W), dptr(b, f32), dptr(g, f32), dptr(stats), dptr(key), dptr(arg),
+                               dptr(queue), st), "sn2_sa2t_fwd")
+        ss, group, peer = _bn_stats_to_ss(lib, bn, stats, g, bt, 32, st)
+        check(lib.sn2_sa2t_finish(dptr(key), dptr(arg), dptr(g), dptr(ss), M, dptr(x2), dptr(amax), st), "sn2_sa2t_finish")
+        ops._count(5)
+        ctx.save_for_backward(x, pos4, qpos4, rowptr, col, W, b, g, u, ss, stats, arg, amax)
+        ctx.sync = (group, peer)
+        return x2
+
+    @staticmethod
+    def backward(ctx, dx2):
+        lib = _lib.load()
+        x, pos4, qpos4, rowptr, col, W, b, g, u, ss, stats, arg, amax = ctx.saved_tensors
+        group, peer = ctx.sync
+        P, M, dev, st = x.shape[0], qpos4.shape[0], x.device, stream_ptr()
+        f32 = torch.float32
+        dx2 = _c(dx2)
+        sums = torch.empty(64, dtype=torch.float64, device=dev)
+        partial = torch.empty((int(lib.sn2_sa1t_blocks()), int(lib.sn2_sa1t_partials())), dtype=f32, device=dev)
+        dW, db = torch.empty_like(W), torch.empty_like(b)
+        du = torch.empty((P, 32), dtype=f32, device=dev)
+        dc = torch.empty((M, 32), dtype=f32, device=dev)
+        queue = torch.empty(4, dtype=torch.int32, device=dev)
+        rp, cp, qp = dptr(rowptr, torch.int32), dptr(col, torch.int32), dptr(qpos4)
+        check(lib.sn2_sa2t_bwd_sums(dptr(dx2, f32), dptr(amax), dptr(arg), M, dptr(sums), st), "sn2_sa2t_bwd_sums")
+        dg, dbt = _bn_bwd_sums(lib, sums, ss, 32, group, peer, st)
+        check(lib.sn2_sa2t_bwd(dptr(u), qp, rp, cp, P, M, dptr(W), dptr(b), dptr(g), dptr(ss), dptr(stats), dptr(sums), dptr(dx2),
+                               dptr(arg), dptr(du), dptr(dc), dptr(queue), st), "sn2_sa2t_bwd")
+        check(lib.sn2_sa2t_bwd_w(dptr(du), dptr(dc), dptr(x), dptr(pos4), qp, P, M, dptr(partial), dptr(dW), dptr(db), st),
+              "sn2_sa2t_bwd_w")
+        ops._count(6)
+        dx = du @ W[:, :16] if ctx.needs_input_grad[0] else None
+        return dx, None, None, None, None, dW, db, dg, dbt, None
+
+
 class Head(torch.autograd.Function):
     """relu(lin1) -> lin2 -> softmax(4) x sigmoid(1) of reference model/point_net2.py:141-153 (dropout p = 0) in one
     kernel each way; the backward recomputes the head from its input row, nothing else is saved.

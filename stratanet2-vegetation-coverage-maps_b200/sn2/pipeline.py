@@ -388,7 +388,7 @@ def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num
     backward).  `structure`: a TrainStructure prepared ahead of time (StructurePrefetcher)."""
     import torch.nn.functional as F
 
-    from .autograd_ops import EdgeMsg, Head, Interp3, InterpPlot, SA1Recompute, SegmentMax, run_mlp, tall_linear
+    from .autograd_ops import EdgeMsg, Head, Interp3, InterpPlot, SA1Recompute, SA2Recompute, SegmentMax, run_mlp, tall_linear
 
     invalidate_packed(model)  # running statistics are about to change behind torch's back
     S = structure if structure is not None else TrainStructure(model, xyz, cloud, device, max_num_neighbors, timer)
@@ -409,8 +409,12 @@ def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num
     else:
         y1, ss1 = run_mlp(sa1.conv.local_nn, EdgeMsg.apply(feat0, pos0, pos1, rowptr1, col1, rows1), rows1, defer_last=True)
         x1, _ = SegmentMax.apply(y1, rowptr1, ss1)
-    y2, ss2 = run_mlp(sa2.conv.local_nn, EdgeMsg.apply(x1, pos1, pos2, rowptr2, col2, rows2), rows2, defer_last=True)
-    x2, _ = SegmentMax.apply(y2, rowptr2, ss2)
+    if os.environ.get("SN2_SA_RECOMPUTE", "1") == "1" and SA2Recompute.supported(sa2.conv.local_nn, x1):
+        l1, _, n1 = list(sa2.conv.local_nn[0])
+        x2 = SA2Recompute.apply(x1, pos1, pos2, rowptr2, col2, l1.weight, l1.bias, n1.weight, n1.bias, n1)
+    else:
+        y2, ss2 = run_mlp(sa2.conv.local_nn, EdgeMsg.apply(x1, pos1, pos2, rowptr2, col2, rows2), rows2, defer_last=True)
+        x2, _ = SegmentMax.apply(y2, rowptr2, ss2)
     y3, ss3 = run_mlp(model.sa3_module.nn, torch.cat([x2, pos2[:, :3]], dim=1), defer_last=True)
     g, _ = SegmentMax.apply(y3, plot_ptr, ss3)
     f3 = run_mlp(model.fp3_module.nn, torch.cat([InterpPlot.apply(g, pos2, M2), x2], dim=1))
