@@ -328,7 +328,7 @@ def run_train(opts, cfg, scaling="strong", quick=False):
     from sn2 import comm as sn2_comm
     from sn2 import losses, ops, parallel
     from sn2.optim import FusedAdam
-    from sn2.pipeline import GraphedTrainStep, StageTimer, StructurePrefetcher
+    from sn2.pipeline import GraphedTrainStep, StageTimer, StructurePrefetcher, sa_recompute_allowed
     from sn2.synth import synth_batch
 
     world, rank, local, dev = dist_ctx()
@@ -469,6 +469,9 @@ def run_train(opts, cfg, scaling="strong", quick=False):
                    "overlap": "StructurePrefetcher: FPS / ball query / kNN of batch i+1 on a side stream under step i",
                    "cuda_graph": ("GraphedTrainStep: fwd + loss + bwd + all-reduces + Adam replayed as ONE CUDA graph per rank (edge lists at "
                                   "fixed capacity, live counts on the device)") if use_graph else "off",
+                   "sa_blocks": ("recompute sweeps (csrc/train_sa.cu: no per-edge array is written)" if sa_recompute_allowed(net.sa1_module.conv.local_nn)
+                                 else "materialised messages (edge_msg + fused Linear-ReLU-BatchNorm + segment_max): data-parallel jobs keep "
+                                      "them, the recompute sweeps are not yet verified on > 1 GPU (SN2_SA_RECOMPUTE_DP=1 opts in)"),
                    "parallelism": f"dp{world} by plot"},
         "points_per_s": value * N,
         "collectives": {"backend": mode,

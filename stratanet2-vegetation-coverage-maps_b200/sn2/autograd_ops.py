@@ -365,7 +365,7 @@ class SA1Recompute(torch.autograd.Function):
                                   dptr(g2, f32), dptr(stats2), dptr(key), dptr(arg), dptr(queue), st), "sn2_sa1t_stats2")
         ss2, group2, peer2 = _bn_stats_to_ss(lib, bn2, stats2, g2, bt2, 16, st)
         check(lib.sn2_sa1t_finish(dptr(key), dptr(arg), dptr(g2), dptr(ss2), M, dptr(x1), dptr(amax), st), "sn2_sa1t_finish")
-        ops._count(8)
+        ops._count(10)  # pre; 2 x (stats init, constant image, sweep, BatchNorm finalize); finish
         ctx.save_for_backward(feat, pos4, qpos4, rowptr, col, W1, b1, W2, b2, g2, u, ss1, ss2, stats1, stats2, arg, amax)
         ctx.sync = (group1, peer1, group2, peer2)
         return x1
@@ -400,7 +400,7 @@ class SA1Recompute(torch.autograd.Function):
                                   dptr(du), dptr(dc), dptr(queue), st), "sn2_sa1t_bwd_in")
         check(lib.sn2_sa1t_bwd_w1(dptr(du), dptr(dc), dptr(feat), dptr(pos4), qp, P, M, dptr(partial), dptr(dW1), dptr(db1), st),
               "sn2_sa1t_bwd_w1")
-        ops._count(9)
+        ops._count(10)  # sparse sums, 2 x BatchNorm parameter gradients, 2 x (constant image, sweep), W2 finish, W1 + its reduction
         dfeat = du @ W1[:, :8] if ctx.needs_input_grad[0] else None
         return dfeat, None, None, None, None, dW1, db1, dg1, dbt1, dW2, db2, dg2, dbt2, None, None
 
@@ -468,7 +468,7 @@ class SA2Recompute(torch.autograd.Function):
                                dptr(arg), dptr(du), dptr(dc), dptr(queue), st), "sn2_sa2t_bwd")
         check(lib.sn2_sa2t_bwd_w(dptr(du), dptr(dc), dptr(x), dptr(pos4), qp, P, M, dptr(partial), dptr(dW), dptr(db), st),
               "sn2_sa2t_bwd_w")
-        ops._count(6)
+        ops._count(5)
         dx = du @ W[:, :16] if ctx.needs_input_grad[0] else None
         return dx, None, None, None, None, dW, db, dg, dbt, None
 

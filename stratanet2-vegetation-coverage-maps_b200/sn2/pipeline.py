@@ -375,6 +375,21 @@ class StructurePrefetcher:
             self.drain()
 
 
+def sa_recompute_allowed(seq) -> bool:
+    """Whether the message MLP `seq` of a set-abstraction level may run as the recompute blocks of csrc/train_sa.cu
+    (SA1Recompute / SA2Recompute) instead of EdgeMsg -> LinReluBN -> SegmentMax.  SN2_SA_RECOMPUTE=0 switches them off.
+    Data-parallel jobs (a SyncBatchNorm with a live process group of more than one rank) keep the materialising blocks
+    unless SN2_SA_RECOMPUTE_DP=1: the recompute blocks issue the same collectives, but their first 2-GPU run in round 2
+    did not finish inside the GPU budget that was left and could not be repeated, so that combination is unverified."""
+    from .autograd_ops import _sync_group
+
+    if os.environ.get("SN2_SA_RECOMPUTE", "1") != "1":
+        return False
+    if os.environ.get("SN2_SA_RECOMPUTE_DP", "0") == "1":
+        return True
+    return all(_sync_group(layer) is None for block in seq for layer in block)
+
+
 def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num_neighbors: int = 2000,
                   trace: ForwardTrace | None = None, timer=None, structure: TrainStructure | None = None):
     """Training-mode forward with autograd (reference :106-153 under ``model.train()``).
@@ -401,7 +416,7 @@ def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num
     rows1, rows2 = getattr(S, "rows1", None), getattr(S, "rows2", None)  # device edge counts of fixed-capacity lists
 
     # the last BatchNorm of each message MLP is applied inside the max aggregation (no pass of its own)
-    if os.environ.get("SN2_SA_RECOMPUTE", "1") == "1" and SA1Recompute.supported(sa1.conv.local_nn, feat0):
+    if sa_recompute_allowed(sa1.conv.local_nn) and SA1Recompute.supported(sa1.conv.local_nn, feat0):
         # no per-edge array is written: every sweep recomputes the messages (csrc/train_sa.cu)
         (l1, _, n1), (l2, _, n2) = list(sa1.conv.local_nn[0]), list(sa1.conv.local_nn[1])
         x1 = SA1Recompute.apply(feat0, pos0, pos1, rowptr1, col1, l1.weight, l1.bias, n1.weight, n1.bias,
@@ -409,7 +424,7 @@ def forward_train(model, xyz: torch.Tensor, cloud: torch.Tensor, device, max_num
     else:
         y1, ss1 = run_mlp(sa1.conv.local_nn, EdgeMsg.apply(feat0, pos0, pos1, rowptr1, col1, rows1), rows1, defer_last=True)
         x1, _ = SegmentMax.apply(y1, rowptr1, ss1)
-    if os.environ.get("SN2_SA_RECOMPUTE", "1") == "1" and SA2Recompute.supported(sa2.conv.local_nn, x1):
+    if sa_recompute_allowed(sa2.conv.local_nn) and SA2Recompute.supported(sa2.conv.local_nn, x1):
         l1, _, n1 = list(sa2.conv.local_nn[0])
         x2 = SA2Recompute.apply(x1, pos1, pos2, rowptr2, col2, l1.weight, l1.bias, n1.weight, n1.bias, n1)
     else:

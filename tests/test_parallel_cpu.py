@@ -85,3 +85,43 @@ def test_sync_batchnorm_conversion_keeps_state_dict_keys():
     net = parallel.convert_sync_batchnorm(net)
     assert list(net.state_dict().keys()) == keys
     assert isinstance(net.sa1_module.conv.local_nn[0][2], torch.nn.SyncBatchNorm)
+
+
+def _route_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from model.point_net2 import MLP
+        from sn2.pipeline import sa_recompute_allowed
+
+        plain = MLP([11, 16, 16]).train()
+        sync = torch.nn.SyncBatchNorm.convert_sync_batchnorm(MLP([11, 16, 16])).train()
+        os.environ.pop("SN2_SA_RECOMPUTE", None)
+        os.environ.pop("SN2_SA_RECOMPUTE_DP", None)
+        a, b = sa_recompute_allowed(plain), sa_recompute_allowed(sync)
+        os.environ["SN2_SA_RECOMPUTE_DP"] = "1"
+        c = sa_recompute_allowed(sync)
+        os.environ.pop("SN2_SA_RECOMPUTE_DP")
+        os.environ["SN2_SA_RECOMPUTE"] = "0"
+        d = sa_recompute_allowed(plain)
+        os.environ.pop("SN2_SA_RECOMPUTE")
+        ret[rank] = (a, b, c, d)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_sa_recompute_routing():
+    """sn2.pipeline.sa_recompute_allowed: the recompute SA blocks (csrc/train_sa.cu) serve single-process training; a
+    SyncBatchNorm with a live process group of two ranks keeps the materialising blocks unless SN2_SA_RECOMPUTE_DP=1
+    (that combination was not verified on > 1 GPU in round 2); SN2_SA_RECOMPUTE=0 switches the blocks off."""
+    from model.point_net2 import MLP
+    from sn2.pipeline import sa_recompute_allowed
+
+    # no process group: a SyncBatchNorm module behaves like BatchNorm1d -> allowed
+    assert sa_recompute_allowed(torch.nn.SyncBatchNorm.convert_sync_batchnorm(MLP([19, 32])).train())
+    world, port = 2, _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_route_worker, args=(world, port, ret), nprocs=world, join=True)
+    for rank in range(world):
+        assert ret[rank] == (True, False, True, False), (rank, ret[rank])
