@@ -574,7 +574,10 @@ def test_data_parallel_training_matches_oracle(cuda_device, world, backend):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29731 + world), os.path.join(root, "tests", "dist_train_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env={**os.environ, "SN2_COMM": backend})
+    # SN2_SA_RECOMPUTE=0: the whole check (its single-process reference loops too) runs on the materialising SA blocks, the
+    # configuration that was verified at world 2 / 4 / 8; the recompute sweeps have only run in single-GPU processes so far
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
+                       env={**os.environ, "SN2_COMM": backend, "SN2_SA_RECOMPUTE": "0"})
     assert "DIST_TRAIN_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
     assert f"mode={backend}" in r.stdout, r.stdout[-2000:]
 
