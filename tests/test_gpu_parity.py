@@ -1183,8 +1183,10 @@ def test_graphed_train_step_matches_eager_loop(cuda_device):
             assert torch.equal(v2, v), k
             continue
         diff = (v2 - v).abs()
-        assert float((diff > 4e-4 + 2e-3 * v.abs()).float().mean()) < 5e-3, k
-        assert float(diff.max()) < 2.5e-3 + 2e-3 * float(v.abs().max()), (k, float(diff.max()))
+        # (round 2: the recompute SA blocks add float atomics -- du, the fp64 statistics -- so a few more near-zero
+        # gradients change sign between two runs; bounds widened from 5e-3 / 2.5e-3 after one flaky failure in ~10 runs)
+        assert float((diff > 4e-4 + 2e-3 * v.abs()).float().mean()) < 1e-2, k
+        assert float(diff.max()) < 4.5e-3 + 2e-3 * float(v.abs().max()), (k, float(diff.max()))
 
 
 def test_full_size_training_makes_progress(cuda_device):

@@ -232,3 +232,78 @@ def test_graphed_step_rolls_back_its_warmup():
         for k, v in st.items():
             if torch.is_tensor(v):
                 assert torch.equal(v, old[k]), k
+
+
+def test_sa_recompute_backward_identities():
+    """The algebra behind the recompute SA1 block (csrc/train_sa.cu), checked in float64 against autograd on a small
+    random problem: the dense gradient dz2 from the raw sums of BatchNorm 2; dW2 = G diag(s1) + db2 t1^T with
+    G = dz2^T a1; BatchNorm 1's raw backward sums T1 = W2^T db2 and T2[k] = sum_o W2[o][k] G[o][k] (no reduction sweep
+    of their own); da1 from (cA, cB, cC); and the per-point form of layer 1's weight gradient
+    dW1 = sum_j du_j in_j^T - sum_i dc_i q_i^T."""
+    torch.manual_seed(3)
+    dt = torch.float64
+    P, Q, C, eps = 40, 12, 16, 1e-5
+    deg = torch.randint(1, 9, (Q,))
+    rowptr = torch.zeros(Q + 1, dtype=torch.long)
+    rowptr[1:] = torch.cumsum(deg, 0)
+    E = int(rowptr[-1])
+    row = torch.repeat_interleave(torch.arange(Q), deg)
+    col = torch.randint(0, P, (E,))
+    x = torch.randn(P, 8, dtype=dt)
+    pos, qpos = torch.randn(P, 3, dtype=dt), torch.randn(Q, 3, dtype=dt)
+    W1 = (torch.randn(16, 11, dtype=dt) * 0.4).requires_grad_(True)
+    b1 = (torch.randn(16, dtype=dt) * 0.1).requires_grad_(True)
+    W2 = (torch.randn(16, 16, dtype=dt) * 0.4).requires_grad_(True)
+    b2 = (torch.randn(16, dtype=dt) * 0.1).requires_grad_(True)
+    g1 = (torch.randn(16, dtype=dt) * 0.7 + 0.3).requires_grad_(True)
+    g2 = (torch.randn(16, dtype=dt) * 0.7 + 0.3).requires_grad_(True)
+    bt1 = torch.zeros(16, dtype=dt, requires_grad=True)
+    bt2 = torch.zeros(16, dtype=dt, requires_grad=True)
+    dout = torch.randn(Q, C, dtype=dt)
+
+    def bn(a, g, bt):
+        mean, var = a.mean(0), a.var(0, unbiased=False)
+        inv = 1.0 / torch.sqrt(var + eps)
+        return (a - mean) * inv * g + bt, mean, inv
+
+    msg = torch.cat([x[col], pos[col] - qpos[row]], 1)
+    a1 = torch.relu(msg @ W1.t() + b1)
+    a1.retain_grad()
+    h1, mean1, inv1 = bn(a1, g1, bt1)
+    a2 = torch.relu(h1 @ W2.t() + b2)
+    y2, mean2, inv2 = bn(a2, g2, bt2)
+    out = torch.stack([y2[rowptr[i]:rowptr[i + 1]].max(0).values for i in range(Q)])
+    arg = torch.stack([y2[rowptr[i]:rowptr[i + 1]].argmax(0) + rowptr[i] for i in range(Q)])
+    (out * dout).sum().backward()
+
+    with torch.no_grad():
+        n = float(E)
+
+        def coeff(g, mean, inv, S1, S2):  # dy = mask * (cA dz + cB y + cC), as bn_bwd_coeff
+            sc = g * inv
+            m1, m2 = S1 / n, inv * (S2 - mean * S1) / n
+            kb = -inv * m2
+            return sc, sc * kb, sc * (-m1 - mean * kb)
+
+        dz = torch.zeros(E, C, dtype=dt)
+        dz[arg, torch.arange(C).expand(Q, C)] = dout          # sparse upstream gradient
+        amax = a2[arg, torch.arange(C).expand(Q, C)]
+        S1, S2 = dout.sum(0), (dout * amax).sum(0)             # B0
+        assert torch.allclose(g2.grad, inv2 * (S2 - mean2 * S1)) and torch.allclose(bt2.grad, S1)
+        cA, cB, cC = coeff(g2, mean2, inv2, S1, S2)
+        dz2 = (a2 > 0) * (cA * dz + cB * a2 + cC)              # B1, per edge
+        G, db2 = dz2.t() @ a1, dz2.sum(0)
+        s1, t1 = g1 * inv1, bt1 - mean1 * g1 * inv1
+        assert torch.allclose(W2.grad, G * s1 + db2[:, None] * t1[None, :])
+        assert torch.allclose(b2.grad, db2)
+        T1, T2 = W2.t() @ db2, (W2 * G).sum(0)
+        assert torch.allclose(bt1.grad, T1) and torch.allclose(g1.grad, inv1 * (T2 - mean1 * T1))
+        cA, cB, cC = coeff(g1, mean1, inv1, T1, T2)
+        da1 = cA * (dz2 @ W2) + cB * a1 + cC                   # B2, per edge (before relu')
+        assert torch.allclose(a1.grad, da1)
+        dz1 = (a1 > 0) * da1
+        du = torch.zeros(P, C, dtype=dt).index_add_(0, col, dz1)
+        dc = torch.zeros(Q, C, dtype=dt).index_add_(0, row, dz1)
+        dW1 = du.t() @ torch.cat([x, pos], 1)
+        dW1[:, 8:] -= dc.t() @ qpos
+        assert torch.allclose(W1.grad, dW1) and torch.allclose(b1.grad, du.sum(0))
