@@ -22,8 +22,8 @@ summarise r2_full_cfg2 $O/r2_ncu_traffic_cfg2.json
 $B2 > $O/ncu_plain_b.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:sa1_tc_kernel -c 2 -f -o $O/r2_full_sa1tc $B2 > $O/ncu_full_b.log 2>&1
 summarise r2_full_sa1tc
 $T > $O/ncu_plain_t.log 2>&1 && ncu --set full --clock-control none --import-source on \
-   -k regex:"lrb_bwd_kernel|lrb_fwd_kernel|lrb_bwd_reduce|lrb_small|edge_msg_fwd|head_|segment_max_fwd|adam_|pointwise|kde_lut|bn_finalize" \
-   -c 40 -f -o $O/r2_full_train $T > $O/ncu_full_t.log 2>&1
+   -k regex:"lrb_bwd_kernel|lrb_fwd_kernel|lrb_bwd_reduce|lrb_small|edge_msg_fwd|head_|segment_max_fwd|adam_|pointwise|kde_lut|bn_finalize|sa1t_|sa2t_|sa_t_" \
+   -c 60 -f -o $O/r2_full_train $T > $O/ncu_full_t.log 2>&1
 summarise r2_full_train
 $P > $O/ncu_plain_p.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"extract_plots|pgrid|finalize_bands|hardveg" -c 7 -f -o $O/r2_full_parcel $P > $O/ncu_full_p.log 2>&1
 summarise r2_full_parcel
