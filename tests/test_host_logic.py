@@ -307,3 +307,41 @@ def test_sa_recompute_backward_identities():
         dW1 = du.t() @ torch.cat([x, pos], 1)
         dW1[:, 8:] -= dc.t() @ qpos
         assert torch.allclose(W1.grad, dW1) and torch.allclose(b1.grad, du.sum(0))
+
+
+def test_ctypes_signatures_mirror_the_header():
+    """Every prototype of include/sn2.h against sn2._lib.SIGNATURES, argument by argument: pointers -> c_void_p, int ->
+    c_int, long long -> c_longlong, float -> c_float (a drifted binding would pass garbage through the C ABI)."""
+    hdr = open(os.path.join(ROOT, "include", "sn2.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", " ", hdr)
+    protos = re.findall(r"\b(?:int|const char \*|size_t|unsigned(?: int)?)\s*\*?\s*(sn2_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr)
+    assert len(protos) == len(_lib.SIGNATURES), (len(protos), len(_lib.SIGNATURES))
+    kind = {ctypes.c_void_p: "ptr", ctypes.c_int: "int", ctypes.c_longlong: "ll", ctypes.c_float: "float",
+            ctypes.c_uint: "uint", ctypes.c_ulonglong: "ull", ctypes.c_size_t: "size", ctypes.c_double: "double"}
+    for name, params in protos:
+        params = " ".join(params.split())
+        want = []
+        if params not in ("", "void"):
+            for p in params.split(","):
+                p = p.strip()
+                if "*" in p:
+                    want.append("ptr")
+                elif re.match(r"(const )?long long\b", p):
+                    want.append("ll")
+                elif re.match(r"(const )?unsigned long long\b", p):
+                    want.append("ull")
+                elif re.match(r"(const )?size_t\b", p):
+                    want.append("size")
+                elif re.match(r"(const )?unsigned\b", p):
+                    want.append("uint")
+                elif re.match(r"(const )?float\b", p):
+                    want.append("float")
+                elif re.match(r"(const )?double\b", p):
+                    want.append("double")
+                elif re.match(r"(const )?int\b", p):
+                    want.append("int")
+                else:
+                    raise AssertionError(f"{name}: unrecognised parameter '{p}'")
+        got = [kind[t] for t in _lib.SIGNATURES[name]]
+        assert got == want, f"{name}: header {want} vs binding {got}"
